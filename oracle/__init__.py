@@ -1,0 +1,194 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes front end of the CPU oracle.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and the CPU legs of ``bench.py`` may import
+this package.  ``fringe_b200`` never does: the product path has no CPU fallback.
+
+Two builds of the same loop text (``oracle/loops.hpp``) exist:
+
+* ``load("port")``      -> ``oracle/liboracle.so``; per-pair / per-matrix workers restated in
+  ``oracle/restated.hpp`` (each function cites the reference file:line it follows).
+* ``load("reference")`` -> ``oracle/_ref/libfringe_ref.so``; workers are the reference's own
+  ``KS2sample.hpp`` / ``AD2unique.hpp`` / ``ulongmask.hpp`` / ``EigenLapack.hpp`` compiled in
+  place from ``/root/reference`` (built in the authoring container only; the ``.so`` travels).
+
+``load()`` prefers the reference build when it is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PATHS = {
+    "port": os.path.join(_HERE, "liboracle.so"),
+    "reference": os.path.join(_HERE, "_ref", "libfringe_ref.so"),
+}
+KS2, AD2 = 0, 1
+EVD, MLE, STBAS = 0, 1, 2
+VARIANT_EVD, VARIANT_PHASE_LINK = 0, 1
+
+
+def build(ref: bool | None = None) -> None:
+    """Compile the oracle (and, where /root/reference exists, the reference-header build)."""
+    subprocess.check_call(["make", "-s", "-C", _HERE, "all"])
+    if ref is None:
+        ref = os.path.isdir("/root/reference")
+    if ref:
+        subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+
+
+def nulong(Nx: int, Ny: int) -> int:
+    return int(np.ceil(((2 * Ny + 1) * (2 * Nx + 1)) / 32.0))
+
+
+class Oracle:
+    def __init__(self, path: str):
+        os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")   # as src/evd/evd.py:43
+        self.lib = lib = C.CDLL(path)
+        fp = C.POINTER(C.c_float)
+        dp = C.POINTER(C.c_double)
+        u8 = C.POINTER(C.c_uint8)
+        u32 = C.POINTER(C.c_uint32)
+        i32 = C.POINTER(C.c_int32)
+        lib.oracle_kind.restype = C.c_char_p
+        lib.oracle_max_threads.restype = C.c_int
+        lib.oracle_set_threads.argtypes = [C.c_int]
+        lib.oracle_ks2_prob.restype = C.c_double
+        lib.oracle_ks2_prob.argtypes = [fp, fp, C.c_int]
+        lib.oracle_kolmogorov_prob.restype = C.c_double
+        lib.oracle_kolmogorov_prob.argtypes = [C.c_double]
+        lib.oracle_ad2_prob.restype = C.c_double
+        lib.oracle_ad2_prob.argtypes = [fp, fp, C.c_int]
+        lib.oracle_ad2_sigma.restype = C.c_double
+        lib.oracle_ad2_sigma.argtypes = [C.c_int]
+        lib.oracle_ad2_pvalue_of_stat.restype = C.c_double
+        lib.oracle_ad2_pvalue_of_stat.argtypes = [C.c_double, C.c_int]
+        lib.oracle_mask_setbit.argtypes = [u32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        lib.oracle_mask_getbit.argtypes = [u32, C.c_int, C.c_int, C.c_int, C.c_int]
+        lib.oracle_eig_extreme.argtypes = [dp, C.c_int, C.c_int, C.c_int, dp, dp]
+        lib.oracle_pd_inverse.argtypes = [dp, C.c_int]
+        lib.oracle_nmap_block.argtypes = [fp, u8, dp] + [C.c_int] * 6 + [C.c_double, i32, u32, fp]
+        lib.oracle_evd_block.argtypes = [fp, u32] + [C.c_int] * 12 + [fp, fp, fp, i32]
+        self.kind = lib.oracle_kind().decode()
+
+    # -- helpers -------------------------------------------------------------------
+    @staticmethod
+    def _p(a, ty):
+        return None if a is None else a.ctypes.data_as(C.POINTER(ty))
+
+    def threads(self) -> int:
+        return int(self.lib.oracle_max_threads())
+
+    def set_threads(self, n: int) -> None:
+        self.lib.oracle_set_threads(int(n))
+
+    # -- single tests --------------------------------------------------------------
+    def ks2_prob(self, a, b) -> float:
+        a = np.ascontiguousarray(a, np.float32)
+        b = np.ascontiguousarray(b, np.float32)
+        return float(self.lib.oracle_ks2_prob(self._p(a, C.c_float), self._p(b, C.c_float), a.size))
+
+    def kolmogorov_prob(self, z: float) -> float:
+        return float(self.lib.oracle_kolmogorov_prob(float(z)))
+
+    def ad2_prob(self, a, b) -> float:
+        a = np.ascontiguousarray(a, np.float32)
+        b = np.ascontiguousarray(b, np.float32)
+        return float(self.lib.oracle_ad2_prob(self._p(a, C.c_float), self._p(b, C.c_float), a.size))
+
+    def ad2_sigma(self, n: int) -> float:
+        return float(self.lib.oracle_ad2_sigma(int(n)))
+
+    def ad2_pvalue_of_stat(self, a2: float, n: int) -> float:
+        return float(self.lib.oracle_ad2_pvalue_of_stat(float(a2), int(n)))
+
+    def mask_setbit(self, words, Ny, Nx, dy, dx, on=True):
+        self.lib.oracle_mask_setbit(self._p(words, C.c_uint32), Ny, Nx, dy, dx, int(on))
+
+    def mask_getbit(self, words, Ny, Nx, dy, dx) -> bool:
+        return bool(self.lib.oracle_mask_getbit(self._p(words, C.c_uint32), Ny, Nx, dy, dx))
+
+    def eig_extreme(self, A, largest=True, want_vec=True):
+        """A: (n,n) Hermitian complex128 (upper triangle is what LAPACK reads)."""
+        A = np.array(A, dtype=np.complex128)
+        n = A.shape[0]
+        buf = np.asfortranarray(A).copy(order="F")
+        val = np.zeros(1)
+        vec = np.zeros(n, np.complex128)
+        info = self.lib.oracle_eig_extreme(self._p(buf, C.c_double), n, int(largest), int(want_vec),
+                                           self._p(val, C.c_double), self._p(vec, C.c_double))
+        return info, float(val[0]), vec
+
+    def pd_inverse(self, A):
+        buf = np.asfortranarray(np.array(A, dtype=np.complex128)).copy(order="F")
+        info = self.lib.oracle_pd_inverse(self._p(buf, C.c_double), buf.shape[0])
+        return info, np.array(buf)
+
+    # -- block drivers -------------------------------------------------------------
+    def nmap_block(self, slc, Nx, Ny, method=KS2, thresh=0.05, mask=None, alpha=None,
+                   want_amp=False):
+        """slc: (bands, lines, cols) complex64 -> count (lines, cols) int32,
+        wts (lines, cols, nulong) uint32 [, sorted amplitudes (lines, cols, bands)]."""
+        slc = np.ascontiguousarray(slc, np.complex64)
+        bands, lines, cols = slc.shape
+        nu = nulong(Nx, Ny)
+        count = np.zeros((lines, cols), np.int32)
+        wts = np.zeros((lines, cols, nu), np.uint32)
+        amp = np.zeros((lines, cols, bands), np.float32) if want_amp else None
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, np.uint8)
+        if alpha is not None:
+            alpha = np.ascontiguousarray(alpha, np.float64)
+        rc = self.lib.oracle_nmap_block(self._p(slc, C.c_float), self._p(mask, C.c_uint8),
+                                        self._p(alpha, C.c_double), cols, lines, bands, Nx, Ny,
+                                        int(method), float(thresh), self._p(count, C.c_int32),
+                                        self._p(wts, C.c_uint32), self._p(amp, C.c_float))
+        if rc != 0:
+            raise RuntimeError(f"oracle_nmap_block rc={rc}")
+        return (count, wts, amp) if want_amp else (count, wts)
+
+    def evd_block(self, slc, wts, Nx, Ny, method=EVD, bandwidth=-1, mini_stack_count=1,
+                  variant=VARIANT_EVD, min_neighbors=2, first_line=0, n_lines=None,
+                  want_npix=False):
+        """slc: (bands, lines, cols) complex64; wts (lines, cols, nulong) uint32 ->
+        out (bands, lines, cols) complex64, tcorr (lines, cols) f32, comp (lines, cols) c64."""
+        slc = np.ascontiguousarray(slc, np.complex64)
+        wts = np.ascontiguousarray(wts, np.uint32)
+        bands, lines, cols = slc.shape
+        if n_lines is None:
+            n_lines = lines - first_line
+        out = np.zeros((bands, lines, cols), np.complex64)
+        tcorr = np.zeros((lines, cols), np.float32)
+        comp = np.zeros((lines, cols), np.complex64)
+        npix = np.zeros((lines, cols), np.int32) if want_npix else None
+        rc = self.lib.oracle_evd_block(self._p(slc, C.c_float), self._p(wts, C.c_uint32), cols, lines,
+                                       bands, Nx, Ny, first_line, n_lines, int(method), int(bandwidth),
+                                       int(mini_stack_count), int(variant), int(min_neighbors),
+                                       self._p(out, C.c_float), self._p(tcorr, C.c_float),
+                                       self._p(comp, C.c_float), self._p(npix, C.c_int32))
+        if rc != 0:
+            raise RuntimeError(f"oracle_evd_block rc={rc}")
+        return (out, tcorr, comp, npix) if want_npix else (out, tcorr, comp)
+
+
+_CACHE: dict[str, Oracle] = {}
+
+
+def available(kind: str) -> bool:
+    return os.path.exists(_PATHS[kind])
+
+
+def load(kind: str | None = None) -> Oracle:
+    if kind is None:
+        kind = "reference" if available("reference") else "port"
+    if kind not in _CACHE:
+        if not available(kind):
+            if kind == "port":
+                build(ref=False)
+            else:
+                raise FileNotFoundError(_PATHS[kind] + " (build with `make -C oracle ref` where /root/reference exists)")
+        _CACHE[kind] = Oracle(_PATHS[kind])
+    return _CACHE[kind]

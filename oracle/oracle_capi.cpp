@@ -1,0 +1,103 @@
+// TEST INFRASTRUCTURE ONLY -- C entry points of the CPU oracle (ctypes-loadable).
+//
+// Compiled twice by oracle/Makefile:
+//   liboracle.so             : workers from oracle/restated.hpp               ("port")
+//   _ref/libfringe_ref.so    : -DORACLE_USE_REFERENCE_HEADERS, workers are the reference's
+//                              own KS2sample.hpp / AD2unique.hpp / ulongmask.hpp /
+//                              EigenLapack.hpp included from /root/reference  ("reference")
+// Nothing in fringe_b200/ links or loads either library.
+#include <cstdio>
+
+#ifdef ORACLE_USE_REFERENCE_HEADERS
+#include <complex>
+#include "KS2sample.hpp"
+#include "AD2unique.hpp"
+#include "fringe/ulongmask.hpp"
+#include "fringe/EigenLapack.hpp"
+struct Impl {
+    typedef KS2sample KS;
+    typedef AD2unique AD;
+    typedef Ulongmask Mask;
+    typedef EVWorker Eig;
+};
+static const char* kKind = "reference";
+static double kprob(double z) { KS2sample t(2); return t.KolmogorovProb(z); }
+static double ad_sigma(int n) { AD2unique t(n); return t.sigmaNorm; }
+static double ad_pvalue(double a2, int n) { AD2unique t(n); return t.PValueADKSamples(a2); }
+#else
+#include "restated.hpp"
+struct Impl {
+    typedef restated::KSTest KS;
+    typedef restated::ADTest AD;
+    typedef restated::WindowMask Mask;
+    typedef restated::EigSolver Eig;
+};
+static const char* kKind = "port";
+static double kprob(double z) { return restated::KSTest::kolmogorov_prob(z); }
+static double ad_sigma(int n) { restated::ADTest t(n); return t.sigma; }
+static double ad_pvalue(double a2, int n) { restated::ADTest t(n); return t.pvalue(a2); }
+#endif
+
+#include "loops.hpp"
+
+extern "C" {
+
+const char* oracle_kind() { return kKind; }
+int oracle_max_threads() { return omp_get_max_threads(); }
+void oracle_set_threads(int n) { omp_set_num_threads(n); }
+
+double oracle_ks2_prob(const float* a, const float* b, int n) {
+    Impl::KS t(n);
+    return t.test(a, b);
+}
+double oracle_kolmogorov_prob(double z) { return kprob(z); }
+double oracle_ad2_prob(const float* a, const float* b, int n) {
+    Impl::AD t(n);
+    return t.test(a, b);
+}
+double oracle_ad2_sigma(int n) { return ad_sigma(n); }
+double oracle_ad2_pvalue_of_stat(double a2, int n) { return ad_pvalue(a2, n); }
+void oracle_mask_setbit(uint32_t* words, int Ny, int Nx, int dy, int dx, int on) {
+    const Impl::Mask m = {Ny, Nx};
+    m.setbit(words, dy, dx, on != 0);
+}
+int oracle_mask_getbit(uint32_t* words, int Ny, int Nx, int dy, int dx) {
+    const Impl::Mask m = {Ny, Nx};
+    return m.getbit(words, dy, dx) ? 1 : 0;
+}
+// which: 0 = smallest, 1 = largest.  A is column-major n x n complex128, destroyed.
+int oracle_eig_extreme(double* A, int n, int which, int want_vec, double* eigval, double* eigvec) {
+    Impl::Eig w;
+    w.prepare(n);
+    std::complex<double>* Ac = reinterpret_cast<std::complex<double>*>(A);
+    const int info = which ? w.largestEigen(Ac, want_vec != 0) : w.smallestEigen(Ac, want_vec != 0);
+    eigval[0] = w.eigval[0];
+    if (want_vec)
+        for (int i = 0; i < n; ++i) { eigvec[2 * i] = w.eigvec[i].real(); eigvec[2 * i + 1] = w.eigvec[i].imag(); }
+    return info;
+}
+int oracle_pd_inverse(double* A, int n) {
+    Impl::Eig w;
+    w.prepare(n);
+    return w.positiveDefiniteInverse(reinterpret_cast<std::complex<double>*>(A));
+}
+
+int oracle_nmap_block(const float* slc, const uint8_t* mask, const double* alpha, int cols, int lines,
+                      int bands, int Nx, int Ny, int method, double thresh, int32_t* count,
+                      uint32_t* wts, float* amp_sorted) {
+    return oracle::nmap_block<Impl>(reinterpret_cast<const oracle::cfloat*>(slc), mask, alpha, cols,
+                                    lines, bands, Nx, Ny, method, thresh, count, wts, amp_sorted);
+}
+
+int oracle_evd_block(const float* slc, const uint32_t* wts, int cols, int lines, int bands, int Nx,
+                     int Ny, int first_line, int n_lines, int method, int bandwidth,
+                     int mini_stack_count, int variant, int min_neighbors, float* out, float* tcorr,
+                     float* comp, int32_t* npix) {
+    return oracle::evd_block<Impl>(reinterpret_cast<const oracle::cfloat*>(slc), wts, cols, lines,
+                                   bands, Nx, Ny, first_line, n_lines, method, bandwidth,
+                                   mini_stack_count, variant, min_neighbors,
+                                   reinterpret_cast<oracle::cfloat*>(out), tcorr,
+                                   reinterpret_cast<oracle::cfloat*>(comp), npix);
+}
+
+}  // extern "C"
