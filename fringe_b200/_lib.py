@@ -1,0 +1,74 @@
+"""ctypes binding of libfringe_b200.so (the C ABI declared in include/fringe_b200.h).
+
+The library is built in-tree by ``fringe_b200.build`` (``__graft_entry__.build()``).  If it is
+missing the import fails loudly: there is no Python or CPU fallback for any compute entry point.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfringe_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "fringe_b200.h")
+
+OK, ERR_METHOD, ERR_ARGUMENT, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_CUDA, ERR_MEMORY = range(7)
+NMAP_KS2, NMAP_AD2 = 0, 1
+EVD_EVD, EVD_MLE, EVD_STBAS = 0, 1, 2
+VARIANT_EVD, VARIANT_PHASE_LINK = 0, 1
+
+
+class FringeError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"fringe_b200 status {status}: {message}")
+        self.status = status
+
+
+def declared_symbols() -> list[str]:
+    """Every function name include/fringe_b200.h declares (used by the ABI export test)."""
+    text = open(HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fringe_[a-z0-9_]+)\s*\(", text)))
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m fringe_b200.build` "
+            "(fringe_b200 has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i, d = C.c_void_p, C.c_int, C.c_double
+    lib.fringe_abi_version.restype = i
+    lib.fringe_device_count.argtypes = [C.POINTER(i)]
+    lib.fringe_create.argtypes = [i, C.POINTER(vp)]
+    lib.fringe_destroy.argtypes = [vp]
+    lib.fringe_last_error.argtypes = [vp]
+    lib.fringe_last_error.restype = C.c_char_p
+    lib.fringe_status_string.argtypes = [i]
+    lib.fringe_status_string.restype = C.c_char_p
+    lib.fringe_synchronize.argtypes = [vp]
+    lib.fringe_launch_count.argtypes = [vp]
+    lib.fringe_launch_count.restype = C.c_int64
+    lib.fringe_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    lib.fringe_host_free.argtypes = [vp]
+    lib.fringe_nulong.argtypes = [i, i]
+    lib.fringe_ks2_critical_count.argtypes = [i, d, C.POINTER(i), C.POINTER(d)]
+    lib.fringe_ad2_critical_sum.argtypes = [i, d, C.POINTER(d)]
+    lib.fringe_ad2_sigma.argtypes = [i, C.POINTER(d)]
+    lib.fringe_evd_max_bands.argtypes = [i, i]
+    nmap_args = [vp, vp, vp, vp, i, i, i, i, i, i, d, vp, vp]
+    lib.fringe_nmap_block.argtypes = nmap_args
+    lib.fringe_nmap_block_device.argtypes = nmap_args + [vp]
+    evd_args = [vp, vp, vp] + [i] * 12 + [vp, vp, vp]
+    lib.fringe_evd_block.argtypes = evd_args
+    lib.fringe_evd_block_device.argtypes = evd_args + [vp]
+    lib.fringe_evd_stats.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.fringe_last_kernel_ms.argtypes = [vp, i, C.POINTER(C.c_float)]
+    lib.fringe_fp32_peak.argtypes = [vp, C.POINTER(d)]
+    for name in declared_symbols():
+        getattr(lib, name)          # AttributeError here = header / library mismatch
+    return lib
+
+
+lib = _load()

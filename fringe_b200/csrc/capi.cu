@@ -1,0 +1,493 @@
+// C ABI of libfringe_b200.so (see include/fringe_b200.h): context, workspaces, host-side
+// threshold arithmetic, and the host / device variants of the two block entry points.
+// There is no CPU fallback anywhere in this file: without a CUDA device every compute entry
+// point returns FRINGE_ERR_NO_DEVICE.
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/fringe_b200.h"
+#include "common.cuh"
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct fringe_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    // workspaces reused across blocks
+    DevBuf amp, valid, zpix, adtab, alpha, stats;
+    DevBuf in_slc, in_mask, in_wts, o_count, o_wts, o_out, o_tcorr, o_comp;
+    // cached AD2 table key
+    int adtab_bands = -1;
+    // CUDA events bracketing the most recent launch of each kernel (on its launching stream)
+    cudaEvent_t ev[FRINGE_KERNEL_COUNT][2] = {};
+    bool ev_valid[FRINGE_KERNEL_COUNT] = {};
+};
+
+namespace {
+
+int fail(fringe_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+int cuda_fail(fringe_ctx* c, cudaError_t e, const char* where) {
+    const int code = (e == cudaErrorMemoryAllocation) ? FRINGE_ERR_MEMORY : FRINGE_ERR_CUDA;
+    return fail(c, code, std::string(where) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                                     \
+    do {                                                             \
+        cudaError_t e__ = (call);                                    \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call);   \
+    } while (0)
+
+// ---- threshold arithmetic (host, double) ------------------------------------------------
+// Kolmogorov distribution series with the constants of src/nmap/KS2sample.hpp:12-19,:42-77.
+double kolmogorov_q(double z) {
+    const double u = std::fabs(z);
+    if (u < 0.2) return 1.0;
+    if (u < 0.755) {
+        const double v = 1.0 / (u * u);
+        return 1 - 2.50662827 * (std::exp(-1.2337005501361697 * v) + std::exp(-11.103304951225528 * v) +
+                                 std::exp(-30.842513753404244 * v)) / u;
+    }
+    if (u < 6.8116) {
+        const double e[4] = {-2, -8, -18, -32};
+        double r[4] = {0, 0, 0, 0};
+        const double v = u * u;
+        const int nj = std::max(1, (int)std::round(3.0 / u));
+        for (int j = 0; j < nj; ++j) r[j] = std::exp(e[j] * v);
+        return 2 * (r[0] - r[1] + r[2] - r[3]);
+    }
+    return 0.0;
+}
+double ks_prob_of_count(int k, int n) {
+    // KS2sample.hpp:139-141 with rdmax = k/N (the reference accumulates k steps of 1/N)
+    const double rn = n;
+    double d = 0.0;
+    const double step = 1.0 / rn;
+    for (int i = 0; i < k; ++i) d += step;
+    return kolmogorov_q(d * std::sqrt(rn * rn / (rn + rn)));
+}
+
+// sigma_N for two samples of equal size, src/nmap/AD2unique.hpp:162-208 (same summation order)
+double ad_sigma(int n) {
+    const int N = 2 * n;
+    const double H = 1.0 / (1.0 * n) + 1.0 / (1.0 * n);
+    double h = 0.0, g = 0.0;
+    if (N < 2000) {
+        std::vector<double> inv(N, 0.0);
+        for (int i = 1; i < N; ++i) { inv[i] = 1.0 / i; h += inv[i]; }
+        for (int i = 1; i < N - 1; ++i) {
+            const double t = inv[N - i];
+            for (int j = i + 1; j < N; ++j) g += t * inv[j];
+        }
+    } else {
+        h = std::log(double(N - 1)) + 0.5772156649015328606065120900824024;
+        g = (M_PI) * (M_PI) / 6.0;
+    }
+    const double k = 2.0, k2 = std::pow(k, 2);
+    const double a = (4 * g - 6) * (k - 1) + (10 - 6 * g) * H;
+    const double b = (2 * g - 4) * k2 + 8 * h * k + (2 * g - 14 * h - 4) * H - 8 * h + 4 * g - 6;
+    const double c = (6 * h + 2 * g - 2) * k2 + (4 * h - 4 * g + 6) * k + (2 * h - 6) * H + 4 * h;
+    const double d = (2 * h + 6) * k2 - 4 * h * k;
+    double s = 0.0;
+    s += a * std::pow(double(N), 3) + b * std::pow(double(N), 2) + c * N + d;
+    s /= (double(N - 1) * double(N - 2) * double(N - 3));
+    return std::sqrt(s);
+}
+// p-value of the standardised statistic, AD2unique.hpp:125-160; knots are column 0 of the
+// reference's table (:9-44), probabilities :47-49.
+double ad_pvalue(double tx) {
+    static const double knot[35] = {
+        -1.1954, -1.1786, -1.166, -1.1407, -1.1253, -1.0777, -1.0489, -0.9978, -0.9417, -0.8981,
+        -0.8598, -0.7258, -0.5966, -0.4572, -0.2966, -0.1009, 0.1571, 0.5357, 1.2255, 1.5262,
+        1.9633, 2.7314, 3.7825, 4.1241, 4.6044, 5.409, 6.4954, 6.8279, 7.2755, 8.1885, 9.3061,
+        9.6132, 10.0989, 10.8825, 11.8537};
+    static const double prob[35] = {
+        .00001, .00005, .0001, .0005, .001, .005, .01, .025, .05, .075, .1, .2, .3, .4, .5, .6, .7,
+        .8, .9, .925, .95, .975, .99, .9925, .995, .9975, .999, .99925, .9995, .99975, .9999,
+        .999925, .99995, .999975, .99999};
+    int i1 = -1;
+    for (int i = 0; i < 35; ++i) { i1 = i - 1; if (tx <= knot[i]) break; }
+    int i2 = i1 + 1;
+    if (i1 < 0) { i1 = 0; i2 = 1; }
+    if (i2 >= 35) { i1 = 33; i2 = 34; }
+    const double lp1 = std::log((1.0 - prob[i1]) / prob[i1]), lp2 = std::log((1.0 - prob[i2]) / prob[i2]);
+    const double lp0 = (lp1 - lp2) * (tx - knot[i2]) / (knot[i1] - knot[i2]) + lp2;
+    return std::exp(lp0) / (1. + std::exp(lp0));
+}
+// AD2unique.hpp:305-348 for equal inner sums S (a-side == b-side, see nmap_kernels.cu)
+double ad_prob_of_sum(double S, int n, double sigma) {
+    double akn2 = 0.0;
+    akn2 = akn2 + S / (n * 1.0);
+    akn2 = akn2 + S / (n * 1.0);
+    akn2 = akn2 / (double)(2 * n);
+    double a2 = akn2 - 1;
+    a2 /= sigma;
+    return ad_pvalue(a2);
+}
+void ad_build_table(int n, std::vector<double>& T) {
+    const int L = 2 * n;
+    T.assign((size_t)(L - 1) * (n + 1), 0.0);
+    for (int j = 0; j < L - 1; ++j) {
+        const double bj = j + 1;
+        for (int u = 0; u <= n; ++u) {
+            const double tmp = (double)n * (double)u;        // |2N*m - N*(j+1)| = N*|2m-(j+1)|
+            T[(size_t)j * (n + 1) + u] = tmp * tmp / (bj * ((double)L - bj));
+        }
+    }
+}
+
+int check_geometry(fringe_ctx* ctx, int cols, int lines, int bands, int Nx, int Ny) {
+    if (!ctx) return FRINGE_ERR_ARGUMENT;
+    if (cols <= 0 || lines <= 0 || bands <= 0 || Nx < 0 || Ny < 0)
+        return fail(ctx, FRINGE_ERR_ARGUMENT, "non-positive geometry");
+    if ((long)fringe_nulong(Nx, Ny) > 32) return fail(ctx, FRINGE_ERR_UNSUPPORTED, "window larger than 1024 pixels");
+    return FRINGE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fringe_abi_version(void) { return FRINGE_ABI_VERSION; }
+
+const char* fringe_status_string(int s) {
+    switch (s) {
+        case FRINGE_OK: return "ok";
+        case FRINGE_ERR_METHOD: return "unknown method";
+        case FRINGE_ERR_ARGUMENT: return "invalid argument";
+        case FRINGE_ERR_UNSUPPORTED: return "unsupported configuration";
+        case FRINGE_ERR_NO_DEVICE: return "no CUDA device (there is no CPU fallback)";
+        case FRINGE_ERR_CUDA: return "CUDA error";
+        case FRINGE_ERR_MEMORY: return "out of memory";
+    }
+    return "unknown status";
+}
+
+int fringe_device_count(int* count) {
+    if (!count) return FRINGE_ERR_ARGUMENT;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { *count = 0; cudaGetLastError(); return FRINGE_ERR_NO_DEVICE; }
+    *count = n;
+    return n > 0 ? FRINGE_OK : FRINGE_ERR_NO_DEVICE;
+}
+
+int fringe_create(int device, fringe_ctx** out) {
+    if (!out) return FRINGE_ERR_ARGUMENT;
+    *out = nullptr;
+    int n = 0;
+    if (fringe_device_count(&n) != FRINGE_OK || device < 0 || device >= n) return FRINGE_ERR_NO_DEVICE;
+    if (cudaSetDevice(device) != cudaSuccess) return FRINGE_ERR_CUDA;
+    fringe_ctx* c = new fringe_ctx();
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return FRINGE_ERR_CUDA; }
+    for (int k = 0; k < FRINGE_KERNEL_COUNT; ++k)
+        for (int j = 0; j < 2; ++j) cudaEventCreate(&c->ev[k][j]);
+    *out = c;
+    return FRINGE_OK;
+}
+
+int fringe_destroy(fringe_ctx* c) {
+    if (!c) return FRINGE_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf* all[] = {&c->amp, &c->valid, &c->zpix, &c->adtab, &c->alpha, &c->stats, &c->in_slc, &c->in_mask,
+                     &c->in_wts, &c->o_count, &c->o_wts, &c->o_out, &c->o_tcorr, &c->o_comp};
+    for (DevBuf* b : all) b->release();
+    for (int k = 0; k < FRINGE_KERNEL_COUNT; ++k)
+        for (int j = 0; j < 2; ++j) if (c->ev[k][j]) cudaEventDestroy(c->ev[k][j]);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return FRINGE_OK;
+}
+
+const char* fringe_last_error(const fringe_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int fringe_synchronize(fringe_ctx* ctx) {
+    if (!ctx) return FRINGE_ERR_ARGUMENT;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return FRINGE_OK;
+}
+
+int64_t fringe_launch_count(const fringe_ctx* c) { return c ? c->launches : 0; }
+
+int fringe_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return FRINGE_ERR_ARGUMENT;
+    cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); *ptr = nullptr; return e == cudaErrorMemoryAllocation ? FRINGE_ERR_MEMORY : FRINGE_ERR_NO_DEVICE; }
+    return FRINGE_OK;
+}
+int fringe_host_free(void* ptr) {
+    if (!ptr) return FRINGE_OK;
+    return cudaFreeHost(ptr) == cudaSuccess ? FRINGE_OK : FRINGE_ERR_CUDA;
+}
+
+int fringe_nulong(int Nx, int Ny) { return ((2 * Ny + 1) * (2 * Nx + 1) + 31) / 32; }
+
+int fringe_ks2_critical_count(int bands, double pvalue, int* kcrit, double* margin) {
+    if (bands <= 0 || !kcrit) return FRINGE_ERR_ARGUMENT;
+    int k = -1;
+    for (int i = 0; i <= bands; ++i) {
+        if (ks_prob_of_count(i, bands) >= pvalue) k = i; else break;
+    }
+    *kcrit = k;
+    if (margin) {
+        double m = DBL_MAX;
+        if (k >= 0) m = std::min(m, std::fabs(ks_prob_of_count(k, bands) - pvalue));
+        if (k < bands) m = std::min(m, std::fabs(ks_prob_of_count(k + 1, bands) - pvalue));
+        *margin = m;
+    }
+    return FRINGE_OK;
+}
+
+int fringe_ad2_sigma(int bands, double* sigma) {
+    if (bands < 2 || !sigma) return FRINGE_ERR_ARGUMENT;
+    *sigma = ad_sigma(bands);
+    return FRINGE_OK;
+}
+
+int fringe_ad2_critical_sum(int bands, double pvalue, double* scrit) {
+    if (bands < 2 || !scrit) return FRINGE_ERR_ARGUMENT;
+    const double sg = ad_sigma(bands);
+    if (!(ad_prob_of_sum(0.0, bands, sg) >= pvalue)) { *scrit = -1.0; return FRINGE_OK; }
+    if (ad_prob_of_sum(DBL_MAX, bands, sg) >= pvalue) { *scrit = DBL_MAX; return FRINGE_OK; }
+    // bisection over the (ordered) bit patterns of non-negative doubles
+    uint64_t lo = 0, hi;
+    double dmax = DBL_MAX;
+    std::memcpy(&hi, &dmax, 8);
+    while (hi - lo > 1) {
+        const uint64_t mid = lo + (hi - lo) / 2;
+        double s;
+        std::memcpy(&s, &mid, 8);
+        if (ad_prob_of_sum(s, bands, sg) >= pvalue) lo = mid; else hi = mid;
+    }
+    std::memcpy(scrit, &lo, 8);
+    return FRINGE_OK;
+}
+
+int fringe_evd_max_bands(int method, int variant) { return fringe::evd_max_bands(method, variant); }
+
+// ---------------------------------------------------------------------------------------
+// nmap
+// ---------------------------------------------------------------------------------------
+int fringe_nmap_block_device(fringe_ctx* ctx, const float* slc, const uint8_t* mask, const double* alpha,
+                             int cols, int lines, int bands, int Nx, int Ny, int method, double pvalue,
+                             int32_t* count, uint32_t* wts, void* stream) {
+    int rc = check_geometry(ctx, cols, lines, bands, Nx, Ny);
+    if (rc) return rc;
+    if (method != FRINGE_NMAP_KS2 && method != FRINGE_NMAP_AD2) return fail(ctx, FRINGE_ERR_METHOD, "method must be KS2 or AD2");
+    if (!slc || !count || !wts) return fail(ctx, FRINGE_ERR_ARGUMENT, "null pointer");
+    if (method == FRINGE_NMAP_AD2 && bands < 2) return fail(ctx, FRINGE_ERR_UNSUPPORTED, "AD2 needs >= 2 bands");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    const size_t npix = (size_t)cols * lines;
+
+    fringe::NmapGeometry g;
+    if (!fringe::nmap_plan(bands, Nx, Ny, method, &g))
+        return fail(ctx, FRINGE_ERR_UNSUPPORTED, "bands x window too large for the shared-memory tile");
+
+    int kcrit = 0;
+    double scrit = 0.0;
+    if (method == FRINGE_NMAP_KS2) {
+        fringe_ks2_critical_count(bands, pvalue, &kcrit, nullptr);
+    } else {
+        fringe_ad2_critical_sum(bands, pvalue, &scrit);
+        if (ctx->adtab_bands != bands) {
+            std::vector<double> T;
+            ad_build_table(bands, T);
+            CU(ctx->adtab.ensure(T.size() * sizeof(double)));
+            CU(cudaMemcpyAsync(ctx->adtab.p, T.data(), T.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+            CU(cudaStreamSynchronize(st));     // T is a local
+            ctx->adtab_bands = bands;
+        }
+    }
+    CU(ctx->amp.ensure(npix * bands * sizeof(float)));
+    CU(ctx->valid.ensure(npix));
+    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_AMP_SORT][0], st));
+    CU(fringe::launch_amp_sort((const float2*)slc, mask, alpha, cols, lines, bands, (float*)ctx->amp.p,
+                               (uint8_t*)ctx->valid.p, st));
+    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_AMP_SORT][1], st));
+    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_NMAP][0], st));
+    CU(fringe::launch_nmap((const float*)ctx->amp.p, (const uint8_t*)ctx->valid.p, cols, lines, bands, Nx, Ny,
+                           method, kcrit, scrit, (const double*)ctx->adtab.p, g, count, wts, st));
+    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_NMAP][1], st));
+    ctx->ev_valid[FRINGE_KERNEL_AMP_SORT] = ctx->ev_valid[FRINGE_KERNEL_NMAP] = true;
+    ctx->launches += 2;
+    return FRINGE_OK;
+}
+
+int fringe_nmap_block(fringe_ctx* ctx, const float* slc, const uint8_t* mask, const double* alpha, int cols,
+                      int lines, int bands, int Nx, int Ny, int method, double pvalue, int32_t* count,
+                      uint32_t* wts) {
+    int rc = check_geometry(ctx, cols, lines, bands, Nx, Ny);
+    if (rc) return rc;
+    if (!slc || !count || !wts) return fail(ctx, FRINGE_ERR_ARGUMENT, "null pointer");
+    CU(cudaSetDevice(ctx->device));
+    const size_t npix = (size_t)cols * lines;
+    const int nu = fringe_nulong(Nx, Ny);
+    cudaStream_t st = ctx->stream;
+    CU(ctx->in_slc.ensure(npix * bands * sizeof(float2)));
+    CU(ctx->o_count.ensure(npix * sizeof(int32_t)));
+    CU(ctx->o_wts.ensure(npix * nu * sizeof(uint32_t)));
+    CU(cudaMemcpyAsync(ctx->in_slc.p, slc, npix * bands * sizeof(float2), cudaMemcpyHostToDevice, st));
+    const uint8_t* dmask = nullptr;
+    if (mask) {
+        CU(ctx->in_mask.ensure(npix));
+        CU(cudaMemcpyAsync(ctx->in_mask.p, mask, npix, cudaMemcpyHostToDevice, st));
+        dmask = (const uint8_t*)ctx->in_mask.p;
+    }
+    const double* dalpha = nullptr;
+    if (alpha) {
+        CU(ctx->alpha.ensure(bands * sizeof(double)));
+        CU(cudaMemcpyAsync(ctx->alpha.p, alpha, bands * sizeof(double), cudaMemcpyHostToDevice, st));
+        dalpha = (const double*)ctx->alpha.p;
+    }
+    rc = fringe_nmap_block_device(ctx, (const float*)ctx->in_slc.p, dmask, dalpha, cols, lines, bands, Nx, Ny,
+                                  method, pvalue, (int32_t*)ctx->o_count.p, (uint32_t*)ctx->o_wts.p, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(count, ctx->o_count.p, npix * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(wts, ctx->o_wts.p, npix * nu * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return FRINGE_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// evd / phase_link
+// ---------------------------------------------------------------------------------------
+static int check_evd(fringe_ctx* ctx, int cols, int lines, int bands, int Nx, int Ny, int first_line,
+                     int n_lines, int method, int bandwidth, int mini_stack_count, int variant) {
+    int rc = check_geometry(ctx, cols, lines, bands, Nx, Ny);
+    if (rc) return rc;
+    if (method != FRINGE_EVD_EVD && method != FRINGE_EVD_MLE && method != FRINGE_EVD_STBAS)
+        return fail(ctx, FRINGE_ERR_METHOD, "method must be EVD, MLE or STBAS");
+    if (variant != FRINGE_VARIANT_EVD && variant != FRINGE_VARIANT_PHASE_LINK)
+        return fail(ctx, FRINGE_ERR_ARGUMENT, "unknown variant");
+    if (first_line < 0 || n_lines < 0 || first_line + n_lines > lines)
+        return fail(ctx, FRINGE_ERR_ARGUMENT, "line range outside block");
+    if (mini_stack_count < 1 || mini_stack_count > bands)
+        return fail(ctx, FRINGE_ERR_ARGUMENT, "miniStackCount outside [1, bands]");
+    if (method == FRINGE_EVD_STBAS && (bandwidth <= 0 || bandwidth >= bands - 1))
+        return fail(ctx, FRINGE_ERR_ARGUMENT, "STBAS bandwidth must be in (0, bands-1)");   // evd.cpp:74-91
+    if (bands > fringe::evd_max_bands(method, variant))
+        return fail(ctx, FRINGE_ERR_UNSUPPORTED, "too many bands for the evd kernels");
+    return FRINGE_OK;
+}
+
+int fringe_evd_block_device(fringe_ctx* ctx, const float* slc, const uint32_t* wts, int cols, int lines,
+                            int bands, int Nx, int Ny, int first_line, int n_lines, int method, int bandwidth,
+                            int mini_stack_count, int variant, int min_neighbors, float* out, float* tcorr,
+                            float* comp, void* stream) {
+    int rc = check_evd(ctx, cols, lines, bands, Nx, Ny, first_line, n_lines, method, bandwidth, mini_stack_count, variant);
+    if (rc) return rc;
+    if (!slc || !wts || !out || !tcorr || !comp) return fail(ctx, FRINGE_ERR_ARGUMENT, "null pointer");
+    if (n_lines == 0) return FRINGE_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    const size_t npix = (size_t)cols * lines;
+    const int NP = (bands + 1) & ~1;
+    CU(ctx->zpix.ensure(npix * NP * sizeof(float2)));
+    CU(ctx->stats.ensure(4 * sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(ctx->stats.p, 0, 4 * sizeof(unsigned long long), st));
+    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_TRANSPOSE][0], st));
+    CU(fringe::launch_transpose((const float2*)slc, (long)npix, bands, NP, (float2*)ctx->zpix.p, st));
+    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_TRANSPOSE][1], st));
+    fringe::EvdArgs a;
+    a.zpix = (const float2*)ctx->zpix.p; a.slc = (const float2*)slc; a.wts = wts;
+    a.cols = cols; a.lines = lines; a.bands = bands; a.NP = NP;
+    a.Nx = Nx; a.Ny = Ny; a.nulong = fringe_nulong(Nx, Ny);
+    a.first_line = first_line; a.n_lines = n_lines;
+    a.method = method; a.bandwidth = bandwidth; a.mini_stack_count = mini_stack_count;
+    a.variant = variant; a.min_neighbors = min_neighbors;
+    a.out = (float2*)out; a.tcorr = tcorr; a.comp = (float2*)comp;
+    a.stats = (unsigned long long*)ctx->stats.p;
+    int nl = 0;
+    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_EVD][0], st));
+    CU(fringe::launch_evd(a, st, &nl));
+    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_EVD][1], st));
+    ctx->ev_valid[FRINGE_KERNEL_TRANSPOSE] = ctx->ev_valid[FRINGE_KERNEL_EVD] = true;
+    ctx->launches += 1 + nl;
+    return FRINGE_OK;
+}
+
+int fringe_evd_block(fringe_ctx* ctx, const float* slc, const uint32_t* wts, int cols, int lines, int bands,
+                     int Nx, int Ny, int first_line, int n_lines, int method, int bandwidth,
+                     int mini_stack_count, int variant, int min_neighbors, float* out, float* tcorr,
+                     float* comp) {
+    int rc = check_evd(ctx, cols, lines, bands, Nx, Ny, first_line, n_lines, method, bandwidth, mini_stack_count, variant);
+    if (rc) return rc;
+    if (!slc || !wts || !out || !tcorr || !comp) return fail(ctx, FRINGE_ERR_ARGUMENT, "null pointer");
+    if (n_lines == 0) return FRINGE_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t npix = (size_t)cols * lines;
+    const int nu = fringe_nulong(Nx, Ny);
+    CU(ctx->in_slc.ensure(npix * bands * sizeof(float2)));
+    CU(ctx->in_wts.ensure(npix * nu * sizeof(uint32_t)));
+    CU(ctx->o_out.ensure(npix * bands * sizeof(float2)));
+    CU(ctx->o_tcorr.ensure(npix * sizeof(float)));
+    CU(ctx->o_comp.ensure(npix * sizeof(float2)));
+    CU(cudaMemcpyAsync(ctx->in_slc.p, slc, npix * bands * sizeof(float2), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->in_wts.p, wts, npix * nu * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    rc = fringe_evd_block_device(ctx, (const float*)ctx->in_slc.p, (const uint32_t*)ctx->in_wts.p, cols, lines,
+                                 bands, Nx, Ny, first_line, n_lines, method, bandwidth, mini_stack_count,
+                                 variant, min_neighbors, (float*)ctx->o_out.p, (float*)ctx->o_tcorr.p,
+                                 (float*)ctx->o_comp.p, st);
+    if (rc) return rc;
+    const size_t off = (size_t)first_line * cols, cnt = (size_t)n_lines * cols;
+    CU(cudaMemcpy2DAsync((float2*)out + off, npix * sizeof(float2), (float2*)ctx->o_out.p + off,
+                         npix * sizeof(float2), cnt * sizeof(float2), bands, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(tcorr + off, (float*)ctx->o_tcorr.p + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync((float2*)comp + off, (float2*)ctx->o_comp.p + off, cnt * sizeof(float2), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return FRINGE_OK;
+}
+
+int fringe_last_kernel_ms(fringe_ctx* ctx, int kernel, float* ms) {
+    if (!ctx || !ms || kernel < 0 || kernel >= FRINGE_KERNEL_COUNT) return FRINGE_ERR_ARGUMENT;
+    if (!ctx->ev_valid[kernel]) return fail(ctx, FRINGE_ERR_ARGUMENT, "kernel has not been launched on this context");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventSynchronize(ctx->ev[kernel][1]));
+    CU(cudaEventElapsedTime(ms, ctx->ev[kernel][0], ctx->ev[kernel][1]));
+    return FRINGE_OK;
+}
+
+int fringe_fp32_peak(fringe_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) return FRINGE_ERR_ARGUMENT;
+    CU(cudaSetDevice(ctx->device));
+    CU(fringe::measure_fp32_peak(ctx->stream, tflops));
+    return FRINGE_OK;
+}
+
+int fringe_evd_stats(fringe_ctx* ctx, int64_t stats[4]) {
+    if (!ctx || !stats) return FRINGE_ERR_ARGUMENT;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    unsigned long long h[4] = {0, 0, 0, 0};
+    if (ctx->stats.p) CU(cudaMemcpy(h, ctx->stats.p, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 4; ++i) stats[i] = (int64_t)h[i];
+    return FRINGE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,53 @@
+// Shared declarations between the kernel translation units and the C ABI (capi.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fringe {
+
+// ---- nmap_kernels.cu ------------------------------------------------------------------
+// amp   : float [bands][npix]  ascending per valid pixel (rank-major so that the window tile
+//         of one rank is a set of contiguous row segments)
+// valid : uint8 [npix]
+cudaError_t launch_amp_sort(const float2* slc, const uint8_t* mask, const double* alpha, int cols,
+                            int lines, int bands, float* amp, uint8_t* valid, cudaStream_t st);
+
+struct NmapGeometry {
+    int tile_w, tile_h;      // output pixels per CTA
+    size_t smem_bytes;
+    bool table_in_smem;      // AD2 term table staged in shared memory
+};
+// Chooses the CTA tile so that tile+halo of all ranks fits in shared memory.
+// Returns false when even the smallest tile does not fit.
+bool nmap_plan(int bands, int Nx, int Ny, int method, NmapGeometry* g);
+
+cudaError_t launch_nmap(const float* amp, const uint8_t* valid, int cols, int lines, int bands,
+                        int Nx, int Ny, int method, int kcrit, double scrit,
+                        const double* ad_table, const NmapGeometry& g, int32_t* count,
+                        uint32_t* wts, cudaStream_t st);
+
+// ---- evd_kernels.cu -------------------------------------------------------------------
+// band-major planes [bands][npix] -> pixel-major vectors [npix][bands_padded] (zero padded)
+cudaError_t launch_transpose(const float2* slc, long npix, int bands, int bands_padded,
+                             float2* zpix, cudaStream_t st);
+
+struct EvdArgs {
+    const float2* zpix;      // [npix][NP]
+    const float2* slc;       // [bands][npix] (original planes; used for the compressed SLC)
+    const uint32_t* wts;     // [npix][nulong]
+    int cols, lines, bands, NP;
+    int Nx, Ny, nulong;
+    int first_line, n_lines;
+    int method, bandwidth, mini_stack_count, variant, min_neighbors;
+    float2* out;             // [bands][npix]
+    float* tcorr;            // [npix]
+    float2* comp;            // [npix]
+    unsigned long long* stats;   // [4] device counters
+};
+int evd_max_bands(int method, int variant);
+cudaError_t launch_evd(const EvdArgs& a, cudaStream_t st, int* n_launches);
+
+// ---- microbench.cu --------------------------------------------------------------------
+cudaError_t measure_fp32_peak(cudaStream_t st, double* tflops);
+
+}  // namespace fringe

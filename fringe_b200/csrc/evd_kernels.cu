@@ -1,0 +1,764 @@
+// Covariance + eigen-solve kernels (sm_100a), generic-N version.
+//
+// What the reference does per pixel (src/evd/evd.cpp:512-788, src/phase_link/phase_link.cpp:
+// 479-666): gather the SHPs flagged in the pixel's window bitmask, accumulate the Hermitian
+// sample covariance, normalise to a coherence matrix C, then
+//   EVD / STBAS : dominant eigenvector of C (LAPACK zheevr),
+//   MLE         : smallest eigenvector of inv(|C|) o C after two PSD gates (zheevr, zpotrf,
+//                 zpotri), with sentinel codes in the tcorr raster on failure,
+// reference the phases to one band, form the compressed SLC and the temporal coherence.
+//
+// How it is done here: one warp owns one pixel at a time.
+//   * the stack is first re-laid out pixel-major ([pixel][band], k_transpose) so a neighbour's
+//     N samples are one contiguous 8N-byte vector;
+//   * covariance: the N(N+1)/2 upper-triangle entries are dealt round-robin to the 32 lanes
+//     and accumulated in FP32 FMA registers over the SHPs (warp-uniform loop over set bits);
+//   * EVD: FP32 power iteration on the shared-memory coherence matrix with a residual test;
+//   * MLE: FP64 in shared memory -- Cholesky-certified gates, Cholesky inverse of |C|, and a
+//     shifted inverse iteration for the smallest eigenpair whose shift is always certified
+//     below the spectrum by a successful Cholesky factorisation (so it cannot lock onto the
+//     wrong eigenvalue);
+//   * phase reference / compression / temporal coherence are fused behind the solve.
+// Sentinels follow the reference: -2/-4 gate failures, -5 inverse failure, -6 solver
+// failure, -7 eigenvalue below 1e-6 (evd.cpp:608-725); phase_link falls back to EVD instead.
+#include <math_constants.h>
+
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace fringe {
+
+// ======================================================================================
+// re-layout: [bands][npix] -> [npix][NP]
+// ======================================================================================
+__global__ void __launch_bounds__(256) k_transpose(const float2* __restrict__ slc, long npix,
+                                                   int bands, int NP, float2* __restrict__ zpix) {
+    extern __shared__ float2 s_t[];                 // [32][NP+1]
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const long p0 = (long)blockIdx.x * 32;
+    const int pitch = NP + 1;
+    for (int b = ty; b < NP; b += 8) {
+        float2 v = make_float2(0.f, 0.f);
+        if (b < bands && p0 + tx < npix) v = __ldg(&slc[(long)b * npix + p0 + tx]);
+        s_t[tx * pitch + b] = v;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 32 * NP; idx += 256) {
+        const int pp = idx / NP, b = idx - pp * NP;
+        if (p0 + pp < npix) zpix[(p0 + pp) * NP + b] = s_t[pp * pitch + b];
+    }
+}
+
+cudaError_t launch_transpose(const float2* slc, long npix, int bands, int NP, float2* zpix,
+                             cudaStream_t st) {
+    const size_t smem = (size_t)32 * (NP + 1) * sizeof(float2);
+    cudaError_t e = cudaFuncSetAttribute(k_transpose, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return e;
+    k_transpose<<<(unsigned)((npix + 31) / 32), 256, smem, st>>>(slc, npix, bands, NP, zpix);
+    return cudaGetLastError();
+}
+
+// ======================================================================================
+// warp helpers
+// ======================================================================================
+#define FULL 0xffffffffu
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cmulc(double2 a, double2 b) {   // a * conj(b)
+    return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+
+// ======================================================================================
+// FP64 shared-memory linear algebra, one warp per matrix.  Row r is owned by lane r%32.
+// ======================================================================================
+// Lower Cholesky of the Hermitian matrix held in the lower triangle of F (row-major, stride
+// ld), in place; dinv[k] = 1/L[k][k].  Returns false (warp-uniform) on a non-positive pivot,
+// the same failure LAPACK zpotrf reports.
+__device__ bool chol_c(double2* F, double* dinv, int n, int ld, int lane) {
+    for (int k = 0; k < n; ++k) {
+        double2 acc[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = lane + 32 * h;
+            acc[h] = make_double2(0.0, 0.0);
+            if (i >= k && i < n) {
+                double2 s = F[i * ld + k];
+                for (int m = 0; m < k; ++m) {
+                    const double2 t = cmulc(F[i * ld + m], F[k * ld + m]);
+                    s.x -= t.x; s.y -= t.y;
+                }
+                acc[h] = s;
+            }
+        }
+        const double d = __shfl_sync(FULL, (k < 32) ? acc[0].x : acc[1].x, k & 31);
+        if (!(d > 0.0)) return false;
+        const double rs = 1.0 / sqrt(d);
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = lane + 32 * h;
+            if (i > k && i < n) F[i * ld + k] = make_double2(acc[h].x * rs, acc[h].y * rs);
+            if (i == k) { F[i * ld + k] = make_double2(d * rs, 0.0); dinv[k] = rs; }
+        }
+        __syncwarp();
+    }
+    return true;
+}
+
+__device__ bool chol_r(double* A, double* dinv, int n, int ld, int lane) {
+    for (int k = 0; k < n; ++k) {
+        double acc[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = lane + 32 * h;
+            acc[h] = 0.0;
+            if (i >= k && i < n) {
+                double s = A[i * ld + k];
+                for (int m = 0; m < k; ++m) s -= A[i * ld + m] * A[k * ld + m];
+                acc[h] = s;
+            }
+        }
+        const double d = __shfl_sync(FULL, (k < 32) ? acc[0] : acc[1], k & 31);
+        if (!(d > 0.0)) return false;
+        const double rs = 1.0 / sqrt(d);
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = lane + 32 * h;
+            if (i > k && i < n) A[i * ld + k] = acc[h] * rs;
+            if (i == k) { A[i * ld + k] = d * rs; dinv[k] = rs; }
+        }
+        __syncwarp();
+    }
+    return true;
+}
+
+// x <- (L L^H)^-1 x for the factor produced by chol_c; x[h] is element lane+32h.
+__device__ void chol_solve_c(const double2* F, const double* dinv, int n, int ld, int lane,
+                             double2 x[2]) {
+    for (int k = 0; k < n; ++k) {                       // L y = x
+        const int src = k & 31;
+        double2 xk;
+        xk.x = __shfl_sync(FULL, (k < 32) ? x[0].x : x[1].x, src);
+        xk.y = __shfl_sync(FULL, (k < 32) ? x[0].y : x[1].y, src);
+        const double dk = dinv[k];
+        xk.x *= dk; xk.y *= dk;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = lane + 32 * h;
+            if (i == k) x[h] = xk;
+            else if (i > k && i < n) {
+                const double2 t = cmul(F[i * ld + k], xk);
+                x[h].x -= t.x; x[h].y -= t.y;
+            }
+        }
+    }
+    for (int k = n - 1; k >= 0; --k) {                  // L^H z = y
+        const int src = k & 31;
+        double2 xk;
+        xk.x = __shfl_sync(FULL, (k < 32) ? x[0].x : x[1].x, src);
+        xk.y = __shfl_sync(FULL, (k < 32) ? x[0].y : x[1].y, src);
+        const double dk = dinv[k];
+        xk.x *= dk; xk.y *= dk;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = lane + 32 * h;
+            if (i == k) x[h] = xk;
+            else if (i < k) {
+                const double2 l = F[k * ld + i];        // conj(L[k][i]) * xk
+                x[h].x -= l.x * xk.x + l.y * xk.y;
+                x[h].y -= l.x * xk.y - l.y * xk.x;
+            }
+        }
+    }
+}
+
+// A (lower Cholesky factor from chol_r, dinv) -> full symmetric inverse written back to A.
+// X is scratch (n x ld doubles).
+__device__ void chol_inverse_r(double* A, double* X, const double* dinv, int n, int ld, int lane) {
+    // column c of L^-1, one column per lane (private forward substitution)
+    for (int h = 0; h < 2; ++h) {
+        const int c = lane + 32 * h;
+        if (c < n) {
+            for (int i = 0; i < n; ++i) {
+                double s = (i == c) ? 1.0 : 0.0;
+                if (i >= c) {
+                    for (int m = c; m < i; ++m) s -= A[i * ld + m] * X[m * ld + c];
+                    s *= dinv[i];
+                } else s = 0.0;
+                X[i * ld + c] = s;
+            }
+        }
+    }
+    __syncwarp();
+    // inv = X^T X ; row i per lane
+    for (int h = 0; h < 2; ++h) {
+        const int i = lane + 32 * h;
+        if (i < n) {
+            for (int j = 0; j < n; ++j) {
+                double s = 0.0;
+                for (int m = max(i, j); m < n; ++m) s += X[m * ld + i] * X[m * ld + j];
+                A[i * ld + j] = s;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// ======================================================================================
+// the per-pixel kernel
+// ======================================================================================
+struct WarpSmem {
+    float2* C;      // [n][ldc] coherence, FP32, full Hermitian
+    float2* xv;     // [n] broadcast vector
+    float* pw;      // [n] powers
+    double2* Cd;    // [n][ld]  coherence, FP64         (DP only)
+    double* A;      // [n][ld]  |C| -> inverse          (DP only)
+    double2* F;     // [n][ld]  factor / scratch        (DP only)
+    double* dinv;   // [n]                              (DP only)
+    double2* xd;    // [n] broadcast vector             (DP only)
+};
+
+__host__ __device__ inline size_t evd_warp_smem_bytes(int n, bool dp) {
+    const int ldc = n | 1, ld = n | 1;
+    size_t b = (size_t)n * ldc * sizeof(float2) + (size_t)n * sizeof(float2) + (size_t)((n + 3) & ~3) * sizeof(float);
+    b = (b + 15) & ~(size_t)15;
+    if (dp) {
+        b += (size_t)n * ld * sizeof(double) + 2 * (size_t)n * ld * sizeof(double2) +
+             (size_t)n * sizeof(double) + (size_t)n * sizeof(double2);
+        b = (b + 15) & ~(size_t)15;
+    }
+    return b;
+}
+
+__device__ inline WarpSmem carve(unsigned char* base, int n, bool dp) {
+    WarpSmem w;
+    const int ldc = n | 1, ld = n | 1;
+    unsigned char* p = base;
+    w.C = reinterpret_cast<float2*>(p); p += (size_t)n * ldc * sizeof(float2);
+    w.xv = reinterpret_cast<float2*>(p); p += (size_t)n * sizeof(float2);
+    w.pw = reinterpret_cast<float*>(p); p += (size_t)((n + 3) & ~3) * sizeof(float);
+    p = base + (((size_t)(p - base) + 15) & ~(size_t)15);
+    w.A = nullptr; w.F = nullptr; w.dinv = nullptr; w.xd = nullptr; w.Cd = nullptr;
+    if (dp) {
+        w.F = reinterpret_cast<double2*>(p); p += (size_t)n * ld * sizeof(double2);
+        w.Cd = reinterpret_cast<double2*>(p); p += (size_t)n * ld * sizeof(double2);
+        w.xd = reinterpret_cast<double2*>(p); p += (size_t)n * sizeof(double2);
+        w.A = reinterpret_cast<double*>(p); p += (size_t)n * ld * sizeof(double);
+        w.dinv = reinterpret_cast<double*>(p);
+    }
+    return w;
+}
+
+// Dominant eigenpair of the FP32 coherence matrix by power iteration (lane owns rows
+// lane, lane+32).  v[] receives the unit eigenvector; returns the eigenvalue.
+__device__ float power_iteration(const WarpSmem& w, int n, int ldc, int lane, int start_col,
+                                 float2 v[2], int* iters, bool* capped) {
+    float2 x[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int i = lane + 32 * h;
+        x[h] = (i < n) ? w.C[i * ldc + start_col] : make_float2(0.f, 0.f);
+    }
+    float nrm = warp_sum(x[0].x * x[0].x + x[0].y * x[0].y + x[1].x * x[1].x + x[1].y * x[1].y);
+    float sc = rsqrtf(nrm);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) { x[h].x *= sc; x[h].y *= sc; }
+    float lam = 0.f;
+    int it = 0;
+    const int kMaxIter = 3000;
+    const float tol2 = 4.0e-12f;          // (2e-6)^2 relative residual
+    *capped = true;
+    for (; it < kMaxIter; ++it) {
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) { const int i = lane + 32 * h; if (i < n) w.xv[i] = x[h]; }
+        __syncwarp();
+        float2 y[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = lane + 32 * h;
+            float yr = 0.f, yi = 0.f;
+            if (i < n) {
+                const float2* row = w.C + i * ldc;
+                for (int j = 0; j < n; ++j) {
+                    const float2 c = row[j];
+                    const float2 xj = w.xv[j];
+                    yr = fmaf(c.x, xj.x, yr); yr = fmaf(-c.y, xj.y, yr);
+                    yi = fmaf(c.x, xj.y, yi); yi = fmaf(c.y, xj.x, yi);
+                }
+            }
+            y[h] = make_float2(yr, yi);
+        }
+        lam = warp_sum(x[0].x * y[0].x + x[0].y * y[0].y + x[1].x * y[1].x + x[1].y * y[1].y);
+        float r2 = 0.f, n2 = 0.f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float rx = y[h].x - lam * x[h].x, ry = y[h].y - lam * x[h].y;
+            r2 += rx * rx + ry * ry;
+            n2 += y[h].x * y[h].x + y[h].y * y[h].y;
+        }
+        r2 = warp_sum(r2);
+        n2 = warp_sum(n2);
+        sc = rsqrtf(n2);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) { x[h].x = y[h].x * sc; x[h].y = y[h].y * sc; }
+        if (r2 <= tol2 * lam * lam) { *capped = false; ++it; break; }
+    }
+    *iters = it;
+    v[0] = x[0]; v[1] = x[1];
+    return lam;
+}
+
+// Smallest eigenpair of the Hermitian PSD matrix M = Ainv o C (Ainv real symmetric in w.A,
+// C FP64 in w.Cd) by inverse iteration with Cholesky-certified shifts.  Returns false when no
+// positive-definite shifted matrix could be factored (caller maps that to the sentinel / the
+// EVD fallback).  v[] = unit eigenvector (lane rows), *lam = eigenvalue.
+__device__ bool smallest_eigen_mle(const WarpSmem& w, int n, int ldc, int ld, int lane,
+                                   double2 v[2], double* lam) {
+    // scale = max diagonal of M (diag(C) = 1 so diag(M) = diag(Ainv))
+    double dmax = 0.0;
+    for (int h = 0; h < 2; ++h) { const int i = lane + 32 * h; if (i < n) dmax = fmax(dmax, fabs(w.A[i * ld + i])); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(FULL, dmax, o));
+
+    auto assemble = [&](double sigma) {
+        for (int h = 0; h < 2; ++h) {
+            const int i = lane + 32 * h;
+            if (i < n) {
+                for (int j = 0; j <= i; ++j) {
+                    const double2 c = w.Cd[i * ld + j];
+                    const double a = w.A[i * ld + j];
+                    double2 m = make_double2(a * c.x, a * c.y);
+                    if (j == i) { m.x -= sigma; m.y = 0.0; }
+                    w.F[i * ld + j] = m;
+                }
+            }
+        }
+        __syncwarp();
+    };
+    auto matvec = [&](const double2 x[2], double2 y[2]) {      // y = M x
+        __syncwarp();
+        for (int h = 0; h < 2; ++h) { const int i = lane + 32 * h; if (i < n) w.xd[i] = x[h]; }
+        __syncwarp();
+        for (int h = 0; h < 2; ++h) {
+            const int i = lane + 32 * h;
+            double2 s = make_double2(0.0, 0.0);
+            if (i < n) {
+                for (int j = 0; j < n; ++j) {
+                    const double2 c = w.Cd[i * ld + j];
+                    const double a = w.A[i * ld + j];
+                    const double2 xj = w.xd[j];
+                    const double mr = a * c.x, mi = (j == i) ? 0.0 : a * c.y;
+                    s.x += mr * xj.x - mi * xj.y;
+                    s.y += mr * xj.y + mi * xj.x;
+                }
+            }
+            y[h] = s;
+        }
+    };
+
+    // first certified shift: just below zero (M is PSD up to rounding)
+    double sigma = 0.0;
+    bool ok = false;
+    double back = 1e-12 * dmax;
+    for (int attempt = 0; attempt < 6 && !ok; ++attempt) {
+        sigma = -back;
+        assemble(sigma);
+        ok = chol_c(w.F, w.dinv, n, ld, lane);
+        back *= 1e3;
+    }
+    if (!ok) return false;
+    double sigma_ok = sigma;
+
+    double2 x[2];
+    for (int h = 0; h < 2; ++h) {
+        const int i = lane + 32 * h;
+        x[h] = (i < n) ? make_double2(1.0, 0.0) : make_double2(0.0, 0.0);
+    }
+    double rho = 0.0, res = 0.0;
+    int since_shift = 0;
+    for (int it = 0; it < 200; ++it) {
+        chol_solve_c(w.F, w.dinv, n, ld, lane, x);
+        double n2 = warp_sum(x[0].x * x[0].x + x[0].y * x[0].y + x[1].x * x[1].x + x[1].y * x[1].y);
+        const double sc = 1.0 / sqrt(n2);
+        for (int h = 0; h < 2; ++h) { x[h].x *= sc; x[h].y *= sc; }
+        double2 y[2];
+        matvec(x, y);
+        rho = warp_sum(x[0].x * y[0].x + x[0].y * y[0].y + x[1].x * y[1].x + x[1].y * y[1].y);
+        double r2 = 0.0;
+        for (int h = 0; h < 2; ++h) {
+            const double rx = y[h].x - rho * x[h].x, ry = y[h].y - rho * x[h].y;
+            r2 += rx * rx + ry * ry;
+        }
+        res = sqrt(warp_sum(r2));
+        if (res <= 1e-11 * dmax) break;
+        ++since_shift;
+        // propose a tighter shift: some eigenvalue lies within `res` of rho
+        const double prop = rho - 2.0 * res;
+        if (since_shift >= 2 && res > 1e-8 * dmax && prop > sigma_ok + 0.25 * (rho - sigma_ok)) {
+            assemble(prop);
+            if (chol_c(w.F, w.dinv, n, ld, lane)) { sigma_ok = prop; }
+            else {                                  // prop >= lambda_min: bisect back
+                const double mid = 0.5 * (sigma_ok + prop);
+                assemble(mid);
+                if (chol_c(w.F, w.dinv, n, ld, lane)) sigma_ok = mid;
+                else { assemble(sigma_ok); if (!chol_c(w.F, w.dinv, n, ld, lane)) return false; }
+            }
+            since_shift = 0;
+        }
+    }
+    v[0] = x[0]; v[1] = x[1];
+    *lam = rho;
+    return true;
+}
+
+template <int SLOTS, bool DP>
+__global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
+    const int WARPS = blockDim.x >> 5;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int N = a.bands, NP = a.NP;
+    const int ldc = N | 1, ld = N | 1;
+    const WarpSmem w = carve(s_raw + (size_t)warp * evd_warp_smem_bytes(N, DP), N, DP);
+    const long npix_block = (long)a.cols * a.lines;
+
+    // entry -> (ti,tj), ti <= tj, row-major over the upper triangle incl. diagonal
+    const int E = N * (N + 1) / 2;
+    unsigned short eti[SLOTS], etj[SLOTS];
+    {
+        int ti = 0, tj = 0, e = 0;
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            const int target = s * 32 + lane;
+            while (e < target && ti < N) { ++e; if (++tj >= N) { ++ti; tj = ti; } }
+            eti[s] = (target < E) ? ti : 0xffff;
+            etj[s] = (target < E) ? tj : 0xffff;
+        }
+    }
+
+    const int WX = 2 * a.Nx + 1, W = WX * (2 * a.Ny + 1), center = a.Ny * WX + a.Nx;
+    const int k0 = a.mini_stack_count - 1;
+    const bool isstbas = (a.method == 2), ismle = (a.method == 1);
+    const int BW = a.bandwidth;
+
+    const long total = (long)a.n_lines * a.cols;
+    const long chunk = (total + gridDim.x - 1) / gridDim.x;
+    const long beg = (long)blockIdx.x * chunk;
+    const long end = min(total, beg + chunk);
+    unsigned long long st_pix = 0, st_it = 0, st_dp = 0, st_cap = 0;
+
+    for (long i = beg + warp; i < end; i += WARPS) {
+        const long p = (long)a.first_line * a.cols + i;
+        const int ci = (int)(p / a.cols), cj = (int)(p - (long)ci * a.cols);
+        const uint32_t myword = (lane < a.nulong) ? __ldg(&a.wts[p * a.nulong + lane]) : 0u;
+        const uint32_t cword = __shfl_sync(FULL, myword, center >> 5);
+        float tc = 0.f;
+        bool have_vec = false;
+        float2 vf[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+
+        if ((cword >> (center & 31)) & 1u) {
+            // ---------------- covariance accumulation (evd.cpp:537-564) ----------------
+            // FP32 FMA accumulators (EVD/STBAS); the MLE / phase_link instantiation instead
+            // reproduces the reference's arithmetic exactly -- float products rounded term by
+            // term as libgcc's complex multiply does, double accumulation in raster order
+            // (evd.cpp:557-559) -- because inv(|C|) amplifies covariance rounding differences.
+            typedef typename std::conditional<DP, double2, float2>::type acc_t;
+            acc_t acc[SLOTS];
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) { acc[s].x = 0; acc[s].y = 0; }
+            double pwd[2] = {0.0, 0.0};
+            int npix = 0;
+            int dy = -a.Ny, dx = -a.Nx;
+            for (int f = 0; f < W; ++f) {
+                const uint32_t wd = __shfl_sync(FULL, myword, f >> 5);
+                const int yy = ci + dy, xx = cj + dx;
+                if (((wd >> (f & 31)) & 1u) && yy >= 0 && yy < a.lines && xx >= 0 && xx < a.cols) {
+                    ++npix;
+                    const float2* zq = a.zpix + ((long)yy * a.cols + xx) * NP;
+#pragma unroll
+                    for (int s = 0; s < SLOTS; ++s) {
+                        if (eti[s] != 0xffff) {
+                            const float2 zi = __ldg(zq + eti[s]);
+                            const float2 zj = __ldg(zq + etj[s]);
+                            if (DP) {
+                                const float pr = __fadd_rn(__fmul_rn(zi.x, zj.x), __fmul_rn(zi.y, zj.y));
+                                const float pi = __fsub_rn(__fmul_rn(zi.y, zj.x), __fmul_rn(zi.x, zj.y));
+                                acc[s].x += pr; acc[s].y += pi;
+                            } else {
+                                acc[s].x = fmaf(zi.x, zj.x, acc[s].x); acc[s].x = fmaf(zi.y, zj.y, acc[s].x);
+                                acc[s].y = fmaf(zi.y, zj.x, acc[s].y); acc[s].y = fmaf(-zi.x, zj.y, acc[s].y);
+                            }
+                        }
+                    }
+                    if (DP) {                  // |z|^2: float hypot, squared and summed in double (:558)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int t = lane + 32 * h;
+                            if (t < N) {
+                                const float2 z = __ldg(zq + t);
+                                const float hy = (float)__dsqrt_rn(__dadd_rn(__dmul_rn((double)z.x, (double)z.x),
+                                                                             __dmul_rn((double)z.y, (double)z.y)));
+                                pwd[h] += (double)hy * (double)hy;
+                            }
+                        }
+                    }
+                }
+                if (++dx > a.Nx) { dx = -a.Nx; ++dy; }
+            }
+            const int need = (a.variant == 0) ? 2 : a.min_neighbors;
+            if (npix >= need) {
+                // ---------------- coherence matrix (evd.cpp:569-582) -------------------
+                __syncwarp();
+                if (DP) {
+                    for (int h = 0; h < 2; ++h) { const int t = lane + 32 * h; if (t < N) w.dinv[t] = pwd[h]; }
+                    __syncwarp();
+#pragma unroll
+                    for (int s = 0; s < SLOTS; ++s) {
+                        if (eti[s] == 0xffff) continue;
+                        const int ti = eti[s], tj = etj[s];
+                        if (ti == tj) {
+                            w.C[ti * ldc + ti] = make_float2(1.f, 0.f);
+                            w.Cd[ti * ld + ti] = make_double2(1.0, 0.0);
+                            continue;
+                        }
+                        const double den = sqrt(w.dinv[ti] * w.dinv[tj]);      // evd.cpp:577
+                        const double2 c = make_double2((double)acc[s].x / den, (double)acc[s].y / den);
+                        w.Cd[ti * ld + tj] = c;
+                        w.Cd[tj * ld + ti] = make_double2(c.x, -c.y);
+                        w.C[ti * ldc + tj] = make_float2((float)c.x, (float)c.y);
+                        w.C[tj * ldc + ti] = make_float2((float)c.x, -(float)c.y);
+                    }
+                } else {
+#pragma unroll
+                    for (int s = 0; s < SLOTS; ++s)
+                        if (eti[s] != 0xffff && eti[s] == etj[s]) w.pw[eti[s]] = sqrtf((float)acc[s].x);
+                    __syncwarp();
+#pragma unroll
+                    for (int s = 0; s < SLOTS; ++s) {
+                        if (eti[s] == 0xffff) continue;
+                        const int ti = eti[s], tj = etj[s];
+                        if (ti == tj) { w.C[ti * ldc + ti] = make_float2(1.f, 0.f); continue; }
+                        const float inv = 1.0f / (w.pw[ti] * w.pw[tj]);
+                        float2 c = make_float2((float)acc[s].x * inv, (float)acc[s].y * inv);
+                        w.C[ti * ldc + tj] = c;
+                        w.C[tj * ldc + ti] = make_float2(c.x, -c.y);
+                    }
+                }
+                __syncwarp();
+                ++st_pix;
+
+                bool run_evd = !ismle && a.variant == 0;
+                bool failed = false;
+                if (DP && (a.variant == 1 || ismle)) {
+                    ++st_dp;
+                    // ---- gate 1 (evd.cpp MLE only): lambda_min(C) >= 1e-6 -------------
+                    if (a.variant == 0) {
+                        for (int h = 0; h < 2; ++h) {
+                            const int r = lane + 32 * h;
+                            if (r < N) for (int j = 0; j <= r; ++j) {
+                                w.F[r * ld + j] = (j == r) ? make_double2(1.0 - 1.0e-6, 0.0) : w.Cd[r * ld + j];
+                            }
+                        }
+                        __syncwarp();
+                        if (!chol_c(w.F, w.dinv, N, ld, lane)) { tc = -2.f; failed = true; }
+                    }
+                    // ---- |C| and its inverse -------------------------------------------
+                    if (!failed) {
+                        auto fill_abs = [&](double dshift) {
+                            for (int h = 0; h < 2; ++h) {
+                                const int r = lane + 32 * h;
+                                if (r < N) for (int j = 0; j <= r; ++j) {
+                                    const double2 c = w.Cd[r * ld + j];
+                                    w.A[r * ld + j] = (j == r) ? 1.0 - dshift : hypot(c.x, c.y);
+                                }
+                            }
+                            __syncwarp();
+                        };
+                        if (a.variant == 0) {               // gate 2: lambda_min(|C|) >= 1e-6
+                            fill_abs(1.0e-6);
+                            if (!chol_r(w.A, w.dinv, N, ld, lane)) { tc = -4.f; failed = true; }
+                        }
+                        if (!failed) {
+                            fill_abs(0.0);
+                            if (!chol_r(w.A, w.dinv, N, ld, lane)) {
+                                if (a.variant == 0) { tc = -5.f; failed = true; }
+                                else run_evd = true;
+                            } else {
+                                chol_inverse_r(w.A, reinterpret_cast<double*>(w.F), w.dinv, N, ld, lane);
+                                double2 vd[2];
+                                double lam = 0.0;
+                                if (!smallest_eigen_mle(w, N, ldc, ld, lane, vd, &lam)) {
+                                    if (a.variant == 0) { tc = -6.f; failed = true; }
+                                    else run_evd = true;
+                                } else if (a.variant == 0 && lam < 1.0e-6) { tc = -7.f; failed = true; }
+                                else {
+                                    // rotate in double so that the reference component is real
+                                    // positive, then hand the FP32 copy to the post-processing
+                                    __syncwarp();
+                                    for (int h = 0; h < 2; ++h) { const int r = lane + 32 * h; if (r < N) w.xd[r] = vd[h]; }
+                                    __syncwarp();
+                                    const double2 ref = w.xd[k0];
+                                    const double rn = 1.0 / fmax(hypot(ref.x, ref.y), 1e-300);
+                                    for (int h = 0; h < 2; ++h) {
+                                        const double2 u = cmulc(vd[h], make_double2(ref.x * rn, ref.y * rn));
+                                        vf[h] = make_float2((float)u.x, (float)u.y);
+                                    }
+                                    have_vec = true;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (run_evd && !failed) {
+                    // ---------------- EVD / STBAS (evd.cpp:689-732) --------------------
+                    if (isstbas && a.variant == 0) {
+                        for (int h = 0; h < 2; ++h) {
+                            const int r = lane + 32 * h;
+                            if (r < N) for (int j = 0; j < N; ++j)
+                                if (abs(j - r) > BW) w.C[r * ldc + j] = make_float2(0.f, 0.f);
+                        }
+                        __syncwarp();
+                    }
+                    int iters = 0;
+                    bool capped = false;
+                    const float lam = power_iteration(w, N, ldc, lane, k0, vf, &iters, &capped);
+                    st_it += iters;
+                    st_cap += capped ? 1 : 0;
+                    if (a.variant == 0 && lam < 1.0e-6f) { tc = -7.f; }
+                    else have_vec = true;
+                }
+            }
+        }
+
+        // -------- phase reference, compression, temporal coherence (evd.cpp:738-786) --
+        float2 o[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        float2 cmp = make_float2(0.f, 0.f);
+        if (have_vec) {
+            __syncwarp();
+            for (int h = 0; h < 2; ++h) { const int r = lane + 32 * h; if (r < N) w.xv[r] = vf[h]; }
+            __syncwarp();
+            const float2 ref = w.xv[k0];
+            float cr = 0.f, cim = 0.f;
+            for (int h = 0; h < 2; ++h) {
+                const int r = lane + 32 * h;
+                if (r < N) {
+                    float ux = vf[h].x * ref.x + vf[h].y * ref.y;      // v * conj(ref)
+                    float uy = vf[h].y * ref.x - vf[h].x * ref.y;
+                    float m = sqrtf(ux * ux + uy * uy);
+                    if (m == 0.f) {                                     // arg(0) = 0 in the reference
+                        const float mr = sqrtf(ref.x * ref.x + ref.y * ref.y);
+                        ux = ref.x / mr; uy = -ref.y / mr;
+                    } else { ux /= m; uy /= m; }
+                    if (r == k0) { ux = 1.f; uy = 0.f; }
+                    o[h] = make_float2(ux, uy);
+                    if (r >= k0) {
+                        const float2 z = __ldg(&a.zpix[p * NP + r]);
+                        cr += z.x * ux + z.y * uy;                      // z * conj(o)
+                        cim += z.y * ux - z.x * uy;
+                    }
+                }
+            }
+            cr = warp_sum(cr); cim = warp_sum(cim);
+            const float invn = 1.0f / (float)(N - a.mini_stack_count + 1);
+            cmp = make_float2(cr * invn, cim * invn);
+            __syncwarp();
+            for (int h = 0; h < 2; ++h) { const int r = lane + 32 * h; if (r < N) w.xv[r] = o[h]; }
+            __syncwarp();
+            float sr = 0.f, si = 0.f;
+            int cnt = 0;
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                if (eti[s] == 0xffff || eti[s] == etj[s]) continue;
+                const int ti = eti[s], tj = etj[s];
+                if (isstbas && (tj - ti) > BW) continue;
+                // upper entry was possibly zeroed for STBAS only outside the band -> untouched here
+                const float2 c = w.C[ti * ldc + tj];
+                const float m = sqrtf(c.x * c.x + c.y * c.y);
+                float ex = 1.f, ey = 0.f;
+                if (m > 0.f) { ex = c.x / m; ey = c.y / m; }
+                const float2 oi = w.xv[ti], oj = w.xv[tj];
+                // e * conj(oi) * oj
+                const float tx = ex * oi.x + ey * oi.y, ty = ey * oi.x - ex * oi.y;
+                sr += tx * oj.x - ty * oj.y;
+                si += tx * oj.y + ty * oj.x;
+                ++cnt;
+            }
+            sr = warp_sum(sr); si = warp_sum(si);
+            cnt = __reduce_add_sync(FULL, cnt);
+            tc = sqrtf(sr * sr + si * si) / (float)cnt;
+        }
+        for (int h = 0; h < 2; ++h) {
+            const int r = lane + 32 * h;
+            if (r < N) a.out[(long)r * npix_block + p] = o[h];
+        }
+        if (lane == 0) { a.tcorr[p] = tc; a.comp[p] = cmp; }
+    }
+    if (a.stats) {
+        if (lane == 0) {
+            atomicAdd(&a.stats[0], st_pix);
+            atomicAdd(&a.stats[1], st_it);
+            atomicAdd(&a.stats[2], st_dp);
+            atomicAdd(&a.stats[3], st_cap);
+        }
+    }
+}
+
+int evd_max_bands(int, int) { return 64; }
+
+template <int SLOTS, bool DP>
+static cudaError_t launch_evd_t(const EvdArgs& a, cudaStream_t st, int WARPS) {
+    const size_t smem = evd_warp_smem_bytes(a.bands, DP) * WARPS;
+    cudaError_t e = cudaFuncSetAttribute(k_evd<SLOTS, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, nsm = 148, occ = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_evd<SLOTS, DP>, WARPS * 32, smem);
+    if (occ < 1) occ = 1;
+    const long total = (long)a.n_lines * a.cols;
+    long grid = (long)nsm * occ * 4;                 // a few chunks per resident CTA slot
+    const long maxgrid = (total + WARPS * 8 - 1) / (WARPS * 8);
+    if (grid > maxgrid) grid = maxgrid;
+    if (grid < 1) grid = 1;
+    k_evd<SLOTS, DP><<<(unsigned)grid, WARPS * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <bool DP>
+static cudaError_t launch_evd_dp(const EvdArgs& a, cudaStream_t st) {
+    const int E = a.bands * (a.bands + 1) / 2;
+    const int slots = (E + 31) / 32;
+    const size_t per_warp = evd_warp_smem_bytes(a.bands, DP);
+    const size_t budget = 200 * 1024;
+    int warps = (int)(budget / per_warp);
+    if (warps < 1) return cudaErrorInvalidValue;
+    if (warps > 8) warps = 8;
+    if (slots > 16 && warps > 4) warps = 4;
+    if (slots <= 4)  return launch_evd_t<4, DP>(a, st, warps);
+    if (slots <= 8)  return launch_evd_t<8, DP>(a, st, warps);
+    if (slots <= 16) return launch_evd_t<16, DP>(a, st, warps);
+    if (slots <= 33) return launch_evd_t<33, DP>(a, st, warps);
+    if (slots <= 65) return launch_evd_t<65, DP>(a, st, warps);
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_evd(const EvdArgs& a, cudaStream_t st, int* n_launches) {
+    const bool dp = (a.method == 1) || (a.variant == 1);
+    if (n_launches) *n_launches = 1;
+    return dp ? launch_evd_dp<true>(a, st) : launch_evd_dp<false>(a, st);
+}
+
+}  // namespace fringe

@@ -1,0 +1,199 @@
+"""Thin Python face of the C ABI: one ``Context`` per GPU.
+
+Host-array calls (``nmap_block`` / ``evd_block``) go through ``fringe_nmap_block`` /
+``fringe_evd_block`` -- the same entry points the C++ block drivers use -- so the parity tests
+exercise exactly the drop-in boundary.  The ``*_device`` calls take torch CUDA tensors (torch is
+only the allocator and stream owner here) and queue work on torch's current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import FringeError, lib
+
+METHODS_NMAP = {"KS2": _lib.NMAP_KS2, "AD2": _lib.NMAP_AD2}
+METHODS_EVD = {"EVD": _lib.EVD_EVD, "MLE": _lib.EVD_MLE, "STBAS": _lib.EVD_STBAS}
+
+
+def nulong(Nx: int, Ny: int) -> int:
+    return int(lib.fringe_nulong(Nx, Ny))
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    lib.fringe_device_count(C.byref(n))
+    return n.value
+
+
+def ks2_critical_count(bands: int, pvalue: float):
+    k, m = C.c_int(0), C.c_double(0)
+    rc = lib.fringe_ks2_critical_count(bands, pvalue, C.byref(k), C.byref(m))
+    if rc:
+        raise FringeError(rc, lib.fringe_status_string(rc).decode())
+    return k.value, m.value
+
+
+def ad2_critical_sum(bands: int, pvalue: float) -> float:
+    s = C.c_double(0)
+    rc = lib.fringe_ad2_critical_sum(bands, pvalue, C.byref(s))
+    if rc:
+        raise FringeError(rc, lib.fringe_status_string(rc).decode())
+    return s.value
+
+
+def ad2_sigma(bands: int) -> float:
+    s = C.c_double(0)
+    rc = lib.fringe_ad2_sigma(bands, C.byref(s))
+    if rc:
+        raise FringeError(rc, lib.fringe_status_string(rc).decode())
+    return s.value
+
+
+def _method(table, m):
+    if isinstance(m, str):
+        if m.upper() not in table:
+            return 99          # let the library report FRINGE_ERR_METHOD like nmap_process does
+        return table[m.upper()]
+    return int(m)
+
+
+class Context:
+    """Owns a ``fringe_ctx`` (stream + device workspaces) on one GPU."""
+
+    def __init__(self, device: int = 0):
+        h = C.c_void_p()
+        rc = lib.fringe_create(int(device), C.byref(h))
+        if rc:
+            raise FringeError(rc, lib.fringe_status_string(rc).decode())
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.fringe_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc:
+            raise FringeError(rc, lib.fringe_last_error(self._h).decode() or lib.fringe_status_string(rc).decode())
+
+    def synchronize(self):
+        self._check(lib.fringe_synchronize(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib.fringe_launch_count(self._h))
+
+    def evd_stats(self) -> dict:
+        arr = (C.c_int64 * 4)()
+        self._check(lib.fringe_evd_stats(self._h, arr))
+        return {"pixels": arr[0], "power_iterations": arr[1], "fp64_pixels": arr[2], "capped": arr[3]}
+
+    KERNELS = {"amp_sort": 0, "nmap": 1, "transpose": 2, "evd": 3}
+
+    def last_kernel_ms(self, kernel: str) -> float:
+        ms = C.c_float(0)
+        self._check(lib.fringe_last_kernel_ms(self._h, self.KERNELS[kernel], C.byref(ms)))
+        return float(ms.value)
+
+    def fp32_peak_tflops(self) -> float:
+        t = C.c_double(0)
+        self._check(lib.fringe_fp32_peak(self._h, C.byref(t)))
+        return float(t.value)
+
+    # ---- host arrays -----------------------------------------------------------------------
+    def nmap_block(self, slc, Nx, Ny, method="KS2", pvalue=0.05, mask=None, alpha=None):
+        """slc (bands, lines, cols) complex64 -> count (lines, cols) int32, wts (lines, cols, nulong) uint32."""
+        slc = np.ascontiguousarray(slc, np.complex64)
+        bands, lines, cols = slc.shape
+        nu = nulong(Nx, Ny)
+        count = np.empty((lines, cols), np.int32)
+        wts = np.empty((lines, cols, nu), np.uint32)
+        mask_p = None
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, np.uint8)
+            mask_p = mask.ctypes.data
+        alpha_p = None
+        if alpha is not None:
+            alpha = np.ascontiguousarray(alpha, np.float64)
+            alpha_p = alpha.ctypes.data
+        self._check(lib.fringe_nmap_block(self._h, slc.ctypes.data, mask_p, alpha_p, cols, lines, bands,
+                                          Nx, Ny, _method(METHODS_NMAP, method), float(pvalue),
+                                          count.ctypes.data, wts.ctypes.data))
+        return count, wts
+
+    def evd_block(self, slc, wts, Nx, Ny, method="EVD", bandwidth=-1, mini_stack_count=1,
+                  variant=_lib.VARIANT_EVD, min_neighbors=2, first_line=0, n_lines=None):
+        """-> out (bands, lines, cols) complex64, tcorr (lines, cols) f32, comp (lines, cols) c64;
+        lines outside [first_line, first_line+n_lines) are returned as zeros."""
+        slc = np.ascontiguousarray(slc, np.complex64)
+        wts = np.ascontiguousarray(wts, np.uint32)
+        bands, lines, cols = slc.shape
+        if n_lines is None:
+            n_lines = lines - first_line
+        out = np.zeros((bands, lines, cols), np.complex64)
+        tcorr = np.zeros((lines, cols), np.float32)
+        comp = np.zeros((lines, cols), np.complex64)
+        self._check(lib.fringe_evd_block(self._h, slc.ctypes.data, wts.ctypes.data, cols, lines, bands, Nx, Ny,
+                                         first_line, n_lines, _method(METHODS_EVD, method), int(bandwidth),
+                                         int(mini_stack_count), int(variant), int(min_neighbors),
+                                         out.ctypes.data, tcorr.ctypes.data, comp.ctypes.data))
+        return out, tcorr, comp
+
+    # ---- device tensors (torch) ------------------------------------------------------------
+    @staticmethod
+    def _stream():
+        import torch
+        h = torch.cuda.current_stream().cuda_stream
+        # torch's default stream has handle 0, which the C ABI reads as "use the context's own
+        # stream"; name the legacy default stream explicitly (cudaStreamLegacy == 0x1) so the
+        # kernels really run on -- and CUDA events really time -- torch's current stream.
+        return C.c_void_p(h if h else 1)
+
+    def nmap_block_device(self, slc, Nx, Ny, method="KS2", pvalue=0.05, mask=None, alpha=None,
+                          count=None, wts=None):
+        """slc: torch complex64 CUDA tensor (bands, lines, cols), contiguous."""
+        import torch
+        assert slc.is_cuda and slc.dtype == torch.complex64 and slc.is_contiguous()
+        bands, lines, cols = slc.shape
+        nu = nulong(Nx, Ny)
+        if count is None:
+            count = torch.empty((lines, cols), dtype=torch.int32, device=slc.device)
+        if wts is None:
+            wts = torch.empty((lines, cols, nu), dtype=torch.int32, device=slc.device)
+        self._check(lib.fringe_nmap_block_device(
+            self._h, slc.data_ptr(), None if mask is None else mask.data_ptr(),
+            None if alpha is None else alpha.data_ptr(), cols, lines, bands, Nx, Ny,
+            _method(METHODS_NMAP, method), float(pvalue), count.data_ptr(), wts.data_ptr(), self._stream()))
+        return count, wts
+
+    def evd_block_device(self, slc, wts, Nx, Ny, method="EVD", bandwidth=-1, mini_stack_count=1,
+                         variant=_lib.VARIANT_EVD, min_neighbors=2, first_line=0, n_lines=None,
+                         out=None, tcorr=None, comp=None):
+        import torch
+        assert slc.is_cuda and slc.dtype == torch.complex64 and slc.is_contiguous()
+        bands, lines, cols = slc.shape
+        if n_lines is None:
+            n_lines = lines - first_line
+        if out is None:
+            out = torch.zeros((bands, lines, cols), dtype=torch.complex64, device=slc.device)
+        if tcorr is None:
+            tcorr = torch.zeros((lines, cols), dtype=torch.float32, device=slc.device)
+        if comp is None:
+            comp = torch.zeros((lines, cols), dtype=torch.complex64, device=slc.device)
+        self._check(lib.fringe_evd_block_device(
+            self._h, slc.data_ptr(), wts.data_ptr(), cols, lines, bands, Nx, Ny, first_line, n_lines,
+            _method(METHODS_EVD, method), int(bandwidth), int(mini_stack_count), int(variant),
+            int(min_neighbors), out.data_ptr(), tcorr.data_ptr(), comp.data_ptr(), self._stream()))
+        return out, tcorr, comp

@@ -86,37 +86,42 @@ def make_stack(bands: int, lines: int, cols: int, seed: int = 0, region: int = 6
 
 def make_stack_torch(bands: int, lines: int, cols: int, seed: int, device, region: int = 64,
                      tau: float = 72.0, dt: float = 12.0, zero_fraction: float = 0.01,
-                     rows_per_chunk: int = 64):
+                     rows_per_chunk: int = 64, row_range=None):
     """Same model generated on `device` with torch (bench-size stacks; not bit-identical to
-    make_stack).  Returns a (bands, lines, cols) complex64 tensor."""
+    make_stack).  Random numbers are drawn per 64-row chunk of the *global* image with a seed
+    derived from the chunk index, so any `row_range=(r0, r1)` sub-block (a rank's tile + halo)
+    holds exactly the rows the full image would.  Returns (bands, r1-r0, cols) complex64."""
     import torch
 
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    out = torch.empty((bands, lines, cols), dtype=torch.complex64, device=device)
+    r_lo, r_hi = (0, lines) if row_range is None else row_range
+    out = torch.empty((bands, r_hi - r_lo, cols), dtype=torch.complex64, device=device)
     rmap = torch.from_numpy(region_map(lines, cols, region)).to(device)
     roots = []
     for (sigma, g0, ginf, rate, seas) in REGION_TYPES:
         L = sigma * matrix_sqrt(coherence_matrix(bands, g0, ginf, tau, phase_series(bands, dt, rate, seas), dt))
         roots.append(torch.from_numpy(L.astype(np.complex64)).to(device))
     roots = torch.stack(roots)                       # (T, bands, bands)
-    for r0 in range(0, lines, rows_per_chunk):
-        r1 = min(lines, r0 + rows_per_chunk)
-        n = (r1 - r0) * cols
+    g = torch.Generator(device=device)
+    for c in range(r_lo // rows_per_chunk, (r_hi + rows_per_chunk - 1) // rows_per_chunk):
+        c0, c1 = c * rows_per_chunk, min(lines, (c + 1) * rows_per_chunk)
+        g.manual_seed(seed * 1000003 + c)
+        n = (c1 - c0) * cols
         re = torch.randn((bands, n), generator=g, device=device)
         im = torch.randn((bands, n), generator=g, device=device)
         noise = torch.complex(re, im) * (0.5 ** 0.5)
-        kinds = rmap[r0:r1].reshape(-1)
+        del re, im
+        kinds = rmap[c0:c1].reshape(-1)
         chunk = torch.empty((bands, n), dtype=torch.complex64, device=device)
         for k in range(roots.shape[0]):
             sel = kinds == k
             if bool(sel.any()):
                 chunk[:, sel] = roots[k] @ noise[:, sel]
-        out[:, r0:r1, :] = chunk.reshape(bands, r1 - r0, cols)
-    if zero_fraction > 0:
-        nz = int(zero_fraction * lines * cols)
-        rr = torch.randint(0, lines, (nz,), generator=g, device=device)
-        cc = torch.randint(0, cols, (nz,), generator=g, device=device)
-        bb = torch.randint(0, bands, (nz,), generator=g, device=device)
-        out[bb, rr, cc] = 0
+        if zero_fraction > 0:
+            nz = int(zero_fraction * n)
+            pp = torch.randint(0, n, (nz,), generator=g, device=device)
+            bb = torch.randint(0, bands, (nz,), generator=g, device=device)
+            chunk[bb, pp] = 0
+        chunk = chunk.reshape(bands, c1 - c0, cols)
+        a, b = max(c0, r_lo), min(c1, r_hi)
+        out[:, a - r_lo:b - r_lo, :] = chunk[:, a - c0:b - c0, :]
     return out

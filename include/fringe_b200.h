@@ -1,0 +1,156 @@
+/* fringe_b200 -- C ABI of the B200-native phase-linking hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, int status codes, no C++ or
+ * torch types.  Everything above it (the C++ block drivers nmap_process / evd_process,
+ * the nmaplib / evdlib / phase_linklib Python modules, the CLIs) only moves rasters around;
+ * everything below it is hand-written sm_100a CUDA.
+ *
+ * The one C-style kernel boundary the reference has is
+ *     void nmapProcessBlock(float* amp, unsigned char* msk, int cols, int lines, int bands,
+ *                           int* cnt, unsigned int* wmask, int wtslen, double pval,
+ *                           int Nx, int Ny);                       (src/nmap/nmap_cuda.h:13-17)
+ * plus lockGPU()/unlockGPU() (src/nmap/nmap_cuda.cu:368-376).  The entry points below keep
+ * its conventions -- caller-owned host buffers, one block of image lines per call, the same
+ * array layouts the reference drivers hold in memory -- and extend them to the whole path.
+ * INTEGRATION.md shows the call sites in the reference that would bind to each of them.
+ *
+ * Array layouts (identical to what the reference block loops hold):
+ *   slc    complex64 [bands][lines*cols]   one plane per date   (arma cpxdata, evd.cpp:193)
+ *   mask   uint8     [lines*cols]          non-zero = use pixel (nmap.cpp:190, :323-343)
+ *   count  int32     [lines*cols]                               (nmap.cpp:194)
+ *   wts    uint32    [lines*cols][nulong]  BIP, bit layout of include/fringe/ulongmask.hpp:57-95
+ *   out    complex64 [bands][lines*cols]   unit phasors         (arma evddata, evd.cpp:194)
+ *   tcorr  float32   [lines*cols]          >=0 coherence, <0 sentinel (evd.cpp:608-725)
+ *   comp   complex64 [lines*cols]          compressed SLC       (evd.cpp:755-762)
+ *
+ * All entry points return FRINGE_OK (0) or a positive error code; none of them calls exit().
+ */
+#ifndef FRINGE_B200_H
+#define FRINGE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRINGE_ABI_VERSION 1
+
+/* status codes */
+enum {
+    FRINGE_OK = 0,
+    FRINGE_ERR_METHOD = 1,       /* unknown method; same value nmap_process returns (nmap.cpp:41) */
+    FRINGE_ERR_ARGUMENT = 2,     /* null pointer / non-positive size / inconsistent geometry */
+    FRINGE_ERR_UNSUPPORTED = 3,  /* valid request the kernels do not cover (e.g. bands too large) */
+    FRINGE_ERR_NO_DEVICE = 4,    /* no CUDA device / driver: there is no CPU fallback */
+    FRINGE_ERR_CUDA = 5,         /* CUDA runtime error; text via fringe_last_error() */
+    FRINGE_ERR_MEMORY = 6        /* device or pinned allocation failed */
+};
+
+/* SHP test selector (nmapOptions::method "KS2" / "AD2", src/nmap/nmap.cpp:27-42) */
+enum { FRINGE_NMAP_KS2 = 0, FRINGE_NMAP_AD2 = 1 };
+/* decomposition selector (evdOptions::method "EVD" / "MLE" / "STBAS", src/evd/evd.cpp:507-510) */
+enum { FRINGE_EVD_EVD = 0, FRINGE_EVD_MLE = 1, FRINGE_EVD_STBAS = 2 };
+/* which driver's per-pixel control flow: src/evd/evd.cpp:566-732 or
+ * src/phase_link/phase_link.cpp:524-618 (MLE with EVD fallback, honours minNeighbors) */
+enum { FRINGE_VARIANT_EVD = 0, FRINGE_VARIANT_PHASE_LINK = 1 };
+
+typedef struct fringe_ctx fringe_ctx;
+
+/* ---- context: one per GPU; owns a stream and reusable device workspaces ---------------
+ * Replaces lockGPU()/unlockGPU() (nmap_cuda.cu:368-376), which pin device 0 and reset it. */
+int fringe_abi_version(void);
+int fringe_device_count(int* count);
+int fringe_create(int device, fringe_ctx** ctx);
+int fringe_destroy(fringe_ctx* ctx);
+const char* fringe_last_error(const fringe_ctx* ctx);   /* never NULL */
+const char* fringe_status_string(int status);
+/* Block until everything queued on the context's own stream has finished. */
+int fringe_synchronize(fringe_ctx* ctx);
+/* Number of kernel launches issued through this context since creation. */
+int64_t fringe_launch_count(const fringe_ctx* ctx);
+
+/* pinned host memory for the block buffers (the reference uses pageable arma arrays) */
+int fringe_host_alloc(void** ptr, size_t bytes);
+int fringe_host_free(void* ptr);
+
+/* ---- host-side helpers (pure integer / double arithmetic, no device needed) ----------- */
+/* ceil((2Ny+1)(2Nx+1)/32), nmap.cpp:65 */
+int fringe_nulong(int Nx, int Ny);
+/* Largest integer k with KolmogorovProb(k/N * sqrt(N/2)) >= pvalue (KS2sample.hpp:42-77,:139-141):
+ * a pair is accepted iff max_v |#{a<=v} - #{b<=v}| <= k.  *margin receives the smaller of the
+ * two distances |p(k)-pvalue|, |p(k+1)-pvalue| so callers can assert the decision is not
+ * rounding-sensitive. */
+int fringe_ks2_critical_count(int bands, double pvalue, int* kcrit, double* margin);
+/* Largest value S of the Anderson-Darling inner sum (AD2unique.hpp:287-303) for which the
+ * reference's p-value chain (:309-348, :125-160) still returns >= pvalue. */
+int fringe_ad2_critical_sum(int bands, double pvalue, double* scrit);
+/* sigma_N of AD2unique::getSigmaN(N,N) (AD2unique.hpp:162-208) */
+int fringe_ad2_sigma(int bands, double* sigma);
+
+/* ---- SHP selection ------------------------------------------------------------------
+ * One block of `lines` image lines, all columns.  Replaces nmapProcessBlock and the CPU loops
+ * src/nmap/nmap.cpp:370-473: amplitude / calibration / validity, per-pixel sort, pair tests,
+ * bitmask and neighbour count.  Unlike nmapProcessBlock it takes the complex samples (the
+ * amplitude is computed on the device) and honours `method` (the reference's GPU path always
+ * runs KS2, nmap_cuda.cu:310).
+ *   mask  may be NULL (all pixels usable);  alpha may be NULL (all 1.0) else [bands] doubles,
+ *   already normalised by band 0 as nmap.cpp:225-230 does.
+ * Host variant: pointers are host memory (pinned preferred); copies in, runs, copies out,
+ * returns when the results are in `count` / `wts`. */
+int fringe_nmap_block(fringe_ctx* ctx, const float* slc, const uint8_t* mask, const double* alpha,
+                      int cols, int lines, int bands, int Nx, int Ny, int method, double pvalue,
+                      int32_t* count, uint32_t* wts);
+/* Device variant: every pointer is device memory on the context's GPU; work is queued on
+ * `stream` (a cudaStream_t, NULL = the context's stream) and the call returns immediately. */
+int fringe_nmap_block_device(fringe_ctx* ctx, const float* slc, const uint8_t* mask,
+                             const double* alpha, int cols, int lines, int bands, int Nx, int Ny,
+                             int method, double pvalue, int32_t* count, uint32_t* wts,
+                             void* stream);
+
+/* ---- covariance + eigen solve + phase referencing + compression + temporal coherence --
+ * One block of `lines` lines; results are produced for lines [first_line, first_line+n_lines)
+ * only (the reference's firstlinetowrite / linestowrite, evd.cpp:414-443); the rest of the
+ * output arrays is left untouched.  Replaces the pixel loops src/evd/evd.cpp:512-788
+ * (variant EVD) and src/phase_link/phase_link.cpp:479-666 (variant PHASE_LINK).
+ *   bandwidth        STBAS only (evd.cpp:74-91 range rules apply)
+ *   mini_stack_count 1-based index of the first non-compressed band (evd.cpp:740,757)
+ *   min_neighbors    used by variant PHASE_LINK only (evd.cpp hard-codes 2, :566) */
+int fringe_evd_block(fringe_ctx* ctx, const float* slc, const uint32_t* wts, int cols, int lines,
+                     int bands, int Nx, int Ny, int first_line, int n_lines, int method,
+                     int bandwidth, int mini_stack_count, int variant, int min_neighbors,
+                     float* out, float* tcorr, float* comp);
+int fringe_evd_block_device(fringe_ctx* ctx, const float* slc, const uint32_t* wts, int cols,
+                            int lines, int bands, int Nx, int Ny, int first_line, int n_lines,
+                            int method, int bandwidth, int mini_stack_count, int variant,
+                            int min_neighbors, float* out, float* tcorr, float* comp,
+                            void* stream);
+
+/* Largest `bands` the evd kernels accept for the given method. */
+int fringe_evd_max_bands(int method, int variant);
+
+/* ---- measurement hooks ----------------------------------------------------------------
+ * Device time of the most recent launch of one kernel, from CUDA events recorded on the
+ * stream it was launched on (synchronises on the closing event). */
+enum {
+    FRINGE_KERNEL_AMP_SORT = 0,   /* amplitude + per-pixel sort */
+    FRINGE_KERNEL_NMAP = 1,       /* window pair tests */
+    FRINGE_KERNEL_TRANSPOSE = 2,  /* band-major -> pixel-major re-layout */
+    FRINGE_KERNEL_EVD = 3,        /* covariance + eigen + post-processing */
+    FRINGE_KERNEL_COUNT = 4
+};
+int fringe_last_kernel_ms(fringe_ctx* ctx, int kernel, float* ms);
+/* FP32 FMA throughput of the device measured with a register-resident FMA loop; the roofline
+ * denominator for the covariance + eigen kernel (MEASURED_PEAKS.json carries no FP32 figure). */
+int fringe_fp32_peak(fringe_ctx* ctx, double* tflops);
+
+/* Per-pixel solver statistics of the most recent evd call on this context (debug/bench):
+ * stats[0] pixels solved, [1] total FP32 power iterations, [2] pixels that took the FP64
+ * certified path, [3] pixels that hit an iteration cap.  Synchronises the context. */
+int fringe_evd_stats(fringe_ctx* ctx, int64_t stats[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRINGE_B200_H */

@@ -1,0 +1,137 @@
+"""GPU parity: covariance + eigen solve through the C ABI (fringe_evd_block) vs the CPU oracle.
+Gates (BASELINE.json north_star): wrapped phase difference <= 1e-3 rad where the oracle's temporal
+coherence > 0.3; |delta tcorr| <= 1e-4; sentinel codes equal."""
+import numpy as np
+import pytest
+
+from conftest import wrapped_diff
+from fringe_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+PHASE_TOL = 1.0e-3
+TCORR_TOL = 1.0e-4
+
+
+def _compare(ref, gpu, rows=slice(None), borderline=0):
+    o_ref, t_ref, c_ref = ref
+    o_gpu, t_gpu, c_gpu = gpu
+    o_ref, o_gpu = o_ref[:, rows], o_gpu[:, rows]
+    t_ref, t_gpu = t_ref[rows], t_gpu[rows]
+    c_ref, c_gpu = c_ref[rows], c_gpu[rows]
+    # sentinels / skipped pixels: same code
+    code_ref = np.where(t_ref < 0, t_ref, 0)
+    code_gpu = np.where(t_gpu < 0, t_gpu, 0)
+    bad_code = code_ref != code_gpu
+    assert bad_code.sum() <= borderline, f"sentinel mismatches: {bad_code.sum()}"
+    solved = (t_ref > 0) & ~bad_code
+    assert solved.sum() > 0
+    dt = np.abs(t_ref - t_gpu)[solved]
+    assert dt.max() <= TCORR_TOL, f"tcorr max diff {dt.max()}"
+    good = solved & (t_ref > 0.3)
+    dphi = wrapped_diff(o_ref[:, good], o_gpu[:, good])
+    assert dphi.max() <= PHASE_TOL, f"phase max diff {dphi.max()}"
+    # unit magnitude / zero for unsolved pixels, exactly like the reference
+    mag = np.abs(o_gpu)
+    assert np.allclose(mag[:, solved], 1.0, atol=1e-5)
+    assert np.all(o_gpu[:, ~(t_gpu > 0)] == 0)
+    # compressed SLC
+    scale = np.abs(c_ref[solved]).max()
+    assert np.abs(c_ref - c_gpu)[good].max() <= 2e-3 * scale
+    return dphi.max(), dt.max()
+
+
+def _nmap(oracle_lib, slc, Nx, Ny):
+    return oracle_lib.nmap_block(slc, Nx, Ny)[1]
+
+
+def test_evd_config1(ctx, oracle_lib):
+    # BASELINE.json configs[0]: 20 dates, 11x5 window, EVD (160x192 crop of 512x512)
+    slc = synth.make_stack(20, 160, 192, seed=1)
+    wts = _nmap(oracle_lib, slc, 5, 2)
+    ref = oracle_lib.evd_block(slc, wts, 5, 2, method=0)
+    gpu = ctx.evd_block(slc, wts, 5, 2, method="EVD")
+    _compare(ref, gpu)
+    st = ctx.evd_stats()
+    assert st["capped"] == 0
+
+
+def test_evd_30_dates(ctx, oracle_lib):
+    slc = synth.make_stack(30, 64, 96, seed=2, region=32)
+    wts = _nmap(oracle_lib, slc, 5, 2)
+    _compare(oracle_lib.evd_block(slc, wts, 5, 2, method=0), ctx.evd_block(slc, wts, 5, 2, method="EVD"))
+
+
+def test_mle_config1(ctx, oracle_lib):
+    slc = synth.make_stack(20, 96, 128, seed=3)
+    wts = _nmap(oracle_lib, slc, 5, 2)
+    ref = oracle_lib.evd_block(slc, wts, 5, 2, method=1)
+    gpu = ctx.evd_block(slc, wts, 5, 2, method="MLE")
+    assert (ref[1] < 0).sum() > 0 and (ref[1] > 0).sum() > 0     # both sentinels and solutions present
+    _compare(ref, gpu, borderline=3)
+
+
+def test_stbas(ctx, oracle_lib):
+    slc = synth.make_stack(16, 48, 64, seed=4, region=16)
+    wts = _nmap(oracle_lib, slc, 4, 2)
+    ref = oracle_lib.evd_block(slc, wts, 4, 2, method=2, bandwidth=5)
+    gpu = ctx.evd_block(slc, wts, 4, 2, method="STBAS", bandwidth=5)
+    _compare(ref, gpu)
+
+
+def test_phase_link_variant(ctx, oracle_lib):
+    slc = synth.make_stack(20, 64, 96, seed=5, region=32)
+    wts = _nmap(oracle_lib, slc, 5, 2)
+    ref = oracle_lib.evd_block(slc, wts, 5, 2, method=1, variant=1, min_neighbors=5)
+    gpu = ctx.evd_block(slc, wts, 5, 2, method="MLE", variant=1, min_neighbors=5)
+    _compare(ref, gpu, borderline=3)
+
+
+def test_mini_stack_count_and_line_range(ctx, oracle_lib):
+    # sequential-style call: first 3 bands are compressed SLCs, interior lines only
+    slc = synth.make_stack(13, 40, 64, seed=6, region=16)
+    wts = _nmap(oracle_lib, slc, 5, 2)
+    ref = oracle_lib.evd_block(slc, wts, 5, 2, method=1, mini_stack_count=4, first_line=2, n_lines=30)
+    gpu = ctx.evd_block(slc, wts, 5, 2, method="MLE", mini_stack_count=4, first_line=2, n_lines=30)
+    _compare(ref, gpu, rows=slice(2, 32), borderline=3)
+    assert np.all(gpu[0][:, :2] == 0) and np.all(gpu[0][:, 32:] == 0)
+    assert np.all(gpu[0][3][2:32][gpu[1][2:32] > 0] == 1.0 + 0j)     # reference band is exactly 1+0j
+
+
+def test_reference_test_scenario_rmse(ctx, oracle_lib):
+    """The reference's own end-to-end assertion (tests/evd/test_evd.py:291-308,:461-463):
+    59 dates, gamma0=0.999, gamma_inf=0.99, tau=72 d, 11x11 homogeneous unit-amplitude window;
+    RMSE(estimated - simulated phase) <= 10 degrees for EVD, MLE and phase_link."""
+    rng = np.random.default_rng(42)
+    n = 59
+    t = np.arange(n) * 12.0
+    ph = 1.0 * t / 365.0 + np.sin(4 * np.pi * t / 365.0) + np.cos(4 * np.pi * t / 365.0) + 0.3 * rng.standard_normal(n)
+    ph = np.angle(np.exp(1j * (ph - ph[0])))
+    L = synth.matrix_sqrt(synth.coherence_matrix(n, 0.999, 0.99, 72.0, ph))
+    z = L @ ((rng.standard_normal((n, 121)) + 1j * rng.standard_normal((n, 121))) / np.sqrt(2))
+    slc = np.exp(1j * np.angle(z)).astype(np.complex64).reshape(n, 11, 11)
+    wts = np.zeros((11, 11, 4), np.uint32)
+    for f in range(121):
+        wts[5, 5, f // 32] |= np.uint32(1 << (f % 32))
+    for method, variant in (("EVD", 0), ("MLE", 0), ("MLE", 1)):
+        out, tcorr, _ = ctx.evd_block(slc, wts, 5, 5, method=method, variant=variant, min_neighbors=5)
+        est = out[:, 5, 5]
+        assert tcorr[5, 5] > 0.9
+        rmse = np.degrees(np.sqrt(np.mean(np.angle(np.exp(1j * ph) * np.conj(est)) ** 2)))
+        assert rmse <= 10.0, (method, variant, rmse)
+        ref = oracle_lib.evd_block(slc, wts, 5, 5, method={"EVD": 0, "MLE": 1}[method], variant=variant, min_neighbors=5)
+        assert wrapped_diff(ref[0][:, 5, 5], est).max() <= PHASE_TOL
+        assert abs(ref[1][5, 5] - tcorr[5, 5]) <= TCORR_TOL
+
+
+def test_argument_errors(ctx):
+    from fringe_b200._lib import FringeError
+    slc = synth.make_stack(6, 8, 8, seed=1)
+    wts = np.zeros((8, 8, 1), np.uint32)
+    with pytest.raises(FringeError) as e:
+        ctx.evd_block(slc, wts, 1, 1, method="FOO")
+    assert e.value.status == 1
+    with pytest.raises(FringeError):
+        ctx.evd_block(slc, wts, 1, 1, method="STBAS", bandwidth=-1)       # evd.cpp:77 -> rc 101
+    with pytest.raises(FringeError):
+        ctx.evd_block(slc, wts, 1, 1, method="EVD", mini_stack_count=9)
