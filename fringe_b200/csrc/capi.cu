@@ -5,6 +5,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -406,7 +407,10 @@ int fringe_evd_block_device(fringe_ctx* ctx, const float* slc, const uint32_t* w
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     const size_t npix = (size_t)cols * lines;
-    const int NP = (bands + 1) & ~1;
+    int NP = (bands + 1) & ~1;
+    const bool generic = getenv("FRINGE_EVD_GENERIC") != nullptr;      // debug switch
+    if (!generic && variant == FRINGE_VARIANT_EVD && method != FRINGE_EVD_MLE && fringe::evd_fast_padded_bands(bands) > 0)
+        NP = fringe::evd_fast_padded_bands(bands);
     CU(ctx->zpix.ensure(npix * NP * sizeof(float2)));
     CU(ctx->stats.ensure(4 * sizeof(unsigned long long)));
     CU(cudaMemsetAsync(ctx->stats.p, 0, 4 * sizeof(unsigned long long), st));
@@ -422,6 +426,7 @@ int fringe_evd_block_device(fringe_ctx* ctx, const float* slc, const uint32_t* w
     a.variant = variant; a.min_neighbors = min_neighbors;
     a.out = (float2*)out; a.tcorr = tcorr; a.comp = (float2*)comp;
     a.stats = (unsigned long long*)ctx->stats.p;
+    a.force_generic = generic ? 1 : 0;
     int nl = 0;
     CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_EVD][0], st));
     CU(fringe::launch_evd(a, st, &nl));

@@ -43,9 +43,17 @@ struct EvdArgs {
     float* tcorr;            // [npix]
     float2* comp;            // [npix]
     unsigned long long* stats;   // [4] device counters
+    int force_generic;           // debug: bypass the register-blocked kernel
 };
 int evd_max_bands(int method, int variant);
 cudaError_t launch_evd(const EvdArgs& a, cudaStream_t st, int* n_launches);
+
+// ---- evd_fast.cu ----------------------------------------------------------------------
+// Register-blocked kernel for EVD/STBAS with bands <= 30.  It needs the pixel-major stack
+// padded to evd_fast_padded_bands(bands) samples per pixel (0 = not eligible).
+int evd_fast_padded_bands(int bands);
+bool evd_fast_supported(const EvdArgs& a);
+cudaError_t launch_evd_fast(const EvdArgs& a, cudaStream_t st);
 
 // ---- microbench.cu --------------------------------------------------------------------
 cudaError_t measure_fp32_peak(cudaStream_t st, double* tflops);
