@@ -411,7 +411,10 @@ int fringe_evd_block_device(fringe_ctx* ctx, const float* slc, const uint32_t* w
     const bool generic = getenv("FRINGE_EVD_GENERIC") != nullptr;      // debug switch
     if (!generic && variant == FRINGE_VARIANT_EVD && method != FRINGE_EVD_MLE && fringe::evd_fast_padded_bands(bands) > 0)
         NP = fringe::evd_fast_padded_bands(bands);
-    CU(ctx->zpix.ensure(npix * NP * sizeof(float2)));
+    // one extra, all-zero sample vector behind the image: the register-blocked kernel points
+    // exhausted / out-of-block SHP slots at it instead of branching
+    CU(ctx->zpix.ensure((npix + 1) * NP * sizeof(float2)));
+    CU(cudaMemsetAsync((float2*)ctx->zpix.p + npix * NP, 0, NP * sizeof(float2), st));
     CU(ctx->stats.ensure(4 * sizeof(unsigned long long)));
     CU(cudaMemsetAsync(ctx->stats.p, 0, 4 * sizeof(unsigned long long), st));
     CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_TRANSPOSE][0], st));

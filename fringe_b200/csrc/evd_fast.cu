@@ -9,53 +9,88 @@
 //               (lanes 0-14 pixel 0, 16-30 pixel 1).  Per SHP a lane loads the 2B samples its
 //               block needs (16-byte loads from the pixel-major stack, served by L1: adjacent
 //               pixels share almost all of their window) and issues B*B complex FMAs, i.e.
-//               3 complex MACs per loaded sample instead of 0.5 in the generic kernel.  The
-//               SHP loop walks the set bits of the window mask (ffs / clear-lowest), so unset
-//               neighbours cost nothing.
-//   eigen       The normalised coherence is parked in shared memory as a packed triangle
-//               (3.7 kB per pixel at N=30) and re-read row-per-lane into registers; the power
-//               iteration then needs only the broadcast vector from shared memory (15
-//               LDS.128 per 120 FMAs).  Residual / normalisation reductions run every 4th
-//               iteration.
+//               3 complex MACs per loaded sample.  The SHP loop walks the set bits of the
+//               window mask (ffs / clear-lowest) with the next SHP's samples prefetched while
+//               the current one is accumulated; exhausted or out-of-block bits point at an
+//               all-zero sample row, so the loop body is branch-free.
+//   eigen       The normalised coherence matrices of both pixels are parked in shared memory
+//               (full Hermitian, row stride = padded order) and re-read row-per-lane into
+//               registers; the power iteration then needs only the broadcast vector from
+//               shared memory (15 LDS.128 per 120 FMAs, 8 independent FMA chains).
+//               Residual / normalisation reductions run every 4th iteration.
 //   epilogue    phase reference, compressed SLC and temporal coherence from registers.
+//
+// Code size matters here: the first version unrolled everything and reached 92 kB of SASS,
+// i.e. 3x the instruction cache, and ncu showed "no instruction" as the top stall.  The hot
+// loops below are rolled (#pragma unroll 1) around fully unrolled bodies.
 #include <math_constants.h>
-
-#include <cstdio>
 
 #include "common.cuh"
 
 namespace fringe {
 
 #define FULLMASK 0xffffffffu
-#ifdef FRINGE_DEBUG_TRACE
-#define TRACE(...) do { if ((lane & 15) == 0 && blockIdx.x == 0) printf(__VA_ARGS__); } while (0)
-#else
-#define TRACE(...) do {} while (0)
-#endif
 
-__device__ __forceinline__ float wsum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
-    return v;
+// single-instruction MUFU approximations (about 1 ulp); arguments here are sums of squares of
+// O(1) quantities, far from the denormal range the IEEE-exact expansions would guard
+__device__ __forceinline__ float fast_rsqrt(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 template <int B>
 struct FastCfg {
     static constexpr int NB = 5;
     static constexpr int NPAD = NB * B;                 // padded matrix order (zpix row length)
-    static constexpr int TRI = NPAD * (NPAD + 1) / 2;   // packed upper triangle incl. diagonal
     static constexpr int WARPS = 4;
-    // per warp: two packed triangles, two broadcast vectors (double buffered), powers
+    // per warp: two full matrices, two broadcast vectors (double buffered), powers
+    static constexpr int MAT = NPAD * NPAD;             // float2 elements per matrix
     static constexpr int SMEM_PER_WARP =
-        (((2 * TRI + 2 * 32) * (int)sizeof(float2) + 2 * NPAD * (int)sizeof(float)) + 15) & ~15;
+        (((2 * MAT + 2 * 32) * (int)sizeof(float2) + 2 * NPAD * (int)sizeof(float)) + 15) & ~15;
 };
 
-__device__ __forceinline__ int tri_index(int i, int j, int n) {   // i <= j
-    return i * n - ((i * (i - 1)) >> 1) + (j - i);
+// One SHP's operands for a lane's block: rows B*bi.. and columns B*bj.. of the sample vector.
+template <int B>
+struct Operands {
+    float2 a[B], b[B];
+    __device__ __forceinline__ void load(const float2* __restrict__ zq, int oa, int ob) {
+        if (B % 2 == 0) {
+            const float4* pa = reinterpret_cast<const float4*>(zq + oa);
+            const float4* pb = reinterpret_cast<const float4*>(zq + ob);
+#pragma unroll
+            for (int i = 0; i < B / 2; ++i) {
+                const float4 va = __ldg(pa + i), vb = __ldg(pb + i);
+                a[2 * i] = make_float2(va.x, va.y); a[2 * i + 1] = make_float2(va.z, va.w);
+                b[2 * i] = make_float2(vb.x, vb.y); b[2 * i + 1] = make_float2(vb.z, vb.w);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < B; ++i) { a[i] = __ldg(zq + oa + i); b[i] = __ldg(zq + ob + i); }
+        }
+    }
+};
+
+template <int B>
+__device__ __forceinline__ void accumulate(float2 (&acc)[B][B], const Operands<B>& op) {
+#pragma unroll
+    for (int i = 0; i < B; ++i)
+#pragma unroll
+        for (int j = 0; j < B; ++j) {      // acc += a_i * conj(b_j)
+            acc[i][j].x = fmaf(op.a[i].x, op.b[j].x, acc[i][j].x);
+            acc[i][j].x = fmaf(op.a[i].y, op.b[j].y, acc[i][j].x);
+            acc[i][j].y = fmaf(op.a[i].y, op.b[j].x, acc[i][j].y);
+            acc[i][j].y = fmaf(-op.a[i].x, op.b[j].y, acc[i][j].y);
+        }
 }
 
 template <int B>
-__global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
+__global__ void __launch_bounds__(128, 2) k_evd_fast(const EvdArgs a) {
     typedef FastCfg<B> Cfg;
     constexpr int NPAD = Cfg::NPAD;
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -63,27 +98,49 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
     const int grp = lane >> 4, l = lane & 15;
     const int N = a.bands;                      // <= NPAD, zpix rows are zero padded to NPAD
 
-    unsigned char* base = s_raw + (size_t)warp * Cfg::SMEM_PER_WARP;
-    float2* s_tri = reinterpret_cast<float2*>(base);                       // [2][TRI]
-    float2* s_vec = s_tri + 2 * Cfg::TRI;                                  // [2][32]
+    // CTA-wide table: window bit index -> (dy, dx)
+    short2* s_off = reinterpret_cast<short2*>(s_raw);
+    const int WX = 2 * a.Nx + 1, W = WX * (2 * a.Ny + 1), center = a.Ny * WX + a.Nx;
+    for (int f = threadIdx.x; f < a.nulong * 32; f += blockDim.x) {
+        const int fy = f / WX;
+        s_off[f] = (f < W) ? make_short2((short)(fy - a.Ny), (short)(f - fy * WX - a.Nx))
+                           : make_short2((short)-30000, (short)-30000);   // never in bounds
+    }
+    __syncthreads();
+    const int lut_bytes = ((a.nulong * 32 * (int)sizeof(short2)) + 15) & ~15;
+
+    unsigned char* base = s_raw + lut_bytes + (size_t)warp * Cfg::SMEM_PER_WARP;
+    float2* s_mat = reinterpret_cast<float2*>(base);                       // [2][NPAD][NPAD]
+    float2* s_vec = s_mat + 2 * Cfg::MAT;                                  // [2][32]
     float* s_pw = reinterpret_cast<float*>(s_vec + 64);                    // [2][NPAD]
 
     // block coordinates of this lane inside its pixel group
     int bi = 0, bj = 0;
     {
-        int k = l;
-        bi = 0;
-        int rowlen = 5;
+        int k = l, rowlen = 5;
         while (bi < 4 && k >= rowlen) { k -= rowlen; ++bi; --rowlen; }
         bj = bi + k;
     }
     const bool blk_active = (l < 15);
+    const int oa = B * bi, ob = B * bj;
 
-    const int WX = 2 * a.Nx + 1, center = a.Ny * WX + a.Nx;
     const int k0 = a.mini_stack_count - 1;
     const bool isstbas = (a.method == 2);
     const int BW = a.bandwidth;
+    // bit j set: the pair (lane, j) enters the temporal-coherence sum (j > lane, inside the
+    // matrix and, for STBAS, inside the band)
+    uint32_t usemask = 0u;
+    for (int j = 0; j < N; ++j)
+        if (j > lane && (!isstbas || (j - lane) <= BW)) usemask |= (1u << j);
+    // number of (i<j) pairs in the temporal-coherence sum (evd.cpp:773-784)
+    float inv_pairs;
+    {
+        int cnt = 0;
+        for (int i = 0; i < N; ++i) cnt += isstbas ? min(BW, N - 1 - i) : (N - 1 - i);
+        inv_pairs = 1.0f / (float)cnt;
+    }
     const long npix_block = (long)a.cols * a.lines;
+    const float2* zero_row = a.zpix + npix_block * NPAD;    // one all-zero sample vector
 
     const int pairs_per_row = (a.cols + 1) >> 1;
     const long total_pairs = (long)a.n_lines * pairs_per_row;
@@ -92,6 +149,7 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
     const long end = min(total_pairs, beg + chunk);
     unsigned long long st_pix = 0, st_it = 0, st_cap = 0;
 
+#pragma unroll 1
     for (long pr = beg + warp; pr < end; pr += Cfg::WARPS) {
         const int row = a.first_line + (int)(pr / pairs_per_row);
         const int col0 = 2 * (int)(pr % pairs_per_row);
@@ -108,78 +166,69 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
         int npix = 0;
         bool center_on = false;
         if (pix_exists) center_on = (__ldg(&a.wts[p * a.nulong + (center >> 5)]) >> (center & 31)) & 1u;
+#pragma unroll 1
         for (int w = 0; w < a.nulong; ++w) {
             uint32_t m = (pix_exists && center_on && blk_active) ? __ldg(&a.wts[p * a.nulong + w]) : 0u;
             // uniform trip count: the longer of the two pixels' bit lists in this word
             const int trips = __reduce_max_sync(FULLMASK, __popc(m));
-#pragma unroll 1
-            for (int t = 0; t < trips; ++t) {
+            // address of the next SHP's sample vector (zero row when exhausted / outside block)
+            auto next_ptr = [&]() -> const float2* {
                 const bool on = (m != 0u);
                 const int f = w * 32 + (on ? (__ffs(m) - 1) : 0);
                 m &= (m - 1u);
-                const int fy = f / WX;
-                const int yy = row + fy - a.Ny, xx = mycol + (f - fy * WX) - a.Nx;
+                const short2 d = s_off[f];
+                const int yy = row + d.x, xx = mycol + d.y;
                 const bool inb = on && yy >= 0 && yy < a.lines && xx >= 0 && xx < a.cols;
                 npix += inb ? 1 : 0;
-                float2 za[B], zb[B];
-                if (inb) {
-                    const float2* zq = a.zpix + ((long)yy * a.cols + xx) * NPAD;
-                    if (B % 2 == 0) {
-                        const float4* pa = reinterpret_cast<const float4*>(zq + B * bi);
-                        const float4* pb = reinterpret_cast<const float4*>(zq + B * bj);
-#pragma unroll
-                        for (int i = 0; i < B / 2; ++i) {
-                            const float4 va = __ldg(pa + i), vb = __ldg(pb + i);
-                            za[2 * i] = make_float2(va.x, va.y); za[2 * i + 1] = make_float2(va.z, va.w);
-                            zb[2 * i] = make_float2(vb.x, vb.y); zb[2 * i + 1] = make_float2(vb.z, vb.w);
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < B; ++i) { za[i] = __ldg(zq + B * bi + i); zb[i] = __ldg(zq + B * bj + i); }
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < B; ++i) { za[i] = make_float2(0.f, 0.f); zb[i] = make_float2(0.f, 0.f); }
-                }
-#pragma unroll
-                for (int i = 0; i < B; ++i)
-#pragma unroll
-                    for (int j = 0; j < B; ++j) {
-                        acc[i][j].x = fmaf(za[i].x, zb[j].x, acc[i][j].x);
-                        acc[i][j].x = fmaf(za[i].y, zb[j].y, acc[i][j].x);
-                        acc[i][j].y = fmaf(za[i].y, zb[j].x, acc[i][j].y);
-                        acc[i][j].y = fmaf(-za[i].x, zb[j].y, acc[i][j].y);
-                    }
+                return inb ? a.zpix + ((long)yy * a.cols + xx) * NPAD : zero_row;
+            };
+            // two-stage software pipeline: while one SHP is accumulated the next one's samples
+            // are already in flight (exhausted lists read the zero row, so no tail handling)
+            Operands<B> opA, opB;
+            if (trips > 0) opA.load(next_ptr(), oa, ob);
+#pragma unroll 1
+            for (int t = 0; t < trips; t += 2) {
+                opB.load(next_ptr(), oa, ob);
+                accumulate<B>(acc, opA);
+                opA.load(next_ptr(), oa, ob);
+                accumulate<B>(acc, opB);
             }
         }
-#ifdef FRINGE_DEBUG_TRACE
-        if ((lane & 15) == 0) printf("b%d w%d l%d pair %ld row %d col0 %d npix %d center %d\n", blockIdx.x, warp, lane, pr, row, col0, npix, (int)center_on);
-#endif
-        // group-uniform: enough SHPs?  (evd.cpp:566 hard-codes 2)
-        const int npix_grp = __shfl_sync(FULLMASK, npix, grp << 4);   // collective first: no short-circuit around it
+        // group-uniform: enough SHPs?  (evd.cpp:566 hard-codes 2).  Collective first: no
+        // short-circuit evaluation around a warp shuffle.
+        const int npix_grp = __shfl_sync(FULLMASK, npix, grp << 4);
         const bool solve_me = pix_exists && center_on && (npix_grp >= 2);
 
         // ------------------------- coherence (evd.cpp:569-582) --------------------------
         __syncwarp();
         if (blk_active && bi == bj) {
 #pragma unroll
-            for (int i = 0; i < B; ++i) s_pw[grp * NPAD + B * bi + i] = sqrtf(acc[i][i].x);
+            for (int i = 0; i < B; ++i) {
+                const int t = oa + i;
+                // padded bands get +inf so that their scaled entries come out as exact zeros
+                s_pw[grp * NPAD + t] = (t < N) ? sqrtf(acc[i][i].x) : CUDART_INF_F;
+            }
         }
         __syncwarp();
         if (blk_active) {
-            float pa[B], pb[B];
+            float ia[B], ib[B];
 #pragma unroll
-            for (int i = 0; i < B; ++i) { pa[i] = s_pw[grp * NPAD + B * bi + i]; pb[i] = s_pw[grp * NPAD + B * bj + i]; }
-            float2* tri = s_tri + grp * Cfg::TRI;
+            for (int i = 0; i < B; ++i) { ia[i] = fast_rcp(s_pw[grp * NPAD + oa + i]); ib[i] = fast_rcp(s_pw[grp * NPAD + ob + i]); }
+            float2* mat = s_mat + grp * Cfg::MAT;
+            float2* up = mat + oa * NPAD + ob;            // block (bi,bj)
+            float2* lo = mat + ob * NPAD + oa;            // its mirror
+            const bool diag = (bi == bj);
 #pragma unroll
             for (int i = 0; i < B; ++i)
 #pragma unroll
                 for (int j = 0; j < B; ++j) {
-                    const int gi = B * bi + i, gj = B * bj + j;
-                    if (gi < gj && gj < N) {
-                        const float inv = 1.0f / (pa[i] * pb[j]);
-                        tri[tri_index(gi, gj, N)] = make_float2(acc[i][j].x * inv, acc[i][j].y * inv);
+                    const float s = ia[i] * ib[j];
+                    const float2 c = make_float2(acc[i][j].x * s, acc[i][j].y * s);
+                    if (!diag || j > i) {                 // off-diagonal entry and its mirror
+                        up[i * NPAD + j] = c;
+                        lo[j * NPAD + i] = make_float2(c.x, -c.y);
                     }
+                    if (j == i && diag) up[i * NPAD + i] = make_float2((oa + i < N) ? 1.f : 0.f, 0.f);
                 }
         }
         __syncwarp();
@@ -194,33 +243,39 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
             float2 o = make_float2(0.f, 0.f);
             float tc = 0.f;
             float2 cmp = make_float2(0.f, 0.f);
-            TRACE("w%d l%d g%d solve %d\n", warp, lane, g, (int)solve_g);
             if (solve_g) {
                 ++st_pix;
-                const float2* tri = s_tri + g * Cfg::TRI;
-                const int r = lane;
+                const int r = (lane < NPAD) ? lane : (NPAD - 1);
                 float2 c[NPAD];
+                if (NPAD % 2 == 0) {
+                    const float4* rowp = reinterpret_cast<const float4*>(s_mat + g * Cfg::MAT + r * NPAD);
 #pragma unroll
-                for (int j = 0; j < NPAD; ++j) {
-                    float2 v = make_float2(0.f, 0.f);
-                    if (r < N && j < N) {
-                        if (j == r) v = make_float2(1.f, 0.f);
-                        else if (j > r) v = tri[tri_index(r, j, N)];
-                        else { v = tri[tri_index(j, r, N)]; v.y = -v.y; }
-                        if (isstbas && abs(j - r) > BW) v = make_float2(0.f, 0.f);
+                    for (int j = 0; j < NPAD; j += 2) {
+                        const float4 v = rowp[j >> 1];
+                        c[j] = make_float2(v.x, v.y); c[j + 1] = make_float2(v.z, v.w);
                     }
-                    c[j] = v;
+                } else {
+                    const float2* rp2 = s_mat + g * Cfg::MAT + r * NPAD;
+#pragma unroll
+                    for (int j = 0; j < NPAD; ++j) c[j] = rp2[j];
                 }
-                // start vector: column k0 of C
-                float2 x = make_float2(0.f, 0.f);
-                if (r < N) {
-                    if (r == k0) x = make_float2(1.f, 0.f);
-                    else if (r < k0) x = tri[tri_index(r, k0, N)];
-                    else { x = tri[tri_index(k0, r, N)]; x.y = -x.y; }
-                    if (isstbas && abs(k0 - r) > BW) x = make_float2(0.f, 0.f);
+                // rows >= N of the padded matrix are exact zeros; only lanes beyond the padded
+                // order (which re-read the last row) have to be silenced
+                const float live = (lane < NPAD) ? 1.f : 0.f;
+                if (isstbas) {                                   // evd.cpp:695-706 band limit
+#pragma unroll
+                    for (int j = 0; j < NPAD; ++j)
+                        if (abs(j - lane) > BW) c[j] = make_float2(0.f, 0.f);
                 }
+                // start vector: column k0 of C  (= conj of row k0; entry k0 is 1)
+                float2 x;
                 {
-                    const float n2 = wsum(x.x * x.x + x.y * x.y);
+                    const float2 v = s_mat[g * Cfg::MAT + k0 * NPAD + r];
+                    const float keep = (isstbas && abs(k0 - lane) > BW) ? 0.f : live;
+                    x = make_float2(v.x * keep, -v.y * keep);
+                    float n2 = x.x * x.x + x.y * x.y;
+#pragma unroll
+                    for (int s = 16; s > 0; s >>= 1) n2 += __shfl_xor_sync(FULLMASK, n2, s);
                     const float sc = rsqrtf(n2);
                     x.x *= sc; x.y *= sc;
                 }
@@ -229,53 +284,51 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
                 bool conv = false;
                 const int kMaxIter = 1000;
                 const float tol2 = 4.0e-12f;
-                while (it < kMaxIter && !conv) {
+#pragma unroll 1
+                for (; it < kMaxIter; ++it) {
+                    float2* xv = s_vec + buf * 32;
+                    buf ^= 1;
+                    xv[lane] = x;
+                    __syncwarp();
+                    // y = C x with 8 independent FMA chains
+                    float r0 = 0.f, r1 = 0.f, r2a = 0.f, r3 = 0.f, i0 = 0.f, i1 = 0.f, i2 = 0.f, i3 = 0.f;
+                    const float4* xv4 = reinterpret_cast<const float4*>(xv);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        float2* xv = s_vec + buf * 32;
-                        buf ^= 1;
-                        xv[lane] = x;
-                        __syncwarp();
-                        float yr = 0.f, yi = 0.f;
-                        const float4* xv4 = reinterpret_cast<const float4*>(xv);
+                    for (int j = 0; j + 1 < NPAD; j += 2) {
+                        const float4 q = xv4[j >> 1];
+                        r0 = fmaf(c[j].x, q.x, r0); r1 = fmaf(-c[j].y, q.y, r1);
+                        i0 = fmaf(c[j].x, q.y, i0); i1 = fmaf(c[j].y, q.x, i1);
+                        r2a = fmaf(c[j + 1].x, q.z, r2a); r3 = fmaf(-c[j + 1].y, q.w, r3);
+                        i2 = fmaf(c[j + 1].x, q.w, i2); i3 = fmaf(c[j + 1].y, q.z, i3);
+                    }
+                    if (NPAD % 2 == 1) {
+                        const float2 q = xv[NPAD - 1];
+                        r0 = fmaf(c[NPAD - 1].x, q.x, r0); r1 = fmaf(-c[NPAD - 1].y, q.y, r1);
+                        i0 = fmaf(c[NPAD - 1].x, q.y, i0); i1 = fmaf(c[NPAD - 1].y, q.x, i1);
+                    }
+                    const float yr = ((r0 + r1) + (r2a + r3)) * live, yi = ((i0 + i1) + (i2 + i3)) * live;
+                    if ((it & 3) != 3) { x.x = yr * inv_lam; x.y = yi * inv_lam; }
+                    else {
+                        // Rayleigh quotient, residual, renormalisation
+                        float xy = x.x * yr + x.y * yi, xx = x.x * x.x + x.y * x.y;
 #pragma unroll
-                        for (int j = 0; j < NPAD; j += 2) {
-                            if (j + 1 < NPAD) {
-                                const float4 q = xv4[j >> 1];
-                                yr = fmaf(c[j].x, q.x, yr); yr = fmaf(-c[j].y, q.y, yr);
-                                yi = fmaf(c[j].x, q.y, yi); yi = fmaf(c[j].y, q.x, yi);
-                                yr = fmaf(c[j + 1].x, q.z, yr); yr = fmaf(-c[j + 1].y, q.w, yr);
-                                yi = fmaf(c[j + 1].x, q.w, yi); yi = fmaf(c[j + 1].y, q.z, yi);
-                            } else {
-                                const float2 q = xv[j];
-                                yr = fmaf(c[j].x, q.x, yr); yr = fmaf(-c[j].y, q.y, yr);
-                                yi = fmaf(c[j].x, q.y, yi); yi = fmaf(c[j].y, q.x, yi);
-                            }
+                        for (int s = 16; s > 0; s >>= 1) {
+                            xy += __shfl_xor_sync(FULLMASK, xy, s);
+                            xx += __shfl_xor_sync(FULLMASK, xx, s);
                         }
-                        ++it;
-                        if (u < 3) { x.x = yr * inv_lam; x.y = yi * inv_lam; }
-                        else {
-                            // Rayleigh quotient, residual, renormalisation
-                            float xy = x.x * yr + x.y * yi, xx = x.x * x.x + x.y * x.y;
+                        lam = xy / xx;
+                        const float rx = yr - lam * x.x, ry = yi - lam * x.y;
+                        float rr2 = rx * rx + ry * ry, y2 = yr * yr + yi * yi;
 #pragma unroll
-                            for (int s = 16; s > 0; s >>= 1) {
-                                xy += __shfl_xor_sync(FULLMASK, xy, s);
-                                xx += __shfl_xor_sync(FULLMASK, xx, s);
-                            }
-                            lam = xy / xx;
-                            const float rx = yr - lam * x.x, ry = yi - lam * x.y;
-                            float r2 = rx * rx + ry * ry, y2 = yr * yr + yi * yi;
-#pragma unroll
-                            for (int s = 16; s > 0; s >>= 1) {
-                                r2 += __shfl_xor_sync(FULLMASK, r2, s);
-                                y2 += __shfl_xor_sync(FULLMASK, y2, s);
-                            }
-                            const float sc = rsqrtf(y2);
-                            x.x = yr * sc; x.y = yi * sc;
-                            inv_lam = 1.0f / lam;
-                            conv = (r2 <= tol2 * lam * lam * xx);
-                            TRACE("w%d l%d g%d it %d lam %g r2 %g xx %g conv %d\n", warp, lane, g, it, lam, r2, xx, (int)conv);
+                        for (int s = 16; s > 0; s >>= 1) {
+                            rr2 += __shfl_xor_sync(FULLMASK, rr2, s);
+                            y2 += __shfl_xor_sync(FULLMASK, y2, s);
                         }
+                        const float sc = rsqrtf(y2);
+                        x.x = yr * sc; x.y = yi * sc;
+                        inv_lam = 1.0f / lam;
+                        conv = (rr2 <= tol2 * lam * lam * xx);
+                        if (conv) { ++it; break; }
                     }
                 }
                 st_it += it;
@@ -288,20 +341,20 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
                     xv[lane] = x;
                     __syncwarp();
                     const float2 ref = xv[k0];
-                    if (r < N) {
+                    {
                         float ux = x.x * ref.x + x.y * ref.y, uy = x.y * ref.x - x.x * ref.y;
                         const float mm = ux * ux + uy * uy;
-                        if (mm == 0.f) {
+                        if (mm == 0.f) {                  // arg(0) = 0 in the reference
                             const float rr = rsqrtf(ref.x * ref.x + ref.y * ref.y);
                             ux = ref.x * rr; uy = -ref.y * rr;
-                        } else { const float rr = rsqrtf(mm); ux *= rr; uy *= rr; }
-                        if (r == k0) { ux = 1.f; uy = 0.f; }
-                        o = make_float2(ux, uy);
+                        } else { const float rr = fast_rsqrt(mm); ux *= rr; uy *= rr; }
+                        if (lane == k0) { ux = 1.f; uy = 0.f; }
+                        o = make_float2(ux * live, uy * live);
                     }
                     // ---------------- compressed SLC (evd.cpp:755-762) ------------------
                     float cr = 0.f, ci = 0.f;
-                    if (r < N && r >= k0) {
-                        const float2 z = __ldg(&a.zpix[pg * NPAD + r]);
+                    if (lane < N && lane >= k0) {
+                        const float2 z = __ldg(&a.zpix[pg * NPAD + lane]);
                         cr = z.x * o.x + z.y * o.y;
                         ci = z.y * o.x - z.x * o.y;
                     }
@@ -311,20 +364,23 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
                     ov[lane] = o;
                     __syncwarp();
                     float wr = 0.f, wi = 0.f;
-                    int cnt = 0;
+                    const float4* ov4 = reinterpret_cast<const float4*>(ov);
 #pragma unroll
                     for (int j = 0; j < NPAD; ++j) {
-                        const bool use = (j > r) && (j < N) && (r < N) && (!isstbas || (j - r) <= BW);
-                        if (use) {
-                            // c[j] may have been zeroed by the STBAS band limit only outside the band
-                            const float m2 = c[j].x * c[j].x + c[j].y * c[j].y;
-                            float ex = 1.f, ey = 0.f;
-                            if (m2 > 0.f) { const float rr = rsqrtf(m2); ex = c[j].x * rr; ey = c[j].y * rr; }
-                            const float2 oj = ov[j];
-                            wr += ex * oj.x - ey * oj.y;
-                            wi += ex * oj.y + ey * oj.x;
-                            ++cnt;
-                        }
+                        // pairs (lane, j) with j > lane, inside the matrix and (STBAS) the band;
+                        // e = C_ij / |C_ij| (arg(0) = 0 as in the reference)
+                        const bool use = (usemask >> j) & 1u;
+                        const float m2 = fmaf(c[j].x, c[j].x, c[j].y * c[j].y);
+                        const float rr = use ? fast_rsqrt(m2) : 0.f;
+                        const float ex = (m2 > 0.f) ? c[j].x * rr : (use ? 1.f : 0.f);
+                        const float ey = (m2 > 0.f) ? c[j].y * rr : 0.f;
+                        float2 oj;
+                        if (NPAD % 2 == 0) {
+                            const float4 q = ov4[j >> 1];
+                            oj = (j & 1) ? make_float2(q.z, q.w) : make_float2(q.x, q.y);
+                        } else oj = ov[j];
+                        wr = fmaf(ex, oj.x, wr); wr = fmaf(-ey, oj.y, wr);
+                        wi = fmaf(ex, oj.y, wi); wi = fmaf(ey, oj.x, wi);
                     }
                     // conj(o_r) * w_r
                     float sr = o.x * wr + o.y * wi, si = o.x * wi - o.y * wr;
@@ -335,8 +391,7 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
                         cr += __shfl_xor_sync(FULLMASK, cr, s);
                         ci += __shfl_xor_sync(FULLMASK, ci, s);
                     }
-                    cnt = __reduce_add_sync(FULLMASK, cnt);
-                    tc = sqrtf(sr * sr + si * si) / (float)cnt;
+                    tc = sqrtf(sr * sr + si * si) * inv_pairs;
                     const float invn = 1.0f / (float)(N - a.mini_stack_count + 1);
                     cmp = make_float2(cr * invn, ci * invn);
                 }
@@ -346,9 +401,6 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
             __syncwarp();
         }
     }
-#ifdef FRINGE_DEBUG_TRACE
-    if (lane == 0) printf("b%d w%d done (pairs %ld..%ld)\n", blockIdx.x, warp, beg, end);
-#endif
     if (a.stats && lane == 0) {
         atomicAdd(&a.stats[0], st_pix);
         atomicAdd(&a.stats[1], st_it);
@@ -359,7 +411,8 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
 template <int B>
 static cudaError_t launch_fast_t(const EvdArgs& a, cudaStream_t st) {
     typedef FastCfg<B> Cfg;
-    const size_t smem = (size_t)Cfg::SMEM_PER_WARP * Cfg::WARPS;
+    const size_t lut = ((size_t)a.nulong * 32 * sizeof(short2) + 15) & ~(size_t)15;
+    const size_t smem = lut + (size_t)Cfg::SMEM_PER_WARP * Cfg::WARPS;
     cudaError_t e = cudaFuncSetAttribute(k_evd_fast<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int dev = 0, nsm = 148, occ = 1;
