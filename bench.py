@@ -168,11 +168,9 @@ def main():
 
     lines, cols = args.lines, args.cols
     # row partition with halos: rank g owns rows [r0, r1), reads [b0, b1)
-    r0 = (lines * rank) // world
-    r1 = (lines * (rank + 1)) // world
-    b0, b1 = max(0, r0 - NY), min(lines, r1 + NY)
+    from fringe_b200.partition import row_tile
+    r0, r1, b0, b1, first_line, n_lines = row_tile(lines, rank, world, NY)
     blines = b1 - b0
-    first_line, n_lines = r0 - b0, r1 - r0
     my_pixels = n_lines * cols
 
     ctx = Context(local)

@@ -326,13 +326,22 @@ __device__ float power_iteration(const WarpSmem& w, int n, int ldc, int lane, in
 // C FP64 in w.Cd) by inverse iteration with Cholesky-certified shifts.  Returns false when no
 // positive-definite shifted matrix could be factored (caller maps that to the sentinel / the
 // EVD fallback).  v[] = unit eigenvector (lane rows), *lam = eigenvalue.
+//
+// MODE 0: M = Ainv o C                       (MLE, evd.cpp:655-665)
+// MODE 1: M = n*I - C  (C PSD, trace n)      -> its smallest eigenvector is the DOMINANT
+//         eigenvector of C: the FP64 route for the EVD fallback of phase_link.cpp:586-600,
+//         *lam then receives the eigenvalue of C.
+template <int MODE>
 __device__ bool smallest_eigen_mle(const WarpSmem& w, int n, int ldc, int ld, int lane,
                                    double2 v[2], double* lam) {
-    // scale = max diagonal of M (diag(C) = 1 so diag(M) = diag(Ainv))
-    double dmax = 0.0;
-    for (int h = 0; h < 2; ++h) { const int i = lane + 32 * h; if (i < n) dmax = fmax(dmax, fabs(w.A[i * ld + i])); }
+    // scale = max diagonal of M (diag(C) = 1 so diag(Ainv o C) = diag(Ainv))
+    double dmax = (double)n;
+    if (MODE == 0) {
+        dmax = 0.0;
+        for (int h = 0; h < 2; ++h) { const int i = lane + 32 * h; if (i < n) dmax = fmax(dmax, fabs(w.A[i * ld + i])); }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(FULL, dmax, o));
+        for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(FULL, dmax, o));
+    }
 
     auto assemble = [&](double sigma) {
         for (int h = 0; h < 2; ++h) {
@@ -340,9 +349,9 @@ __device__ bool smallest_eigen_mle(const WarpSmem& w, int n, int ldc, int ld, in
             if (i < n) {
                 for (int j = 0; j <= i; ++j) {
                     const double2 c = w.Cd[i * ld + j];
-                    const double a = w.A[i * ld + j];
+                    const double a = (MODE == 0) ? w.A[i * ld + j] : -1.0;
                     double2 m = make_double2(a * c.x, a * c.y);
-                    if (j == i) { m.x -= sigma; m.y = 0.0; }
+                    if (j == i) { m.x += ((MODE == 0) ? 0.0 : (double)n) - sigma; m.y = 0.0; }
                     w.F[i * ld + j] = m;
                 }
             }
@@ -359,9 +368,10 @@ __device__ bool smallest_eigen_mle(const WarpSmem& w, int n, int ldc, int ld, in
             if (i < n) {
                 for (int j = 0; j < n; ++j) {
                     const double2 c = w.Cd[i * ld + j];
-                    const double a = w.A[i * ld + j];
+                    const double a = (MODE == 0) ? w.A[i * ld + j] : -1.0;
                     const double2 xj = w.xd[j];
-                    const double mr = a * c.x, mi = (j == i) ? 0.0 : a * c.y;
+                    const double mr = a * c.x + ((MODE == 1 && j == i) ? (double)n : 0.0);
+                    const double mi = (j == i) ? 0.0 : a * c.y;
                     s.x += mr * xj.x - mi * xj.y;
                     s.y += mr * xj.y + mi * xj.x;
                 }
@@ -387,6 +397,7 @@ __device__ bool smallest_eigen_mle(const WarpSmem& w, int n, int ldc, int ld, in
     for (int h = 0; h < 2; ++h) {
         const int i = lane + 32 * h;
         x[h] = (i < n) ? make_double2(1.0, 0.0) : make_double2(0.0, 0.0);
+        if (MODE == 1 && i < n) x[h] = v[h];          // caller-provided start (a column of C)
     }
     double rho = 0.0, res = 0.0;
     int since_shift = 0;
@@ -421,7 +432,7 @@ __device__ bool smallest_eigen_mle(const WarpSmem& w, int n, int ldc, int ld, in
         }
     }
     v[0] = x[0]; v[1] = x[1];
-    *lam = rho;
+    *lam = (MODE == 0) ? rho : (double)n - rho;
     return true;
 }
 
@@ -600,7 +611,7 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
                                 chol_inverse_r(w.A, reinterpret_cast<double*>(w.F), w.dinv, N, ld, lane);
                                 double2 vd[2];
                                 double lam = 0.0;
-                                if (!smallest_eigen_mle(w, N, ldc, ld, lane, vd, &lam)) {
+                                if (!smallest_eigen_mle<0>(w, N, ldc, ld, lane, vd, &lam)) {
                                     if (a.variant == 0) { tc = -6.f; failed = true; }
                                     else run_evd = true;
                                 } else if (a.variant == 0 && lam < 1.0e-6) { tc = -7.f; failed = true; }
@@ -632,13 +643,39 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
                         }
                         __syncwarp();
                     }
-                    int iters = 0;
-                    bool capped = false;
-                    const float lam = power_iteration(w, N, ldc, lane, k0, vf, &iters, &capped);
-                    st_it += iters;
-                    st_cap += capped ? 1 : 0;
-                    if (a.variant == 0 && lam < 1.0e-6f) { tc = -7.f; }
-                    else have_vec = true;
+                    bool done = false;
+                    if (DP && a.variant == 1) {
+                        // phase_link's EVD fallback in FP64 (the exact covariance is already in
+                        // w.Cd): certified inverse iteration on n*I - C
+                        double2 vd[2];
+                        for (int h = 0; h < 2; ++h) {
+                            const int r = lane + 32 * h;
+                            vd[h] = (r < N) ? w.Cd[r * ld + k0] : make_double2(0.0, 0.0);
+                        }
+                        double lamd = 0.0;
+                        if (smallest_eigen_mle<1>(w, N, ldc, ld, lane, vd, &lamd)) {
+                            __syncwarp();
+                            for (int h = 0; h < 2; ++h) { const int r = lane + 32 * h; if (r < N) w.xd[r] = vd[h]; }
+                            __syncwarp();
+                            const double2 ref = w.xd[k0];
+                            const double rn = 1.0 / fmax(hypot(ref.x, ref.y), 1e-300);
+                            for (int h = 0; h < 2; ++h) {
+                                const double2 u = cmulc(vd[h], make_double2(ref.x * rn, ref.y * rn));
+                                vf[h] = make_float2((float)u.x, (float)u.y);
+                            }
+                            have_vec = true;
+                            done = true;
+                        }
+                    }
+                    if (!done) {
+                        int iters = 0;
+                        bool capped = false;
+                        const float lam = power_iteration(w, N, ldc, lane, k0, vf, &iters, &capped);
+                        st_it += iters;
+                        st_cap += capped ? 1 : 0;
+                        if (a.variant == 0 && lam < 1.0e-6f) { tc = -7.f; }
+                        else have_vec = true;
+                    }
                 }
             }
         }
