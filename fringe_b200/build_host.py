@@ -1,0 +1,33 @@
+"""Builds the C++ host side: libfringe_host.so (block drivers + raster I/O over the C ABI) and the
+three Python extension modules nmaplib / evdlib / phase_linklib (pybind11), all in-tree."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sysconfig
+
+import pybind11
+
+from .build import CSRC, HERE, LIBDIR, HOST_CXX, _newer, _run
+
+HOST = os.path.join(CSRC, "host")
+BINDINGS = os.path.join(HERE, "bindings")
+HOST_LIB = os.path.join(LIBDIR, "libfringe_host.so")
+
+
+def build(force: bool = False) -> None:
+    os.makedirs(BINDINGS, exist_ok=True)
+    hdrs = [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".hpp")]
+    common = ["-O2", "-std=c++17", "-fPIC", "-pthread", "-Wall"]
+    if force or _newer(HOST_LIB, [os.path.join(HOST, "drivers.cpp"), __file__] + hdrs):
+        _run([HOST_CXX] + common + ["-shared", "-o", HOST_LIB, os.path.join(HOST, "drivers.cpp"),
+                                    "-L" + LIBDIR, "-lfringe_b200", "-Wl,-rpath,$ORIGIN"])
+    ext = sysconfig.get_config_var("EXT_SUFFIX")
+    inc = ["-I" + pybind11.get_include(), "-I" + sysconfig.get_paths()["include"]]
+    link = ["-L" + LIBDIR, "-lfringe_host", "-lfringe_b200", "-Wl,-rpath,$ORIGIN/../lib"]
+    for mod, src, defs in (("nmaplib", "nmaplib.cpp", []), ("evdlib", "evdlib.cpp", []),
+                           ("phase_linklib", "evdlib.cpp", ["-DFRINGE_PHASE_LINK"])):
+        out = os.path.join(BINDINGS, mod + ext)
+        if force or _newer(out, [os.path.join(HOST, src), HOST_LIB, __file__] + hdrs):
+            _run([HOST_CXX] + common + ["-fvisibility=hidden", "-shared"] + defs + inc +
+                 ["-o", out, os.path.join(HOST, src)] + link)

@@ -1,0 +1,73 @@
+// Option structs of the block drivers: the C++ side of the drop-in boundary.  Member names,
+// types and defaults follow src/nmap/nmap.hpp:23-65, src/evd/evd.hpp:19-68 and
+// src/phase_link/phase_link.hpp (the args.hxx command-line parsers are not reproduced: the
+// Python bindings never call them).
+#pragma once
+#include <iostream>
+#include <string>
+
+struct nmapOptions {
+    std::string inputDS;     // input VRT with SLCs as bands
+    std::string maskDS;      // optional byte mask
+    bool noGPU;              // kept for interface compatibility; there is no CPU path here
+    std::string wtsDS;       // output neighbourhood bit mask
+    std::string ncountDS;    // output neighbour count
+    std::string method;      // KS2 or AD2
+    int blocksize;           // block quantum in lines
+    int memsize;             // MB the block buffers may use
+    int Nx, Ny;              // half window sizes
+    double prob;             // minimum p-value
+
+    nmapOptions() : noGPU(false), method("KS2"), blocksize(64), memsize(512), Nx(5), Ny(5), prob(0.05) {}
+    void print() const {
+        std::cout << "Input Dataset: " << inputDS << std::endl;
+        std::cout << "Weights Dataset: " << wtsDS << std::endl;
+        std::cout << "Count Dataset: " << ncountDS << std::endl;
+        std::cout << "Mask Dataset: " << maskDS << std::endl;
+        std::cout << "Window size: " << Nx << " " << Ny << std::endl;
+        std::cout << "Threshold : " << prob << std::endl;
+        std::cout << "Memsize: " << memsize << " Mb \n";
+        std::cout << "Blocksize: " << blocksize << " lines \n";
+        std::cout << "GPU user request: " << !(noGPU) << " \n";
+    }
+};
+
+struct evdOptions {
+    std::string inputDS;                    // input VRT with SLCs as bands
+    std::string wtsDS;                      // neighbourhood bit mask from nmap
+    std::string compSlc;                    // name of the compressed SLC
+    std::string outputCompressedSlcFolder;  // folder of the compressed SLC
+    std::string outputFolder;               // output stack folder (must not exist)
+    std::string coherence;                  // unused by the reference driver
+    std::string compSLC;                    // written by the reference's CLI parser only
+    int blocksize, memsize;
+    int Nx, Ny;
+    int minNeighbors;
+    std::string method;                     // MLE / EVD / STBAS
+    int miniStackCount;
+    int bandWidth;
+
+    evdOptions() : blocksize(64), memsize(2048), Nx(5), Ny(5), minNeighbors(2), method("MLE"),
+                   miniStackCount(1), bandWidth(-1) {}
+    void print() const {
+        std::cout << "Input Dataset: " << inputDS << std::endl;
+        std::cout << "Weights Dataset: " << wtsDS << std::endl;
+        std::cout << "Output Folder " << outputFolder << std::endl;
+        std::cout << "Output compressed SLC folder " << outputCompressedSlcFolder << std::endl;
+        std::cout << "Output compressed SLC " << compSlc << std::endl;
+        std::cout << "Window size: " << Nx << " " << Ny << std::endl;
+        std::cout << "Memsize: " << memsize << " Mb \n";
+        std::cout << "Blocksize: " << blocksize << " lines \n";
+        std::cout << "Minimum neighbors: " << minNeighbors << "\n";
+        std::cout << "Mini-stack counter: " << miniStackCount << "\n";
+        std::cout << "Decomposition method: " << method << "\n";
+        if (method.compare("STBAS") == 0) std::cout << "STBAS Bandwidth: " << bandWidth << "\n";
+    }
+};
+
+// Block drivers (drivers.cpp).  Return 0 or the reference's error codes
+// (nmap: 1,102,104,105,106,108,111; evd: 101,102,105-110,112-121), plus 200+status when the
+// device library reports an error (there is no CPU fallback).
+int nmap_process(nmapOptions* opts);
+int evd_process(evdOptions* opts);            // src/evd/evd.cpp control flow
+int phase_link_process(evdOptions* opts);     // src/phase_link/phase_link.cpp control flow

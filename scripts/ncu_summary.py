@@ -1,0 +1,45 @@
+#!/usr/bin/env python3
+"""Condense an .ncu-rep (read with `ncu -i ... --page raw --csv`) into the handful of metrics
+the roofline discussion needs.  usage: ncu_summary.py report.ncu-rep > profiles/xxx.txt"""
+import csv
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__sass_inst_executed_op_local_ld.sum", "smsp__sass_inst_executed_op_local_st.sum",
+    "smsp__thread_inst_executed_per_inst_executed.ratio",
+]
+STALL = "smsp__average_warps_issue_stalled_"
+
+
+def main(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
+        print(f"== {name}")
+        d = dict(zip(hdr, zip(units, r)))
+        for k in KEYS:
+            if k in d:
+                print(f"{k:75s} {d[k][1]:>18s} {d[k][0]}")
+        stalls = sorted(((float(v[1]), k[len(STALL):].replace("_per_issue_active.ratio", "")) for k, v in d.items()
+                         if k.startswith(STALL) and k.endswith("_per_issue_active.ratio") and v[1]), reverse=True)
+        print("warp stall reasons (warps stalled per issue-active cycle):")
+        for val, k in stalls[:9]:
+            print(f"    {k:40s} {val:8.3f}")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])

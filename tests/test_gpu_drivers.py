@@ -1,0 +1,109 @@
+"""GPU: the file-level drop-in boundary -- Python bindings (nmaplib / evdlib / phase_linklib), the
+C++ block drivers with the reference's block/halo schedule, VRT stack in and ENVI rasters out --
+against the CPU oracle run on the same stack in memory."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import wrapped_diff
+from fringe_b200 import stackio, synth
+from fringe_b200.cli import evd as evd_cli
+from fringe_b200.cli import nmap as nmap_cli
+from fringe_b200.cli import phase_link as pl_cli
+from fringe_b200.cli import sequential as seq_cli
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def stack(tmp_path_factory):
+    root = str(tmp_path_factory.mktemp("stack"))
+    slc = synth.make_stack(12, 150, 96, seed=31, region=32)
+    vrt = stackio.make_stack_on_disk(root, slc)
+    return root, slc, vrt
+
+
+def test_nmap_evd_cli_multi_block(stack, oracle_lib):
+    root, slc, vrt = stack
+    wts_path = os.path.join(root, "KS2", "nmap")
+    cnt_path = os.path.join(root, "KS2", "count")
+    # 1 MB -> 64-line blocks -> 3 overlapping blocks for 150 lines (nmap.cpp:166-183 schedule)
+    nmap_cli.main(["-i", vrt, "-o", wts_path, "-c", cnt_path, "-x", "5", "-y", "2", "-r", "1"])
+    count = stackio.read_envi(cnt_path)
+    wts = stackio.read_envi(wts_path)
+    assert count.dtype == np.int16 and wts.dtype == np.uint32 and wts.shape == (150, 96, 2)
+    hdr = stackio.read_envi_header(wts_path)
+    assert hdr["halfwindowx"] == "5" and hdr["halfwindowy"] == "2" and hdr["interleave"] == "bip"
+    c_ref, w_ref = oracle_lib.nmap_block(slc, 5, 2)
+    assert np.array_equal(count.astype(np.int32), c_ref) and np.array_equal(wts, w_ref)
+
+    out_dir = os.path.join(root, "EVD")
+    evd_cli.main(["-i", vrt, "-w", wts_path, "-o", out_dir, "-x", "5", "-y", "2", "-m", "EVD", "-r", "1"])
+    o_ref, t_ref, c_ref2 = oracle_lib.evd_block(slc, w_ref, 5, 2, method=0)
+    tcorr = stackio.read_envi(os.path.join(out_dir, "tcorr.bin"))
+    comp = stackio.read_envi(os.path.join(out_dir, "compslc.bin"))
+    dates = stackio.default_dates(12)
+    out = np.stack([stackio.read_envi(os.path.join(out_dir, d + ".slc")) for d in dates])
+    assert all(os.path.exists(os.path.join(out_dir, d + ".slc.vrt")) for d in dates)
+    ok = t_ref > 0
+    assert np.abs(tcorr - t_ref)[ok].max() <= 1e-4
+    good = t_ref > 0.3
+    assert wrapped_diff(out[:, good], o_ref[:, good]).max() <= 1e-3
+    assert np.abs(comp - c_ref2)[good].max() <= 2e-3 * np.abs(c_ref2).max()
+    # rerun refuses to overwrite (evd.cpp:229-251 -> rc 113)
+    with pytest.raises(RuntimeError, match="113"):
+        evd_cli.main(["-i", vrt, "-w", wts_path, "-o", out_dir, "-x", "5", "-y", "2", "-m", "EVD"])
+
+
+def test_phase_link_cli_and_error_codes(stack, oracle_lib):
+    root, slc, vrt = stack
+    wts_path = os.path.join(root, "KS2", "nmap")
+    out_dir = os.path.join(root, "PL")
+    pl_cli.main(["-i", vrt, "-w", wts_path, "-o", out_dir, "-x", "5", "-y", "2", "-n", "5", "-r", "2"])
+    w_ref = stackio.read_envi(wts_path)
+    o_ref, t_ref, _ = oracle_lib.evd_block(slc, w_ref, 5, 2, method=1, variant=1, min_neighbors=5)
+    tcorr = stackio.read_envi(os.path.join(out_dir, "tcorr.bin"))
+    assert np.array_equal(tcorr < 0, t_ref < 0)
+    assert np.abs(tcorr - t_ref)[t_ref > 0].max() <= 1e-4
+    # window mismatch between wts metadata and request -> rc 109 (evd.cpp:131-141)
+    with pytest.raises(RuntimeError, match="109"):
+        evd_cli.main(["-i", vrt, "-w", wts_path, "-o", os.path.join(root, "X1"), "-x", "4", "-y", "2"])
+    with pytest.raises(RuntimeError, match="102"):
+        nmap_cli.main(["-i", os.path.join(root, "missing.vrt"), "-o", os.path.join(root, "a"), "-c", os.path.join(root, "b")])
+    with pytest.raises(RuntimeError, match="returned 1"):
+        nmap_cli.main(["-i", vrt, "-o", os.path.join(root, "a"), "-c", os.path.join(root, "b"), "-s", "XYZ"])
+
+
+def test_sequential_chain(stack, oracle_lib):
+    """BASELINE.json configs[3] in miniature: 12 dates in ministacks of 5 (5+5+2) with compressed-SLC
+    hand-off, then the datum connection; every stage compared with the oracle fed the same inputs."""
+    root, slc, vrt = stack
+    wts_path = os.path.join(root, "KS2", "nmap")
+    out = os.path.join(root, "seq")
+    seq_cli.main(["-i", os.path.join(root, "SLC"), "-w", wts_path, "-o", out, "-x", "5", "-y", "2", "-s", "5", "-r", "2"])
+    w_ref = stackio.read_envi(wts_path)
+    dates = stackio.default_dates(12)
+    comps = []
+    for k, (a, b) in enumerate([(0, 5), (5, 10), (10, 12)], start=1):
+        bands = np.concatenate([np.array(comps).reshape(-1, 150, 96), slc[a:b]]) if comps else slc[a:b]
+        o_ref, t_ref, c_ref = oracle_lib.evd_block(bands.astype(np.complex64), w_ref, 5, 2, method=1, mini_stack_count=k)
+        d = os.path.join(out, "miniStacks", dates[a] + "_" + dates[b - 1], "EVD")
+        tcorr = stackio.read_envi(os.path.join(d, "tcorr.bin"))
+        assert np.mean((tcorr < 0) == (t_ref < 0)) > 0.999
+        both = (t_ref > 0) & (tcorr > 0)
+        assert np.abs(tcorr - t_ref)[both].max() <= 1e-4
+        comp = stackio.read_envi(os.path.join(out, "compressedSlc", dates[b - 1], dates[b - 1] + ".slc"))
+        good = both & (t_ref > 0.3)
+        assert np.abs(comp - c_ref)[good].max() <= 2e-3 * np.abs(c_ref[good]).max()
+        comps.append(comp)                       # feed OUR compressed SLC forward, like the chain does
+    dc = os.path.join(out, "Datum_connection", "EVD")
+    o_ref, t_ref, _ = oracle_lib.evd_block(np.array(comps).astype(np.complex64), w_ref, 5, 2, method=1, mini_stack_count=1)
+    tcorr = stackio.read_envi(os.path.join(dc, "tcorr.bin"))
+    both = (t_ref > 0) & (tcorr > 0)
+    assert np.mean((tcorr < 0) == (t_ref < 0)) > 0.999 and np.abs(tcorr - t_ref)[both].max() <= 1e-4
+    # skip-if-exists resume semantics (sequential.py:206-207): a second run only redoes the datum step
+    import shutil
+    shutil.rmtree(os.path.join(out, "Datum_connection"))
+    seq_cli.main(["-i", os.path.join(root, "SLC"), "-w", wts_path, "-o", out, "-x", "5", "-y", "2", "-s", "5", "-r", "2"])
+    assert os.path.exists(os.path.join(dc, "tcorr.bin"))
