@@ -5,6 +5,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -43,6 +44,13 @@ struct fringe_ctx {
     // CUDA events bracketing the most recent launch of each kernel (on its launching stream)
     cudaEvent_t ev[FRINGE_KERNEL_COUNT][2] = {};
     bool ev_valid[FRINGE_KERNEL_COUNT] = {};
+    // copy streams + event pool of the pipelined host entry points
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t pool_event(size_t i) {
+        while (pool.size() <= i) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); pool.push_back(e); }
+        return pool[i];
+    }
 };
 
 namespace {
@@ -205,6 +213,8 @@ int fringe_create(int device, fringe_ctx** out) {
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return FRINGE_ERR_CUDA; }
     for (int k = 0; k < FRINGE_KERNEL_COUNT; ++k)
         for (int j = 0; j < 2; ++j) cudaEventCreate(&c->ev[k][j]);
+    cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
     *out = c;
     return FRINGE_OK;
 }
@@ -218,6 +228,9 @@ int fringe_destroy(fringe_ctx* c) {
     for (DevBuf* b : all) b->release();
     for (int k = 0; k < FRINGE_KERNEL_COUNT; ++k)
         for (int j = 0; j < 2; ++j) if (c->ev[k][j]) cudaEventDestroy(c->ev[k][j]);
+    for (cudaEvent_t e : c->pool) cudaEventDestroy(e);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
     cudaStreamDestroy(c->stream);
     delete c;
     return FRINGE_OK;
@@ -293,28 +306,29 @@ int fringe_evd_max_bands(int method, int variant) { return fringe::evd_max_bands
 // ---------------------------------------------------------------------------------------
 // nmap
 // ---------------------------------------------------------------------------------------
-int fringe_nmap_block_device(fringe_ctx* ctx, const float* slc, const uint8_t* mask, const double* alpha,
-                             int cols, int lines, int bands, int Nx, int Ny, int method, double pvalue,
-                             int32_t* count, uint32_t* wts, void* stream) {
+namespace {
+
+struct NmapPlan {
+    fringe::NmapGeometry g;
+    int kcrit = 0;
+    double scrit = 0.0;
+};
+
+// validation + thresholds + workspaces shared by the host and device variants
+int nmap_prepare(fringe_ctx* ctx, int cols, int lines, int bands, int Nx, int Ny, int method, double pvalue,
+                 cudaStream_t st, NmapPlan* plan) {
     int rc = check_geometry(ctx, cols, lines, bands, Nx, Ny);
     if (rc) return rc;
     if (method != FRINGE_NMAP_KS2 && method != FRINGE_NMAP_AD2) return fail(ctx, FRINGE_ERR_METHOD, "method must be KS2 or AD2");
-    if (!slc || !count || !wts) return fail(ctx, FRINGE_ERR_ARGUMENT, "null pointer");
     if (method == FRINGE_NMAP_AD2 && bands < 2) return fail(ctx, FRINGE_ERR_UNSUPPORTED, "AD2 needs >= 2 bands");
     CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     const size_t npix = (size_t)cols * lines;
-
-    fringe::NmapGeometry g;
-    if (!fringe::nmap_plan(bands, Nx, Ny, method, &g))
+    if (!fringe::nmap_plan(bands, Nx, Ny, method, &plan->g))
         return fail(ctx, FRINGE_ERR_UNSUPPORTED, "bands x window too large for the shared-memory tile");
-
-    int kcrit = 0;
-    double scrit = 0.0;
     if (method == FRINGE_NMAP_KS2) {
-        fringe_ks2_critical_count(bands, pvalue, &kcrit, nullptr);
+        fringe_ks2_critical_count(bands, pvalue, &plan->kcrit, nullptr);
     } else {
-        fringe_ad2_critical_sum(bands, pvalue, &scrit);
+        fringe_ad2_critical_sum(bands, pvalue, &plan->scrit);
         if (ctx->adtab_bands != bands) {
             std::vector<double> T;
             ad_build_table(bands, T);
@@ -326,50 +340,105 @@ int fringe_nmap_block_device(fringe_ctx* ctx, const float* slc, const uint8_t* m
     }
     CU(ctx->amp.ensure(npix * bands * sizeof(float)));
     CU(ctx->valid.ensure(npix));
-    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_AMP_SORT][0], st));
-    CU(fringe::launch_amp_sort((const float2*)slc, mask, alpha, cols, lines, bands, (float*)ctx->amp.p,
-                               (uint8_t*)ctx->valid.p, st));
-    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_AMP_SORT][1], st));
-    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_NMAP][0], st));
-    CU(fringe::launch_nmap((const float*)ctx->amp.p, (const uint8_t*)ctx->valid.p, cols, lines, bands, Nx, Ny,
-                           method, kcrit, scrit, (const double*)ctx->adtab.p, g, count, wts, st));
-    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_NMAP][1], st));
-    ctx->ev_valid[FRINGE_KERNEL_AMP_SORT] = ctx->ev_valid[FRINGE_KERNEL_NMAP] = true;
-    ctx->launches += 2;
     return FRINGE_OK;
 }
 
+// amplitude+sort for input rows [s0, s0+sn), pair tests producing output rows [r0, r0+rn)
+int nmap_launch_rows(fringe_ctx* ctx, const NmapPlan& plan, const float* slc, const uint8_t* mask,
+                     const double* alpha, int cols, int lines, int bands, int Nx, int Ny, int method,
+                     int32_t* count, uint32_t* wts, int s0, int sn, int r0, int rn, cudaStream_t st) {
+    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_AMP_SORT][0], st));
+    CU(fringe::launch_amp_sort((const float2*)slc, mask, alpha, cols, lines, bands, (float*)ctx->amp.p,
+                               (uint8_t*)ctx->valid.p, s0, sn, st));
+    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_AMP_SORT][1], st));
+    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_NMAP][0], st));
+    CU(fringe::launch_nmap((const float*)ctx->amp.p, (const uint8_t*)ctx->valid.p, cols, lines, bands, Nx, Ny,
+                           method, plan.kcrit, plan.scrit, (const double*)ctx->adtab.p, plan.g, count, wts,
+                           r0, rn, st));
+    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_NMAP][1], st));
+    ctx->ev_valid[FRINGE_KERNEL_AMP_SORT] = ctx->ev_valid[FRINGE_KERNEL_NMAP] = true;
+    ctx->launches += (sn > 0 ? 1 : 0) + (rn > 0 ? 1 : 0);
+    return FRINGE_OK;
+}
+
+// rows per pipeline stage: ~192 MB of input per stage, at least 8 rows
+int chunk_rows(int cols, int bands, int total_rows) {
+    if (const char* e = getenv("FRINGE_CHUNK_ROWS")) { const int v = atoi(e); if (v > 0) return v; }
+    const double row_bytes = (double)cols * bands * 8.0;
+    int r = (int)(192.0e6 / row_bytes);
+    if (r < 8) r = 8;
+    if (r > total_rows) r = total_rows;
+    return r;
+}
+
+}  // namespace
+
+int fringe_nmap_block_device(fringe_ctx* ctx, const float* slc, const uint8_t* mask, const double* alpha,
+                             int cols, int lines, int bands, int Nx, int Ny, int method, double pvalue,
+                             int32_t* count, uint32_t* wts, void* stream) {
+    if (!ctx) return FRINGE_ERR_ARGUMENT;
+    if (!slc || !count || !wts) return fail(ctx, FRINGE_ERR_ARGUMENT, "null pointer");
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    NmapPlan plan;
+    int rc = nmap_prepare(ctx, cols, lines, bands, Nx, Ny, method, pvalue, st, &plan);
+    if (rc) return rc;
+    return nmap_launch_rows(ctx, plan, slc, mask, alpha, cols, lines, bands, Nx, Ny, method, count, wts,
+                            0, lines, 0, lines, st);
+}
+
+// Host variant: the block is cut into row chunks and pipelined over three streams -- upload of
+// chunk k+1, kernels of chunk k and download of chunk k-1 overlap (pinned host memory needed for
+// real overlap; pageable memory still works, serialised by the driver).
 int fringe_nmap_block(fringe_ctx* ctx, const float* slc, const uint8_t* mask, const double* alpha, int cols,
                       int lines, int bands, int Nx, int Ny, int method, double pvalue, int32_t* count,
                       uint32_t* wts) {
-    int rc = check_geometry(ctx, cols, lines, bands, Nx, Ny);
-    if (rc) return rc;
+    if (!ctx) return FRINGE_ERR_ARGUMENT;
     if (!slc || !count || !wts) return fail(ctx, FRINGE_ERR_ARGUMENT, "null pointer");
-    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    NmapPlan plan;
+    int rc = nmap_prepare(ctx, cols, lines, bands, Nx, Ny, method, pvalue, st, &plan);
+    if (rc) return rc;
     const size_t npix = (size_t)cols * lines;
     const int nu = fringe_nulong(Nx, Ny);
-    cudaStream_t st = ctx->stream;
     CU(ctx->in_slc.ensure(npix * bands * sizeof(float2)));
     CU(ctx->o_count.ensure(npix * sizeof(int32_t)));
     CU(ctx->o_wts.ensure(npix * nu * sizeof(uint32_t)));
-    CU(cudaMemcpyAsync(ctx->in_slc.p, slc, npix * bands * sizeof(float2), cudaMemcpyHostToDevice, st));
     const uint8_t* dmask = nullptr;
-    if (mask) {
-        CU(ctx->in_mask.ensure(npix));
-        CU(cudaMemcpyAsync(ctx->in_mask.p, mask, npix, cudaMemcpyHostToDevice, st));
-        dmask = (const uint8_t*)ctx->in_mask.p;
-    }
+    if (mask) { CU(ctx->in_mask.ensure(npix)); dmask = (const uint8_t*)ctx->in_mask.p; }
     const double* dalpha = nullptr;
     if (alpha) {
         CU(ctx->alpha.ensure(bands * sizeof(double)));
         CU(cudaMemcpyAsync(ctx->alpha.p, alpha, bands * sizeof(double), cudaMemcpyHostToDevice, st));
         dalpha = (const double*)ctx->alpha.p;
     }
-    rc = fringe_nmap_block_device(ctx, (const float*)ctx->in_slc.p, dmask, dalpha, cols, lines, bands, Nx, Ny,
-                                  method, pvalue, (int32_t*)ctx->o_count.p, (uint32_t*)ctx->o_wts.p, st);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(count, ctx->o_count.p, npix * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(wts, ctx->o_wts.p, npix * nu * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    const int step = chunk_rows(cols, bands, lines);
+    int uploaded = 0;                  // input rows [0, uploaded) are on the device and sorted
+    size_t ev = 0;
+    for (int r0 = 0; r0 < lines; r0 += step) {
+        const int r1 = std::min(lines, r0 + step);
+        const int need = std::min(lines, r1 + Ny);          // pair tests of rows < r1 read rows < r1+Ny
+        const int s0 = uploaded, sn = need - uploaded;
+        if (sn > 0) {
+            const size_t off = (size_t)s0 * cols, cnt = (size_t)sn * cols;
+            CU(cudaMemcpy2DAsync((float2*)ctx->in_slc.p + off, npix * sizeof(float2), (const float2*)slc + off,
+                                 npix * sizeof(float2), cnt * sizeof(float2), bands, cudaMemcpyHostToDevice, ctx->s_in));
+            if (mask) CU(cudaMemcpyAsync((uint8_t*)ctx->in_mask.p + off, mask + off, cnt, cudaMemcpyHostToDevice, ctx->s_in));
+            uploaded = need;
+        }
+        cudaEvent_t e_in = ctx->pool_event(ev++), e_done = ctx->pool_event(ev++);
+        CU(cudaEventRecord(e_in, ctx->s_in));
+        CU(cudaStreamWaitEvent(st, e_in, 0));
+        rc = nmap_launch_rows(ctx, plan, (const float*)ctx->in_slc.p, dmask, dalpha, cols, lines, bands, Nx, Ny,
+                              method, (int32_t*)ctx->o_count.p, (uint32_t*)ctx->o_wts.p, s0, sn, r0, r1 - r0, st);
+        if (rc) return rc;
+        CU(cudaEventRecord(e_done, st));
+        CU(cudaStreamWaitEvent(ctx->s_out, e_done, 0));
+        const size_t off = (size_t)r0 * cols, cnt = (size_t)(r1 - r0) * cols;
+        CU(cudaMemcpyAsync(count + off, (int32_t*)ctx->o_count.p + off, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_out));
+        CU(cudaMemcpyAsync(wts + off * nu, (uint32_t*)ctx->o_wts.p + off * nu, cnt * nu * sizeof(uint32_t),
+                           cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    CU(cudaStreamSynchronize(ctx->s_out));
     CU(cudaStreamSynchronize(st));
     return FRINGE_OK;
 }
@@ -396,6 +465,59 @@ static int check_evd(fringe_ctx* ctx, int cols, int lines, int bands, int Nx, in
     return FRINGE_OK;
 }
 
+namespace {
+
+struct EvdPlan { int NP = 0; bool generic = false; };
+
+int evd_prepare(fringe_ctx* ctx, int cols, int lines, int bands, int method, int variant, cudaStream_t st,
+                EvdPlan* plan) {
+    CU(cudaSetDevice(ctx->device));
+    const size_t npix = (size_t)cols * lines;
+    plan->NP = (bands + 1) & ~1;
+    plan->generic = getenv("FRINGE_EVD_GENERIC") != nullptr;      // debug switch
+    if (!plan->generic && variant == FRINGE_VARIANT_EVD && method != FRINGE_EVD_MLE &&
+        fringe::evd_fast_padded_bands(bands) > 0)
+        plan->NP = fringe::evd_fast_padded_bands(bands);
+    // one extra, all-zero sample vector behind the image: the register-blocked kernel points
+    // exhausted / out-of-block SHP slots at it instead of branching
+    CU(ctx->zpix.ensure((npix + 1) * plan->NP * sizeof(float2)));
+    CU(cudaMemsetAsync((float2*)ctx->zpix.p + npix * plan->NP, 0, plan->NP * sizeof(float2), st));
+    CU(ctx->stats.ensure(4 * sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(ctx->stats.p, 0, 4 * sizeof(unsigned long long), st));
+    return FRINGE_OK;
+}
+
+// re-layout of input rows [t0, t0+tn), then the solve for output rows [first_line, first_line+n_lines)
+int evd_launch_rows(fringe_ctx* ctx, const EvdPlan& plan, const float* slc, const uint32_t* wts, int cols,
+                    int lines, int bands, int Nx, int Ny, int t0, int tn, int first_line, int n_lines,
+                    int method, int bandwidth, int mini_stack_count, int variant, int min_neighbors,
+                    float* out, float* tcorr, float* comp, cudaStream_t st) {
+    const size_t npix = (size_t)cols * lines;
+    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_TRANSPOSE][0], st));
+    CU(fringe::launch_transpose((const float2*)slc, (long)npix, (long)t0 * cols, (long)tn * cols, bands, plan.NP,
+                                (float2*)ctx->zpix.p, st));
+    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_TRANSPOSE][1], st));
+    fringe::EvdArgs a;
+    a.zpix = (const float2*)ctx->zpix.p; a.slc = (const float2*)slc; a.wts = wts;
+    a.cols = cols; a.lines = lines; a.bands = bands; a.NP = plan.NP;
+    a.Nx = Nx; a.Ny = Ny; a.nulong = fringe_nulong(Nx, Ny);
+    a.first_line = first_line; a.n_lines = n_lines;
+    a.method = method; a.bandwidth = bandwidth; a.mini_stack_count = mini_stack_count;
+    a.variant = variant; a.min_neighbors = min_neighbors;
+    a.out = (float2*)out; a.tcorr = tcorr; a.comp = (float2*)comp;
+    a.stats = (unsigned long long*)ctx->stats.p;
+    a.force_generic = plan.generic ? 1 : 0;
+    int nl = 0;
+    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_EVD][0], st));
+    if (n_lines > 0) CU(fringe::launch_evd(a, st, &nl));
+    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_EVD][1], st));
+    ctx->ev_valid[FRINGE_KERNEL_TRANSPOSE] = ctx->ev_valid[FRINGE_KERNEL_EVD] = true;
+    ctx->launches += (tn > 0 ? 1 : 0) + nl;
+    return FRINGE_OK;
+}
+
+}  // namespace
+
 int fringe_evd_block_device(fringe_ctx* ctx, const float* slc, const uint32_t* wts, int cols, int lines,
                             int bands, int Nx, int Ny, int first_line, int n_lines, int method, int bandwidth,
                             int mini_stack_count, int variant, int min_neighbors, float* out, float* tcorr,
@@ -404,41 +526,18 @@ int fringe_evd_block_device(fringe_ctx* ctx, const float* slc, const uint32_t* w
     if (rc) return rc;
     if (!slc || !wts || !out || !tcorr || !comp) return fail(ctx, FRINGE_ERR_ARGUMENT, "null pointer");
     if (n_lines == 0) return FRINGE_OK;
-    CU(cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-    const size_t npix = (size_t)cols * lines;
-    int NP = (bands + 1) & ~1;
-    const bool generic = getenv("FRINGE_EVD_GENERIC") != nullptr;      // debug switch
-    if (!generic && variant == FRINGE_VARIANT_EVD && method != FRINGE_EVD_MLE && fringe::evd_fast_padded_bands(bands) > 0)
-        NP = fringe::evd_fast_padded_bands(bands);
-    // one extra, all-zero sample vector behind the image: the register-blocked kernel points
-    // exhausted / out-of-block SHP slots at it instead of branching
-    CU(ctx->zpix.ensure((npix + 1) * NP * sizeof(float2)));
-    CU(cudaMemsetAsync((float2*)ctx->zpix.p + npix * NP, 0, NP * sizeof(float2), st));
-    CU(ctx->stats.ensure(4 * sizeof(unsigned long long)));
-    CU(cudaMemsetAsync(ctx->stats.p, 0, 4 * sizeof(unsigned long long), st));
-    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_TRANSPOSE][0], st));
-    CU(fringe::launch_transpose((const float2*)slc, (long)npix, bands, NP, (float2*)ctx->zpix.p, st));
-    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_TRANSPOSE][1], st));
-    fringe::EvdArgs a;
-    a.zpix = (const float2*)ctx->zpix.p; a.slc = (const float2*)slc; a.wts = wts;
-    a.cols = cols; a.lines = lines; a.bands = bands; a.NP = NP;
-    a.Nx = Nx; a.Ny = Ny; a.nulong = fringe_nulong(Nx, Ny);
-    a.first_line = first_line; a.n_lines = n_lines;
-    a.method = method; a.bandwidth = bandwidth; a.mini_stack_count = mini_stack_count;
-    a.variant = variant; a.min_neighbors = min_neighbors;
-    a.out = (float2*)out; a.tcorr = tcorr; a.comp = (float2*)comp;
-    a.stats = (unsigned long long*)ctx->stats.p;
-    a.force_generic = generic ? 1 : 0;
-    int nl = 0;
-    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_EVD][0], st));
-    CU(fringe::launch_evd(a, st, &nl));
-    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_EVD][1], st));
-    ctx->ev_valid[FRINGE_KERNEL_TRANSPOSE] = ctx->ev_valid[FRINGE_KERNEL_EVD] = true;
-    ctx->launches += 1 + nl;
-    return FRINGE_OK;
+    EvdPlan plan;
+    rc = evd_prepare(ctx, cols, lines, bands, method, variant, st, &plan);
+    if (rc) return rc;
+    // only the rows the requested lines can see need the re-layout
+    const int t0 = std::max(0, first_line - Ny), t1 = std::min(lines, first_line + n_lines + Ny);
+    return evd_launch_rows(ctx, plan, slc, wts, cols, lines, bands, Nx, Ny, t0, t1 - t0, first_line, n_lines, method,
+                           bandwidth, mini_stack_count, variant, min_neighbors, out, tcorr, comp, st);
 }
 
+// Host variant, pipelined like fringe_nmap_block: row chunks flow through upload -> re-layout +
+// solve -> download on three streams.
 int fringe_evd_block(fringe_ctx* ctx, const float* slc, const uint32_t* wts, int cols, int lines, int bands,
                      int Nx, int Ny, int first_line, int n_lines, int method, int bandwidth,
                      int mini_stack_count, int variant, int min_neighbors, float* out, float* tcorr,
@@ -447,8 +546,10 @@ int fringe_evd_block(fringe_ctx* ctx, const float* slc, const uint32_t* wts, int
     if (rc) return rc;
     if (!slc || !wts || !out || !tcorr || !comp) return fail(ctx, FRINGE_ERR_ARGUMENT, "null pointer");
     if (n_lines == 0) return FRINGE_OK;
-    CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    EvdPlan plan;
+    rc = evd_prepare(ctx, cols, lines, bands, method, variant, st, &plan);
+    if (rc) return rc;
     const size_t npix = (size_t)cols * lines;
     const int nu = fringe_nulong(Nx, Ny);
     CU(ctx->in_slc.ensure(npix * bands * sizeof(float2)));
@@ -456,18 +557,40 @@ int fringe_evd_block(fringe_ctx* ctx, const float* slc, const uint32_t* wts, int
     CU(ctx->o_out.ensure(npix * bands * sizeof(float2)));
     CU(ctx->o_tcorr.ensure(npix * sizeof(float)));
     CU(ctx->o_comp.ensure(npix * sizeof(float2)));
-    CU(cudaMemcpyAsync(ctx->in_slc.p, slc, npix * bands * sizeof(float2), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->in_wts.p, wts, npix * nu * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    rc = fringe_evd_block_device(ctx, (const float*)ctx->in_slc.p, (const uint32_t*)ctx->in_wts.p, cols, lines,
-                                 bands, Nx, Ny, first_line, n_lines, method, bandwidth, mini_stack_count,
-                                 variant, min_neighbors, (float*)ctx->o_out.p, (float*)ctx->o_tcorr.p,
-                                 (float*)ctx->o_comp.p, st);
-    if (rc) return rc;
-    const size_t off = (size_t)first_line * cols, cnt = (size_t)n_lines * cols;
-    CU(cudaMemcpy2DAsync((float2*)out + off, npix * sizeof(float2), (float2*)ctx->o_out.p + off,
-                         npix * sizeof(float2), cnt * sizeof(float2), bands, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(tcorr + off, (float*)ctx->o_tcorr.p + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync((float2*)comp + off, (float2*)ctx->o_comp.p + off, cnt * sizeof(float2), cudaMemcpyDeviceToHost, st));
+    const int step = chunk_rows(cols, bands, n_lines);
+    const int last = first_line + n_lines;
+    int uploaded = std::max(0, first_line - Ny);      // input rows [.., uploaded) are on the device
+    size_t ev = 0;
+    for (int r0 = first_line; r0 < last; r0 += step) {
+        const int r1 = std::min(last, r0 + step);
+        const int need = std::min(lines, r1 + Ny);
+        const int t0 = uploaded, tn = need - uploaded;
+        if (tn > 0) {
+            const size_t off = (size_t)t0 * cols, cnt = (size_t)tn * cols;
+            CU(cudaMemcpy2DAsync((float2*)ctx->in_slc.p + off, npix * sizeof(float2), (const float2*)slc + off,
+                                 npix * sizeof(float2), cnt * sizeof(float2), bands, cudaMemcpyHostToDevice, ctx->s_in));
+            uploaded = need;
+        }
+        {   // the mask words of the output rows only
+            const size_t off = (size_t)r0 * cols * nu, cnt = (size_t)(r1 - r0) * cols * nu;
+            CU(cudaMemcpyAsync((uint32_t*)ctx->in_wts.p + off, wts + off, cnt * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->s_in));
+        }
+        cudaEvent_t e_in = ctx->pool_event(ev++), e_done = ctx->pool_event(ev++);
+        CU(cudaEventRecord(e_in, ctx->s_in));
+        CU(cudaStreamWaitEvent(st, e_in, 0));
+        rc = evd_launch_rows(ctx, plan, (const float*)ctx->in_slc.p, (const uint32_t*)ctx->in_wts.p, cols, lines, bands,
+                             Nx, Ny, t0, tn, r0, r1 - r0, method, bandwidth, mini_stack_count, variant, min_neighbors,
+                             (float*)ctx->o_out.p, (float*)ctx->o_tcorr.p, (float*)ctx->o_comp.p, st);
+        if (rc) return rc;
+        CU(cudaEventRecord(e_done, st));
+        CU(cudaStreamWaitEvent(ctx->s_out, e_done, 0));
+        const size_t off = (size_t)r0 * cols, cnt = (size_t)(r1 - r0) * cols;
+        CU(cudaMemcpy2DAsync((float2*)out + off, npix * sizeof(float2), (float2*)ctx->o_out.p + off,
+                             npix * sizeof(float2), cnt * sizeof(float2), bands, cudaMemcpyDeviceToHost, ctx->s_out));
+        CU(cudaMemcpyAsync(tcorr + off, (float*)ctx->o_tcorr.p + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_out));
+        CU(cudaMemcpyAsync((float2*)comp + off, (float2*)ctx->o_comp.p + off, cnt * sizeof(float2), cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    CU(cudaStreamSynchronize(ctx->s_out));
     CU(cudaStreamSynchronize(st));
     return FRINGE_OK;
 }

@@ -9,8 +9,10 @@ namespace fringe {
 // amp   : float [bands][npix]  ascending per valid pixel (rank-major so that the window tile
 //         of one rank is a set of contiguous row segments)
 // valid : uint8 [npix]
+// rows [row0, row0+nrows) of the block are processed (plane stride stays lines*cols)
 cudaError_t launch_amp_sort(const float2* slc, const uint8_t* mask, const double* alpha, int cols,
-                            int lines, int bands, float* amp, uint8_t* valid, cudaStream_t st);
+                            int lines, int bands, float* amp, uint8_t* valid, int row0, int nrows,
+                            cudaStream_t st);
 
 struct NmapGeometry {
     int tile_w, tile_h;      // output pixels per CTA
@@ -24,12 +26,13 @@ bool nmap_plan(int bands, int Nx, int Ny, int method, NmapGeometry* g);
 cudaError_t launch_nmap(const float* amp, const uint8_t* valid, int cols, int lines, int bands,
                         int Nx, int Ny, int method, int kcrit, double scrit,
                         const double* ad_table, const NmapGeometry& g, int32_t* count,
-                        uint32_t* wts, cudaStream_t st);
+                        uint32_t* wts, int row0, int nrows, cudaStream_t st);
 
 // ---- evd_kernels.cu -------------------------------------------------------------------
 // band-major planes [bands][npix] -> pixel-major vectors [npix][bands_padded] (zero padded)
-cudaError_t launch_transpose(const float2* slc, long npix, int bands, int bands_padded,
-                             float2* zpix, cudaStream_t st);
+// pixels [first, first+count) of the block
+cudaError_t launch_transpose(const float2* slc, long npix, long first, long count, int bands,
+                             int bands_padded, float2* zpix, cudaStream_t st);
 
 struct EvdArgs {
     const float2* zpix;      // [npix][NP]

@@ -33,29 +33,31 @@ namespace fringe {
 // re-layout: [bands][npix] -> [npix][NP]
 // ======================================================================================
 __global__ void __launch_bounds__(256) k_transpose(const float2* __restrict__ slc, long npix,
-                                                   int bands, int NP, float2* __restrict__ zpix) {
+                                                   long first, long pend, int bands, int NP,
+                                                   float2* __restrict__ zpix) {
     extern __shared__ float2 s_t[];                 // [32][NP+1]
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const long p0 = (long)blockIdx.x * 32;
+    const long p0 = first + (long)blockIdx.x * 32;  // pixels [first, pend) of the block
     const int pitch = NP + 1;
     for (int b = ty; b < NP; b += 8) {
         float2 v = make_float2(0.f, 0.f);
-        if (b < bands && p0 + tx < npix) v = __ldg(&slc[(long)b * npix + p0 + tx]);
+        if (b < bands && p0 + tx < pend) v = __ldg(&slc[(long)b * npix + p0 + tx]);
         s_t[tx * pitch + b] = v;
     }
     __syncthreads();
     for (int idx = threadIdx.x; idx < 32 * NP; idx += 256) {
         const int pp = idx / NP, b = idx - pp * NP;
-        if (p0 + pp < npix) zpix[(p0 + pp) * NP + b] = s_t[pp * pitch + b];
+        if (p0 + pp < pend) zpix[(p0 + pp) * NP + b] = s_t[pp * pitch + b];
     }
 }
 
-cudaError_t launch_transpose(const float2* slc, long npix, int bands, int NP, float2* zpix,
-                             cudaStream_t st) {
+cudaError_t launch_transpose(const float2* slc, long npix, long first, long count, int bands, int NP,
+                             float2* zpix, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
     const size_t smem = (size_t)32 * (NP + 1) * sizeof(float2);
     cudaError_t e = cudaFuncSetAttribute(k_transpose, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e != cudaSuccess) return e;
-    k_transpose<<<(unsigned)((npix + 31) / 32), 256, smem, st>>>(slc, npix, bands, NP, zpix);
+    k_transpose<<<(unsigned)((count + 31) / 32), 256, smem, st>>>(slc, npix, first, first + count, bands, NP, zpix);
     return cudaGetLastError();
 }
 

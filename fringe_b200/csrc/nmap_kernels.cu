@@ -38,13 +38,14 @@ namespace fringe {
 __global__ void __launch_bounds__(128) k_amp_sort(const float2* __restrict__ slc,
                                                   const uint8_t* __restrict__ mask,
                                                   const double* __restrict__ alpha, long npix,
+                                                  long p0, long pcount,
                                                   int bands, float* __restrict__ amp,
                                                   uint8_t* __restrict__ valid) {
     extern __shared__ float s_col[];   // [bands][blockDim.x]
     const int tid = threadIdx.x;
     const int nt = blockDim.x;
-    const long p = (long)blockIdx.x * nt + tid;
-    if (p >= npix) return;
+    const long p = p0 + (long)blockIdx.x * nt + tid;     // pixels [p0, p0+pcount) of the block
+    if (p >= p0 + pcount) return;
     bool ok = mask ? (mask[p] != 0) : true;
     for (int b = 0; b < bands; ++b) {
         const float2 z = __ldg(&slc[(long)b * npix + p]);
@@ -75,15 +76,18 @@ __global__ void __launch_bounds__(128) k_amp_sort(const float2* __restrict__ slc
 }
 
 cudaError_t launch_amp_sort(const float2* slc, const uint8_t* mask, const double* alpha, int cols,
-                            int lines, int bands, float* amp, uint8_t* valid, cudaStream_t st) {
+                            int lines, int bands, float* amp, uint8_t* valid, int row0, int nrows,
+                            cudaStream_t st) {
     const long npix = (long)cols * lines;
+    const long p0 = (long)row0 * cols, pcount = (long)nrows * cols;
+    if (pcount <= 0) return cudaSuccess;
     int nt = 128;
     while (nt > 32 && (size_t)nt * bands * sizeof(float) > 160 * 1024) nt >>= 1;
     const size_t smem = (size_t)nt * bands * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(k_amp_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    const long nblk = (npix + nt - 1) / nt;
-    k_amp_sort<<<(unsigned)nblk, nt, smem, st>>>(slc, mask, alpha, npix, bands, amp, valid);
+    const long nblk = (pcount + nt - 1) / nt;
+    k_amp_sort<<<(unsigned)nblk, nt, smem, st>>>(slc, mask, alpha, npix, p0, pcount, bands, amp, valid);
     return cudaGetLastError();
 }
 
@@ -94,6 +98,7 @@ struct NmapKernelArgs {
     const float* amp;
     const uint8_t* valid;
     int cols, lines, bands, Nx, Ny, nulong;
+    int row0, row1;           // output rows [row0, row1) of the block are produced by this launch
     int kcrit;
     double scrit;
     const double* ad_table;   // [(2N-1)][N+1]
@@ -160,7 +165,7 @@ __global__ void k_nmap(const NmapKernelArgs a) {
     float* s_amp = reinterpret_cast<float*>(s_tab + tab_elems);
     uint8_t* s_valid = reinterpret_cast<uint8_t*>(s_amp + (size_t)(N + 1) * RP);
 
-    const int x0 = blockIdx.x * TW - Nx, y0 = blockIdx.y * TH - Ny;
+    const int x0 = blockIdx.x * TW - Nx, y0 = a.row0 + blockIdx.y * TH - Ny;
     for (int rp = tid; rp < RP; rp += nthr) {
         const int gy = y0 + rp / RW, gx = x0 + rp % RW;
         const bool inb = (gy >= 0) && (gy < a.lines) && (gx >= 0) && (gx < a.cols);
@@ -176,8 +181,8 @@ __global__ void k_nmap(const NmapKernelArgs a) {
     for (int i = tid; i < tab_elems; i += nthr) s_tab[i] = a.ad_table[i];
     __syncthreads();
 
-    const int gx = blockIdx.x * TW + threadIdx.x, gy = blockIdx.y * TH + threadIdx.y;
-    if (gx >= a.cols || gy >= a.lines) return;
+    const int gx = blockIdx.x * TW + threadIdx.x, gy = a.row0 + blockIdx.y * TH + threadIdx.y;
+    if (gx >= a.cols || gy >= a.row1) return;
     const long p = (long)gy * a.cols + gx;
     const int rp = (threadIdx.y + Ny) * RW + threadIdx.x + Nx;
     uint32_t* wp = a.wts + p * a.nulong;
@@ -238,14 +243,16 @@ bool nmap_plan(int bands, int Nx, int Ny, int method, NmapGeometry* g) {
 cudaError_t launch_nmap(const float* amp, const uint8_t* valid, int cols, int lines, int bands,
                         int Nx, int Ny, int method, int kcrit, double scrit,
                         const double* ad_table, const NmapGeometry& g, int32_t* count,
-                        uint32_t* wts, cudaStream_t st) {
+                        uint32_t* wts, int row0, int nrows, cudaStream_t st) {
+    if (nrows <= 0) return cudaSuccess;
     NmapKernelArgs a;
+    a.row0 = row0; a.row1 = row0 + nrows;
     a.amp = amp; a.valid = valid; a.cols = cols; a.lines = lines; a.bands = bands;
     a.Nx = Nx; a.Ny = Ny; a.nulong = ((2 * Ny + 1) * (2 * Nx + 1) + 31) / 32;
     a.kcrit = kcrit; a.scrit = scrit; a.ad_table = ad_table; a.table_in_smem = g.table_in_smem ? 1 : 0;
     a.count = count; a.wts = wts;
     dim3 block(g.tile_w, g.tile_h);
-    dim3 grid((cols + g.tile_w - 1) / g.tile_w, (lines + g.tile_h - 1) / g.tile_h);
+    dim3 grid((cols + g.tile_w - 1) / g.tile_w, (nrows + g.tile_h - 1) / g.tile_h);
     cudaError_t e;
     if (method == 0) {
         e = cudaFuncSetAttribute(k_nmap<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes);
