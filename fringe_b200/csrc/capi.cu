@@ -356,8 +356,10 @@ int nmap_launch_rows(fringe_ctx* ctx, const NmapPlan& plan, const float* slc, co
                            method, plan.kcrit, plan.scrit, (const double*)ctx->adtab.p, plan.g, count, wts,
                            r0, rn, st));
     CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_NMAP][1], st));
+    // forward tests of rows < r0+rn have now delivered every bit of rows [r0, r0+rn)
+    CU(fringe::launch_count(wts, cols, fringe_nulong(Nx, Ny), r0, rn, count, st));
     ctx->ev_valid[FRINGE_KERNEL_AMP_SORT] = ctx->ev_valid[FRINGE_KERNEL_NMAP] = true;
-    ctx->launches += (sn > 0 ? 1 : 0) + (rn > 0 ? 1 : 0);
+    ctx->launches += (sn > 0 ? 1 : 0) + (rn > 0 ? 2 : 0);
     return FRINGE_OK;
 }
 
@@ -382,6 +384,7 @@ int fringe_nmap_block_device(fringe_ctx* ctx, const float* slc, const uint8_t* m
     NmapPlan plan;
     int rc = nmap_prepare(ctx, cols, lines, bands, Nx, Ny, method, pvalue, st, &plan);
     if (rc) return rc;
+    CU(cudaMemsetAsync(wts, 0, (size_t)cols * lines * fringe_nulong(Nx, Ny) * sizeof(uint32_t), st));
     return nmap_launch_rows(ctx, plan, slc, mask, alpha, cols, lines, bands, Nx, Ny, method, count, wts,
                             0, lines, 0, lines, st);
 }
@@ -411,6 +414,7 @@ int fringe_nmap_block(fringe_ctx* ctx, const float* slc, const uint8_t* mask, co
         CU(cudaMemcpyAsync(ctx->alpha.p, alpha, bands * sizeof(double), cudaMemcpyHostToDevice, st));
         dalpha = (const double*)ctx->alpha.p;
     }
+    CU(cudaMemsetAsync(ctx->o_wts.p, 0, npix * nu * sizeof(uint32_t), st));
     const int step = chunk_rows(cols, bands, lines);
     int uploaded = 0;                  // input rows [0, uploaded) are on the device and sorted
     size_t ev = 0;

@@ -28,6 +28,10 @@ cudaError_t launch_nmap(const float* amp, const uint8_t* valid, int cols, int li
                         const double* ad_table, const NmapGeometry& g, int32_t* count,
                         uint32_t* wts, int row0, int nrows, cudaStream_t st);
 
+// count[p] = popcount of the finished mask words, rows [row0, row0+nrows)
+cudaError_t launch_count(const uint32_t* wts, int cols, int nulong, int row0, int nrows, int32_t* count,
+                         cudaStream_t st);
+
 // ---- evd_kernels.cu -------------------------------------------------------------------
 // band-major planes [bands][npix] -> pixel-major vectors [npix][bands_padded] (zero padded)
 // pixels [first, first+count) of the block

@@ -9,10 +9,10 @@
 //   k_amp_sort   one thread per pixel; the N amplitudes of a pixel live in a shared-memory
 //                column (bank = thread), are insertion-sorted there and written rank-major
 //                ([rank][pixel]) so later tile loads are contiguous row segments.
-//   k_nmap<M>    one CTA per tile of output pixels; the sorted vectors of tile+halo are staged
-//                in shared memory once ([rank][region pixel], + one +inf sentinel rank); one
-//                thread per output pixel walks its window and runs a branch-free merge per
-//                neighbour.
+//   k_nmap<M>    one CTA per tile of pixels; the sorted vectors of tile + forward halo are
+//                staged in shared memory once as integer keys ([rank][region pixel], + one
+//                all-ones sentinel rank); one thread per pixel walks the forward half of its
+//                window and runs a branch-free merge per neighbour.
 //                KS2: the p-value threshold is turned into an integer bound on
 //                     max_v |#{a<=v} - #{b<=v}| on the host (fringe_ks2_critical_count), so
 //                     the device test is exact integer arithmetic.
@@ -21,8 +21,9 @@
 //                     the host with the reference's expression and the device adds the same
 //                     doubles in the same order, so the sum is bit-identical and the
 //                     threshold is a single comparison against a host-computed bound.
-//   Each pixel tests its whole window and writes only its own words: no atomics, results
-//   are deterministic and equal to the race-free reading of the reference loop.
+//   Each unordered pair is tested once (forward half-plane, as nmap.cpp:404-409) and sets both
+//   pixels' bits with atomic ORs into a pre-zeroed mask: order-independent, hence deterministic
+//   and equal to the race-free reading of the reference loop; counts = popcounts (k_count).
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -107,117 +108,138 @@ struct NmapKernelArgs {
     uint32_t* wts;
 };
 
-// KS2sample.hpp:91-144 as an integer walk.  A/B point at rank 0 of the two pixels, consecutive
-// ranks are `stride` floats apart, rank `n` holds +inf.  Returns max |#b - #a| sampled only
-// where every element equal to the last consumed value has been consumed on both sides.
-__device__ __forceinline__ int ks_max_count_diff(const float* __restrict__ A,
-                                                 const float* __restrict__ B, int n, int stride) {
-    int ia = 0, ib = 0, kmax = 0;
-    float va = A[0], vb = B[0];
+// The sorted amplitudes are non-negative, NaN-free floats, so their bit patterns order like
+// unsigned integers.  The walks below therefore run on uint32 keys: comparisons are integer
+// compares, ties are equal bit patterns, and the sentinel rank is 0xFFFFFFFF -- strictly above
+// every real key including +inf -- so no index guards are needed and the loop body is a single
+// shared-memory load from a selected address (no divergent branches).
+//
+// KS2sample.hpp:91-144 as an integer walk.  ia / ib index rank 0 of the two pixels inside
+// s_key, consecutive ranks are `stride` keys apart.  Returns max |#b - #a| sampled only where
+// every element equal to the last consumed value has been consumed on both sides (the
+// reference's tie rule).
+__device__ __forceinline__ int ks_max_count_diff(const uint32_t* __restrict__ s_key, uint32_t ia,
+                                                 uint32_t ib, int n, uint32_t stride) {
+    uint32_t va = s_key[ia], vb = s_key[ib];
+    int d = 0, kmax = 0;
+#pragma unroll 4
     for (int s = 0; s < 2 * n; ++s) {
-        const bool ta = (ib >= n) || ((ia < n) && (va <= vb));
-        const float x = ta ? va : vb;
-        ia += ta ? 1 : 0;
-        ib += ta ? 0 : 1;
-        const float nxt = ta ? A[ia * stride] : B[ib * stride];
+        const bool ta = va <= vb;
+        const uint32_t x = min(va, vb);
+        ia += ta ? stride : 0u;
+        ib += ta ? 0u : stride;
+        d += ta ? -1 : 1;
+        const uint32_t nxt = s_key[ta ? ia : ib];
         va = ta ? nxt : va;
         vb = ta ? vb : nxt;
-        const int k = abs(ib - ia);
-        kmax = ((va > x) && (vb > x)) ? max(kmax, k) : kmax;
+        const bool ev = (va > x) & (vb > x);
+        kmax = ev ? max(kmax, abs(d)) : kmax;
     }
     return kmax;
 }
 
 // AD2unique.hpp:211-303: merge (on equality the element of B goes first) and table sum.
-// A must be the pixel that comes first in raster order.
-__device__ __forceinline__ double ad_inner_sum(const float* __restrict__ A,
-                                               const float* __restrict__ B, int n, int stride,
+// The pixel at ia must be the one that comes first in raster order.
+__device__ __forceinline__ double ad_inner_sum(const uint32_t* __restrict__ s_key, uint32_t ia,
+                                               uint32_t ib, int n, uint32_t stride,
                                                const double* __restrict__ T) {
-    int ia = 0, ib = 0;
-    float va = A[0], vb = B[0];
+    uint32_t va = s_key[ia], vb = s_key[ib];
     double S = 0.0;
-    const int L = 2 * n;
-    for (int j = 0; j < L - 1; ++j) {
-        const bool ta = (ib >= n) || ((ia < n) && (va < vb));
-        ia += ta ? 1 : 0;
-        ib += ta ? 0 : 1;
-        const float nxt = ta ? A[ia * stride] : B[ib * stride];
+    int m2 = 0;                          // 2 * (#a consumed) - (j+1)
+    const double* Tj = T;
+#pragma unroll 2
+    for (int j = 0; j < 2 * n - 1; ++j) {
+        const bool ta = va < vb;
+        ia += ta ? stride : 0u;
+        ib += ta ? 0u : stride;
+        m2 += ta ? 1 : -1;
+        const uint32_t nxt = s_key[ta ? ia : ib];
         va = ta ? nxt : va;
         vb = ta ? vb : nxt;
-        const int u = abs(2 * ia - (j + 1));
-        S = __dadd_rn(S, T[j * (n + 1) + u]);
+        S = __dadd_rn(S, Tj[abs(m2)]);
+        Tj += n + 1;
     }
     return S;
 }
 
+// Forward half-plane pair tests (nmap.cpp:404-473): the thread of pixel p tests the neighbours q
+// that follow it in raster order inside the window; an accepted pair sets bit (dy,dx) of p and
+// bit (-dy,-dx) of q, exactly like the reference's symmetric update, but with atomic ORs into the
+// (pre-zeroed) global mask so the result does not depend on scheduling.  Neighbour counts are
+// the popcounts of the finished masks (k_count).
 template <int METHOD>
 __global__ void k_nmap(const NmapKernelArgs a) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int N = a.bands, Nx = a.Nx, Ny = a.Ny;
     const int TW = blockDim.x, TH = blockDim.y;
-    const int RW = TW + 2 * Nx, RH = TH + 2 * Ny, RP = RW * RH;
+    const int RW = TW + 2 * Nx, RH = TH + Ny, RP = RW * RH;       // tile + forward halo
     const int tid = threadIdx.y * TW + threadIdx.x, nthr = TW * TH;
     const long npix = (long)a.cols * a.lines;
 
-    // carve: [double table (optional)] [float amps (N+1)*RP] [uint8 valid RP]
+    // carve: [double table (optional)] [uint32 keys (N+1)*RP] [uint8 valid RP]
     double* s_tab = reinterpret_cast<double*>(s_raw);
     const int tab_elems = (METHOD == 1 && a.table_in_smem) ? (2 * N - 1) * (N + 1) : 0;
-    float* s_amp = reinterpret_cast<float*>(s_tab + tab_elems);
-    uint8_t* s_valid = reinterpret_cast<uint8_t*>(s_amp + (size_t)(N + 1) * RP);
+    uint32_t* s_key = reinterpret_cast<uint32_t*>(s_tab + tab_elems);
+    uint8_t* s_valid = reinterpret_cast<uint8_t*>(s_key + (size_t)(N + 1) * RP);
 
-    const int x0 = blockIdx.x * TW - Nx, y0 = a.row0 + blockIdx.y * TH - Ny;
+    const int x0 = blockIdx.x * TW - Nx, y0 = a.row0 + blockIdx.y * TH;
     for (int rp = tid; rp < RP; rp += nthr) {
         const int gy = y0 + rp / RW, gx = x0 + rp % RW;
-        const bool inb = (gy >= 0) && (gy < a.lines) && (gx >= 0) && (gx < a.cols);
+        const bool inb = (gy < a.lines) && (gx >= 0) && (gx < a.cols);
         s_valid[rp] = inb ? a.valid[(long)gy * a.cols + gx] : 0;
-        s_amp[(size_t)N * RP + rp] = CUDART_INF_F;
+        s_key[(size_t)N * RP + rp] = 0xFFFFFFFFu;
     }
     for (int idx = tid; idx < N * RP; idx += nthr) {
         const int k = idx / RP, rp = idx - k * RP;
         const int gy = y0 + rp / RW, gx = x0 + rp % RW;
-        const bool inb = (gy >= 0) && (gy < a.lines) && (gx >= 0) && (gx < a.cols);
-        s_amp[idx] = inb ? __ldg(&a.amp[(long)k * npix + (long)gy * a.cols + gx]) : 0.f;
+        const bool inb = (gy < a.lines) && (gx >= 0) && (gx < a.cols);
+        s_key[idx] = inb ? __float_as_uint(__ldg(&a.amp[(long)k * npix + (long)gy * a.cols + gx])) : 0u;
     }
     for (int i = tid; i < tab_elems; i += nthr) s_tab[i] = a.ad_table[i];
     __syncthreads();
 
-    const int gx = blockIdx.x * TW + threadIdx.x, gy = a.row0 + blockIdx.y * TH + threadIdx.y;
+    const int gx = blockIdx.x * TW + threadIdx.x, gy = y0 + threadIdx.y;
     if (gx >= a.cols || gy >= a.row1) return;
+    const int rp = threadIdx.y * RW + threadIdx.x + Nx;
+    if (!s_valid[rp]) return;                       // mask words stay zero
     const long p = (long)gy * a.cols + gx;
-    const int rp = (threadIdx.y + Ny) * RW + threadIdx.x + Nx;
     uint32_t* wp = a.wts + p * a.nulong;
-    if (!s_valid[rp]) {
-        a.count[p] = 0;
-        for (int w = 0; w < a.nulong; ++w) wp[w] = 0u;
-        return;
-    }
     const double* T = (METHOD == 1) ? (a.table_in_smem ? s_tab : a.ad_table) : nullptr;
     const int WX = 2 * Nx + 1, W = WX * (2 * Ny + 1), center = Ny * WX + Nx;
-    uint32_t word = 0u;
-    int cnt = 0;
-    int dy = -Ny, dx = -Nx;
-    for (int f = 0; f < W; ++f) {
+    uint32_t word = 1u << (center & 31);            // a valid pixel is always its own neighbour
+    int dy = 0, dx = 1;
+    for (int f = center + 1; f < W; ++f) {
+        if (dx > Nx) { dx = -Nx; ++dy; }
+        if ((f & 31) == 0) { atomicOr(&wp[(f - 1) >> 5], word); word = 0u; }
         const int rq = rp + dy * RW + dx;
-        bool similar = false;
         if (s_valid[rq]) {
-            if (f == center) similar = true;
-            else if (METHOD == 0) {
-                similar = ks_max_count_diff(s_amp + rp, s_amp + rq, N, RP) <= a.kcrit;
-            } else {
-                const float* first = s_amp + (f < center ? rq : rp);
-                const float* second = s_amp + (f < center ? rp : rq);
-                similar = ad_inner_sum(first, second, N, RP, T) <= a.scrit;
+            bool similar;
+            if (METHOD == 0) similar = ks_max_count_diff(s_key, rp, rq, N, RP) <= a.kcrit;
+            else similar = ad_inner_sum(s_key, rp, rq, N, RP, T) <= a.scrit;
+            if (similar) {
+                word |= (1u << (f & 31));
+                const int fm = W - 1 - f;               // bit of (-dy,-dx) in q's mask
+                atomicOr(&a.wts[(p + (long)dy * a.cols + dx) * a.nulong + (fm >> 5)], 1u << (fm & 31));
             }
         }
-        if (similar) { word |= (1u << (f & 31)); ++cnt; }
-        if ((f & 31) == 31 || f == W - 1) { wp[f >> 5] = word; word = 0u; }
-        if (++dx > Nx) { dx = -Nx; ++dy; }
+        ++dx;
     }
-    a.count[p] = cnt;
+    atomicOr(&wp[(W - 1) >> 5], word);
+}
+
+// neighbour count = number of set bits (count(pp) is incremented exactly once per bit set,
+// nmap.cpp:447-468)
+__global__ void __launch_bounds__(256) k_count(const uint32_t* __restrict__ wts, int nulong, long p0,
+                                               long pend, int32_t* __restrict__ count) {
+    const long p = p0 + (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pend) return;
+    int c = 0;
+    for (int w = 0; w < nulong; ++w) c += __popc(wts[p * nulong + w]);
+    count[p] = c;
 }
 
 static size_t nmap_smem(int bands, int Nx, int Ny, int tw, int th, bool table) {
-    const size_t RP = (size_t)(tw + 2 * Nx) * (th + 2 * Ny);
+    const size_t RP = (size_t)(tw + 2 * Nx) * (th + Ny);
     size_t b = (size_t)(bands + 1) * RP * sizeof(float) + RP;
     if (table) b += (size_t)(2 * bands - 1) * (bands + 1) * sizeof(double);
     return (b + 15) & ~(size_t)15;
@@ -263,6 +285,14 @@ cudaError_t launch_nmap(const float* amp, const uint8_t* valid, int cols, int li
         if (e != cudaSuccess) return e;
         k_nmap<1><<<grid, block, g.smem_bytes, st>>>(a);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_count(const uint32_t* wts, int cols, int nulong, int row0, int nrows, int32_t* count,
+                         cudaStream_t st) {
+    if (nrows <= 0) return cudaSuccess;
+    const long p0 = (long)row0 * cols, pend = p0 + (long)nrows * cols;
+    k_count<<<(unsigned)((pend - p0 + 255) / 256), 256, 0, st>>>(wts, nulong, p0, pend, count);
     return cudaGetLastError();
 }
 
