@@ -1,6 +1,9 @@
 // FP32 FMA peak microbenchmark: the measured denominator of the covariance + eigen roofline.
 // Two register-resident variants are timed (scalar FFMA chains and packed fma.rn.f32x2, the
 // sm_100 two-wide FP32 FMA); the better one is reported.
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace fringe {
@@ -77,7 +80,9 @@ cudaError_t measure_fp32_peak(cudaStream_t st, double* tflops) {
             cudaEventSynchronize(e1);
             float ms = 0.f;
             cudaEventElapsedTime(&ms, e0, e1);
-            if (rep > 0 && ms > 0.f) best = flops / (ms * 1e-3) * 1e-12 > best ? flops / (ms * 1e-3) * 1e-12 : best;
+            const double tf = (ms > 0.f) ? flops / (ms * 1e-3) * 1e-12 : 0.0;
+            if (rep > 0 && getenv("FRINGE_PEAK_VERBOSE")) printf("fp32 peak variant %d rep %d: %.2f TFLOP/s\n", variant, rep, tf);
+            if (rep > 0 && tf > best) best = tf;
         }
     }
     cudaEventDestroy(e0);
