@@ -510,7 +510,7 @@ int evd_launch_rows(fringe_ctx* ctx, const EvdPlan& plan, const float* slc, cons
     a.variant = variant; a.min_neighbors = min_neighbors;
     a.out = (float2*)out; a.tcorr = tcorr; a.comp = (float2*)comp;
     a.stats = (unsigned long long*)ctx->stats.p;
-    a.force_generic = plan.generic ? 1 : 0;
+    a.force_generic = (plan.generic ? 1 : 0) | (getenv("FRINGE_EVD_DEBUG_SHORT") ? (atoi(getenv("FRINGE_EVD_DEBUG_SHORT")) << 1) : 0);
     int nl = 0;
     CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_EVD][0], st));
     if (n_lines > 0) CU(fringe::launch_evd(a, st, &nl));

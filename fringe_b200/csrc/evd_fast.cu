@@ -25,6 +25,8 @@
 // loops below are rolled (#pragma unroll 1) around fully unrolled bodies.
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace fringe {
@@ -90,7 +92,7 @@ __device__ __forceinline__ void accumulate(float2 (&acc)[B][B], const Operands<B
 }
 
 template <int B>
-__global__ void __launch_bounds__(128, 2) k_evd_fast(const EvdArgs a) {
+__global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
     typedef FastCfg<B> Cfg;
     constexpr int NPAD = Cfg::NPAD;
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -148,6 +150,8 @@ __global__ void __launch_bounds__(128, 2) k_evd_fast(const EvdArgs a) {
     const long beg = (long)blockIdx.x * chunk;
     const long end = min(total_pairs, beg + chunk);
     unsigned long long st_pix = 0, st_it = 0, st_cap = 0;
+    float2 xwarm = make_float2(0.f, 0.f);       // last converged eigenvector of this warp (warm start)
+    bool have_warm = false;
 
 #pragma unroll 1
     for (long pr = beg + warp; pr < end; pr += Cfg::WARPS) {
@@ -267,22 +271,29 @@ __global__ void __launch_bounds__(128, 2) k_evd_fast(const EvdArgs a) {
                     for (int j = 0; j < NPAD; ++j)
                         if (abs(j - lane) > BW) c[j] = make_float2(0.f, 0.f);
                 }
-                // start vector: column k0 of C  (= conj of row k0; entry k0 is 1)
+                // start vector: the eigenvector of the previous pixel this warp solved (its window
+                // overlaps this one almost completely), else column k0 of C
                 float2 x;
                 {
                     const float2 v = s_mat[g * Cfg::MAT + k0 * NPAD + r];
                     const float keep = (isstbas && abs(k0 - lane) > BW) ? 0.f : live;
-                    x = make_float2(v.x * keep, -v.y * keep);
+                    x = have_warm ? xwarm : make_float2(v.x * keep, -v.y * keep);
                     float n2 = x.x * x.x + x.y * x.y;
 #pragma unroll
                     for (int s = 16; s > 0; s >>= 1) n2 += __shfl_xor_sync(FULLMASK, n2, s);
                     const float sc = rsqrtf(n2);
                     x.x *= sc; x.y *= sc;
                 }
-                float lam = 1.f, inv_lam = 1.f;
+                // Power iteration with heavy-ball momentum: x+ = C x / lambda - beta * x-.  beta = 0
+                // (plain power iteration) until the decay rate r ~ lambda2/lambda1 of the residual
+                // has been observed over one check interval; then beta = (0.95 r / 2)^2, which is
+                // the optimal Chebyshev-type acceleration if r is exact and merely a weaker
+                // acceleration if r is underestimated (never a divergence: beta < 1/4).
+                float lam = 1.f, inv_lam = 1.f, beta = 0.f, rho_prev = -1.f;
+                float2 xp = make_float2(0.f, 0.f);
                 int it = 0, buf = 0;
                 bool conv = false;
-                const int kMaxIter = 1000;
+                const int kMaxIter = (a.force_generic >> 1) ? (a.force_generic >> 1) : 1000;   // upper bits: timing experiment only
                 const float tol2 = 4.0e-12f;
 #pragma unroll 1
                 for (; it < kMaxIter; ++it) {
@@ -307,8 +318,10 @@ __global__ void __launch_bounds__(128, 2) k_evd_fast(const EvdArgs a) {
                         i0 = fmaf(c[NPAD - 1].x, q.y, i0); i1 = fmaf(c[NPAD - 1].y, q.x, i1);
                     }
                     const float yr = ((r0 + r1) + (r2a + r3)) * live, yi = ((i0 + i1) + (i2 + i3)) * live;
-                    if ((it & 3) != 3) { x.x = yr * inv_lam; x.y = yi * inv_lam; }
-                    else {
+                    if ((it & 3) != 3) {
+                        const float2 xn = make_float2(fmaf(-beta, xp.x, yr * inv_lam), fmaf(-beta, xp.y, yi * inv_lam));
+                        xp = x; x = xn;
+                    } else {
                         // Rayleigh quotient, residual, renormalisation
                         float xy = x.x * yr + x.y * yi, xx = x.x * x.x + x.y * x.y;
 #pragma unroll
@@ -324,15 +337,30 @@ __global__ void __launch_bounds__(128, 2) k_evd_fast(const EvdArgs a) {
                             rr2 += __shfl_xor_sync(FULLMASK, rr2, s);
                             y2 += __shfl_xor_sync(FULLMASK, y2, s);
                         }
-                        const float sc = rsqrtf(y2);
-                        x.x = yr * sc; x.y = yi * sc;
                         inv_lam = 1.0f / lam;
-                        conv = (rr2 <= tol2 * lam * lam * xx);
-                        if (conv) { ++it; break; }
+                        const float rho2 = rr2 / (lam * lam * xx);           // relative residual^2
+                        conv = (rho2 <= tol2);
+                        if (conv) {                                          // final vector: one more plain step
+                            const float sc = rsqrtf(y2);
+                            x.x = yr * sc; x.y = yi * sc;
+                            ++it; break;
+                        }
+                        if (beta == 0.f && rho_prev > 0.f && rho2 < rho_prev) {
+                            const float r = sqrtf(sqrtf(sqrtf(rho2 / rho_prev)));   // (rho2 ratio)^(1/8): per-iteration rate
+                            const float hb = 0.475f * r;
+                            beta = hb * hb;
+                        }
+                        rho_prev = rho2;
+                        // momentum step, then put (x, x-) back on a unit scale
+                        const float sc = rsqrtf(xx);
+                        const float2 xn = make_float2(fmaf(-beta, xp.x, yr * inv_lam) * sc, fmaf(-beta, xp.y, yi * inv_lam) * sc);
+                        xp = make_float2(x.x * sc, x.y * sc);
+                        x = xn;
                     }
                 }
                 st_it += it;
                 st_cap += conv ? 0 : 1;
+                xwarm = x; have_warm = false && conv;   // warm start disabled: it makes results depend on the block schedule at the 1e-7 level
                 if (lam < 1.0e-6f) tc = -7.f;             // evd.cpp:723-727
                 else {
                     // ---------------- phase reference (evd.cpp:738-749) -----------------
@@ -421,7 +449,9 @@ static cudaError_t launch_fast_t(const EvdArgs& a, cudaStream_t st) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_evd_fast<B>, Cfg::WARPS * 32, smem);
     if (occ < 1) occ = 1;
     const long total_pairs = (long)a.n_lines * ((a.cols + 1) / 2);
-    long grid = (long)nsm * occ * 8;
+    int mult = 8;
+    if (const char* e = getenv("FRINGE_EVD_CHUNKS")) { const int v = atoi(e); if (v > 0) mult = v; }
+    long grid = (long)nsm * occ * mult;
     const long maxgrid = (total_pairs + Cfg::WARPS * 4 - 1) / (Cfg::WARPS * 4);
     if (grid > maxgrid) grid = maxgrid;
     if (grid < 1) grid = 1;

@@ -797,7 +797,7 @@ static cudaError_t launch_evd_dp(const EvdArgs& a, cudaStream_t st) {
 cudaError_t launch_evd(const EvdArgs& a, cudaStream_t st, int* n_launches) {
     const bool dp = (a.method == 1) || (a.variant == 1);
     if (n_launches) *n_launches = 1;
-    if (!a.force_generic && evd_fast_supported(a)) return launch_evd_fast(a, st);
+    if (!(a.force_generic & 1) && evd_fast_supported(a)) return launch_evd_fast(a, st);
     return dp ? launch_evd_dp<true>(a, st) : launch_evd_dp<false>(a, st);
 }
 
