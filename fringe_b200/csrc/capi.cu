@@ -471,7 +471,7 @@ static int check_evd(fringe_ctx* ctx, int cols, int lines, int bands, int Nx, in
 
 namespace {
 
-struct EvdPlan { int NP = 0; bool generic = false; };
+struct EvdPlan { int NP = 0; int zblock = 0; bool generic = false; };
 
 int evd_prepare(fringe_ctx* ctx, int cols, int lines, int bands, int method, int variant, cudaStream_t st,
                 EvdPlan* plan) {
@@ -481,7 +481,10 @@ int evd_prepare(fringe_ctx* ctx, int cols, int lines, int bands, int method, int
     plan->generic = getenv("FRINGE_EVD_GENERIC") != nullptr;      // debug switch
     if (!plan->generic && variant == FRINGE_VARIANT_EVD && method != FRINGE_EVD_MLE &&
         fringe::evd_fast_padded_bands(bands) > 0)
+    {
         plan->NP = fringe::evd_fast_padded_bands(bands);
+        plan->zblock = fringe::evd_fast_block(bands);
+    }
     // one extra, all-zero sample vector behind the image: the register-blocked kernel points
     // exhausted / out-of-block SHP slots at it instead of branching
     CU(ctx->zpix.ensure((npix + 1) * plan->NP * sizeof(float2)));
@@ -499,7 +502,7 @@ int evd_launch_rows(fringe_ctx* ctx, const EvdPlan& plan, const float* slc, cons
     const size_t npix = (size_t)cols * lines;
     CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_TRANSPOSE][0], st));
     CU(fringe::launch_transpose((const float2*)slc, (long)npix, (long)t0 * cols, (long)tn * cols, bands, plan.NP,
-                                (float2*)ctx->zpix.p, st));
+                                plan.zblock, (float2*)ctx->zpix.p, st));
     CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_TRANSPOSE][1], st));
     fringe::EvdArgs a;
     a.zpix = (const float2*)ctx->zpix.p; a.slc = (const float2*)slc; a.wts = wts;
@@ -510,6 +513,7 @@ int evd_launch_rows(fringe_ctx* ctx, const EvdPlan& plan, const float* slc, cons
     a.variant = variant; a.min_neighbors = min_neighbors;
     a.out = (float2*)out; a.tcorr = tcorr; a.comp = (float2*)comp;
     a.stats = (unsigned long long*)ctx->stats.p;
+    a.zblock = plan.zblock; a.tile_pairs = 0;
     a.force_generic = (plan.generic ? 1 : 0) | (getenv("FRINGE_EVD_DEBUG_SHORT") ? (atoi(getenv("FRINGE_EVD_DEBUG_SHORT")) << 1) : 0);
     int nl = 0;
     CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_EVD][0], st));

@@ -35,8 +35,10 @@ cudaError_t launch_count(const uint32_t* wts, int cols, int nulong, int row0, in
 // ---- evd_kernels.cu -------------------------------------------------------------------
 // band-major planes [bands][npix] -> pixel-major vectors [npix][bands_padded] (zero padded)
 // pixels [first, first+count) of the block
+// zblock = 0: zpix[pix][NP] complex; zblock = B: per pixel and per block of B samples, B real parts
+// then B imaginary parts
 cudaError_t launch_transpose(const float2* slc, long npix, long first, long count, int bands,
-                             int bands_padded, float2* zpix, cudaStream_t st);
+                             int bands_padded, int zblock, float2* zpix, cudaStream_t st);
 
 struct EvdArgs {
     const float2* zpix;      // [npix][NP]
@@ -50,15 +52,19 @@ struct EvdArgs {
     float* tcorr;            // [npix]
     float2* comp;            // [npix]
     unsigned long long* stats;   // [4] device counters
-    int force_generic;           // debug: bypass the register-blocked kernel
+    int force_generic;           // debug: bit 0 bypasses the register-blocked kernel, upper bits cap iterations
+    int tile_pairs;              // set by the fast kernel's launcher: pixel pairs per CTA tile
+    int zblock;                  // 0: zpix is interleaved complex; B > 0: de-interleaved per block of B samples
 };
 int evd_max_bands(int method, int variant);
 cudaError_t launch_evd(const EvdArgs& a, cudaStream_t st, int* n_launches);
 
 // ---- evd_fast.cu ----------------------------------------------------------------------
-// Register-blocked kernel for EVD/STBAS with bands <= 30.  It needs the pixel-major stack
-// padded to evd_fast_padded_bands(bands) samples per pixel (0 = not eligible).
+// Register-blocked packed-FMA kernel (evd_fast2.cu) for EVD/STBAS with bands <= 30.  It needs the
+// pixel-major stack padded to evd_fast_padded_bands(bands) samples per pixel (0 = not eligible)
+// and de-interleaved per block of evd_fast_block(bands) samples.
 int evd_fast_padded_bands(int bands);
+int evd_fast_block(int bands);
 bool evd_fast_supported(const EvdArgs& a);
 cudaError_t launch_evd_fast(const EvdArgs& a, cudaStream_t st);
 

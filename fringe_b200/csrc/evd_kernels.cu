@@ -33,7 +33,7 @@ namespace fringe {
 // re-layout: [bands][npix] -> [npix][NP]
 // ======================================================================================
 __global__ void __launch_bounds__(256) k_transpose(const float2* __restrict__ slc, long npix,
-                                                   long first, long pend, int bands, int NP,
+                                                   long first, long pend, int bands, int NP, int zblock,
                                                    float2* __restrict__ zpix) {
     extern __shared__ float2 s_t[];                 // [32][NP+1]
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -45,19 +45,31 @@ __global__ void __launch_bounds__(256) k_transpose(const float2* __restrict__ sl
         s_t[tx * pitch + b] = v;
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < 32 * NP; idx += 256) {
-        const int pp = idx / NP, b = idx - pp * NP;
-        if (p0 + pp < pend) zpix[(p0 + pp) * NP + b] = s_t[pp * pitch + b];
+    if (zblock == 0) {
+        for (int idx = threadIdx.x; idx < 32 * NP; idx += 256) {
+            const int pp = idx / NP, b = idx - pp * NP;
+            if (p0 + pp < pend) zpix[(p0 + pp) * NP + b] = s_t[pp * pitch + b];
+        }
+    } else {
+        // de-interleaved: float index = (b / B) * 2B + (b % B) for the real part, + B for the imaginary part
+        float* zf = reinterpret_cast<float*>(zpix);
+        for (int idx = threadIdx.x; idx < 32 * 2 * NP; idx += 256) {
+            const int pp = idx / (2 * NP), f = idx - pp * 2 * NP;
+            const int blk = f / (2 * zblock), w = f - blk * 2 * zblock;
+            const int b = blk * zblock + (w < zblock ? w : w - zblock);
+            const float2 v = s_t[pp * pitch + b];
+            if (p0 + pp < pend) zf[(p0 + pp) * 2 * NP + f] = (w < zblock) ? v.x : v.y;
+        }
     }
 }
 
 cudaError_t launch_transpose(const float2* slc, long npix, long first, long count, int bands, int NP,
-                             float2* zpix, cudaStream_t st) {
+                             int zblock, float2* zpix, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
     const size_t smem = (size_t)32 * (NP + 1) * sizeof(float2);
     cudaError_t e = cudaFuncSetAttribute(k_transpose, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e != cudaSuccess) return e;
-    k_transpose<<<(unsigned)((count + 31) / 32), 256, smem, st>>>(slc, npix, first, first + count, bands, NP, zpix);
+    k_transpose<<<(unsigned)((count + 31) / 32), 256, smem, st>>>(slc, npix, first, first + count, bands, NP, zblock, zpix);
     return cudaGetLastError();
 }
 

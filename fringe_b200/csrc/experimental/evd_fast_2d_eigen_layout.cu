@@ -14,10 +14,10 @@
 //               the current one is accumulated; exhausted or out-of-block bits point at an
 //               all-zero sample row, so the loop body is branch-free.
 //   eigen       The normalised coherence matrices of both pixels are parked in shared memory
-//               (full Hermitian, row stride = padded order) and re-read row-per-lane into
-//               registers; the power iteration then needs only the broadcast vector from
-//               shared memory (15 LDS.128 per 120 FMAs, 8 independent FMA chains).
-//               Residual / normalisation reductions run every 4th iteration.
+//               (full Hermitian) and re-read as 8 x 4 register sub-blocks on a 4 x 8 lane grid;
+//               a matrix-vector product is 128 FMAs + 22 shuffles per lane and touches no
+//               shared memory.  Power iteration with heavy-ball momentum; residual /
+//               normalisation reductions run every 4th iteration.
 //   epilogue    phase reference, compressed SLC and temporal coherence from registers.
 //
 // Code size matters here: the first version unrolled everything and reached 92 kB of SASS,
@@ -129,11 +129,17 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
     const int k0 = a.mini_stack_count - 1;
     const bool isstbas = (a.method == 2);
     const int BW = a.bandwidth;
-    // bit j set: the pair (lane, j) enters the temporal-coherence sum (j > lane, inside the
-    // matrix and, for STBAS, inside the band)
+    // 2-D eigen layout: lane (ri, cj) owns rows {ri + 4k} x columns {4cj + t}; result row ri + 4cj
+    const int ri = lane >> 3, cj = lane & 7;
+    const int myrow = ri + 4 * cj;
+    // bit k*4+t set: matrix entry (ri+4k, 4cj+t) enters the temporal-coherence sum (row < column,
+    // inside the matrix and, for STBAS, inside the band)
     uint32_t usemask = 0u;
-    for (int j = 0; j < N; ++j)
-        if (j > lane && (!isstbas || (j - lane) <= BW)) usemask |= (1u << j);
+    for (int k = 0; k < 8; ++k)
+        for (int t = 0; t < 4; ++t) {
+            const int rr = ri + 4 * k, cc = 4 * cj + t;
+            if (rr < cc && cc < N && (!isstbas || (cc - rr) <= BW)) usemask |= (1u << (k * 4 + t));
+        }
     // number of (i<j) pairs in the temporal-coherence sum (evd.cpp:773-784)
     float inv_pairs;
     {
@@ -150,8 +156,6 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
     const long beg = (long)blockIdx.x * chunk;
     const long end = min(total_pairs, beg + chunk);
     unsigned long long st_pix = 0, st_it = 0, st_cap = 0;
-    float2 xwarm = make_float2(0.f, 0.f);       // last converged eigenvector of this warp (warm start)
-    bool have_warm = false;
 
 #pragma unroll 1
     for (long pr = beg + warp; pr < end; pr += Cfg::WARPS) {
@@ -238,6 +242,13 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
         __syncwarp();
 
         // ------------------------- per pixel: eigen + epilogue --------------------------
+        // 2-D register layout for the matrix-vector products: lane (ri, cj) = (lane>>3, lane&7)
+        // holds the 8 x 4 sub-block  rows {ri + 4k}, k<8  x  columns {4cj + t}, t<4  of the padded
+        // 32 x 32 matrix.  A product then needs only the 4 vector entries of the lane's columns
+        // (8 shuffles) and a reduce-scatter of the 8 partial row sums over the 8 lanes sharing ri
+        // (14 shuffles); the result row of lane (ri, cj) is ri + 4cj.  The earlier lane-per-row
+        // layout broadcast the whole vector from shared memory to every lane -- 64 shared-memory
+        // wavefronts per product -- and made this phase shared-memory-bandwidth bound.
 #pragma unroll 1
         for (int g = 0; g < 2; ++g) {
             const bool exists_g = (col0 + g) < a.cols;
@@ -249,35 +260,22 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
             float2 cmp = make_float2(0.f, 0.f);
             if (solve_g) {
                 ++st_pix;
-                const int r = (lane < NPAD) ? lane : (NPAD - 1);
-                float2 c[NPAD];
-                if (NPAD % 2 == 0) {
-                    const float4* rowp = reinterpret_cast<const float4*>(s_mat + g * Cfg::MAT + r * NPAD);
+                const float2* mat = s_mat + g * Cfg::MAT;
+                float2 c[8][4];
 #pragma unroll
-                    for (int j = 0; j < NPAD; j += 2) {
-                        const float4 v = rowp[j >> 1];
-                        c[j] = make_float2(v.x, v.y); c[j + 1] = make_float2(v.z, v.w);
+                for (int k = 0; k < 8; ++k)
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int rr = ri + 4 * k, cc = 4 * cj + t;
+                        const bool in = (rr < N) && (cc < N) && (!isstbas || abs(rr - cc) <= BW);
+                        c[k][t] = in ? mat[rr * NPAD + cc] : make_float2(0.f, 0.f);
                     }
-                } else {
-                    const float2* rp2 = s_mat + g * Cfg::MAT + r * NPAD;
-#pragma unroll
-                    for (int j = 0; j < NPAD; ++j) c[j] = rp2[j];
-                }
-                // rows >= N of the padded matrix are exact zeros; only lanes beyond the padded
-                // order (which re-read the last row) have to be silenced
-                const float live = (lane < NPAD) ? 1.f : 0.f;
-                if (isstbas) {                                   // evd.cpp:695-706 band limit
-#pragma unroll
-                    for (int j = 0; j < NPAD; ++j)
-                        if (abs(j - lane) > BW) c[j] = make_float2(0.f, 0.f);
-                }
-                // start vector: the eigenvector of the previous pixel this warp solved (its window
-                // overlaps this one almost completely), else column k0 of C
+                // start vector: column k0 of C (= conj of row k0), entry of my own row
                 float2 x;
                 {
-                    const float2 v = s_mat[g * Cfg::MAT + k0 * NPAD + r];
-                    const float keep = (isstbas && abs(k0 - lane) > BW) ? 0.f : live;
-                    x = have_warm ? xwarm : make_float2(v.x * keep, -v.y * keep);
+                    const bool in = (myrow < N) && (!isstbas || abs(myrow - k0) <= BW);
+                    const float2 v = in ? mat[k0 * NPAD + myrow] : make_float2(0.f, 0.f);
+                    x = make_float2(v.x, -v.y);
                     float n2 = x.x * x.x + x.y * x.y;
 #pragma unroll
                     for (int s = 16; s > 0; s >>= 1) n2 += __shfl_xor_sync(FULLMASK, n2, s);
@@ -286,38 +284,57 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
                 }
                 // Power iteration with heavy-ball momentum: x+ = C x / lambda - beta * x-.  beta = 0
                 // (plain power iteration) until the decay rate r ~ lambda2/lambda1 of the residual
-                // has been observed over one check interval; then beta = (0.95 r / 2)^2, which is
-                // the optimal Chebyshev-type acceleration if r is exact and merely a weaker
-                // acceleration if r is underestimated (never a divergence: beta < 1/4).
+                // has been observed over one check interval; then beta = (0.95 r / 2)^2, the
+                // Chebyshev-optimal value if r is exact and a weaker acceleration if r is
+                // underestimated (never a divergence: beta < 1/4).
                 float lam = 1.f, inv_lam = 1.f, beta = 0.f, rho_prev = -1.f;
                 float2 xp = make_float2(0.f, 0.f);
-                int it = 0, buf = 0;
+                int it = 0;
                 bool conv = false;
                 const int kMaxIter = (a.force_generic >> 1) ? (a.force_generic >> 1) : 1000;   // upper bits: timing experiment only
                 const float tol2 = 4.0e-12f;
 #pragma unroll 1
                 for (; it < kMaxIter; ++it) {
-                    float2* xv = s_vec + buf * 32;
-                    buf ^= 1;
-                    xv[lane] = x;
-                    __syncwarp();
-                    // y = C x with 8 independent FMA chains
-                    float r0 = 0.f, r1 = 0.f, r2a = 0.f, r3 = 0.f, i0 = 0.f, i1 = 0.f, i2 = 0.f, i3 = 0.f;
-                    const float4* xv4 = reinterpret_cast<const float4*>(xv);
+                    // my four column entries live in lanes (t, cj)
+                    float2 xc[4];
 #pragma unroll
-                    for (int j = 0; j + 1 < NPAD; j += 2) {
-                        const float4 q = xv4[j >> 1];
-                        r0 = fmaf(c[j].x, q.x, r0); r1 = fmaf(-c[j].y, q.y, r1);
-                        i0 = fmaf(c[j].x, q.y, i0); i1 = fmaf(c[j].y, q.x, i1);
-                        r2a = fmaf(c[j + 1].x, q.z, r2a); r3 = fmaf(-c[j + 1].y, q.w, r3);
-                        i2 = fmaf(c[j + 1].x, q.w, i2); i3 = fmaf(c[j + 1].y, q.z, i3);
+                    for (int t = 0; t < 4; ++t) {
+                        xc[t].x = __shfl_sync(FULLMASK, x.x, t * 8 + cj);
+                        xc[t].y = __shfl_sync(FULLMASK, x.y, t * 8 + cj);
                     }
-                    if (NPAD % 2 == 1) {
-                        const float2 q = xv[NPAD - 1];
-                        r0 = fmaf(c[NPAD - 1].x, q.x, r0); r1 = fmaf(-c[NPAD - 1].y, q.y, r1);
-                        i0 = fmaf(c[NPAD - 1].x, q.y, i0); i1 = fmaf(c[NPAD - 1].y, q.x, i1);
+                    float2 y[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        float yr = 0.f, yi = 0.f;
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            yr = fmaf(c[k][t].x, xc[t].x, yr); yr = fmaf(-c[k][t].y, xc[t].y, yr);
+                            yi = fmaf(c[k][t].x, xc[t].y, yi); yi = fmaf(c[k][t].y, xc[t].x, yi);
+                        }
+                        y[k] = make_float2(yr, yi);
                     }
-                    const float yr = ((r0 + r1) + (r2a + r3)) * live, yi = ((i0 + i1) + (i2 + i3)) * live;
+                    // reduce-scatter over cj: after the three steps y[0] is the full sum of row ri + 4cj
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const bool up = (cj & 4) != 0;
+                        const float2 keep = up ? y[k + 4] : y[k], send = up ? y[k] : y[k + 4];
+                        y[k].x = keep.x + __shfl_xor_sync(FULLMASK, send.x, 4);
+                        y[k].y = keep.y + __shfl_xor_sync(FULLMASK, send.y, 4);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const bool up = (cj & 2) != 0;
+                        const float2 keep = up ? y[k + 2] : y[k], send = up ? y[k] : y[k + 2];
+                        y[k].x = keep.x + __shfl_xor_sync(FULLMASK, send.x, 2);
+                        y[k].y = keep.y + __shfl_xor_sync(FULLMASK, send.y, 2);
+                    }
+                    {
+                        const bool up = (cj & 1) != 0;
+                        const float2 keep = up ? y[1] : y[0], send = up ? y[0] : y[1];
+                        y[0].x = keep.x + __shfl_xor_sync(FULLMASK, send.x, 1);
+                        y[0].y = keep.y + __shfl_xor_sync(FULLMASK, send.y, 1);
+                    }
+                    const float yr = y[0].x, yi = y[0].y;
                     if ((it & 3) != 3) {
                         const float2 xn = make_float2(fmaf(-beta, xp.x, yr * inv_lam), fmaf(-beta, xp.y, yi * inv_lam));
                         xp = x; x = xn;
@@ -360,15 +377,11 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
                 }
                 st_it += it;
                 st_cap += conv ? 0 : 1;
-                xwarm = x; have_warm = false && conv;   // warm start disabled: it makes results depend on the block schedule at the 1e-7 level
                 if (lam < 1.0e-6f) tc = -7.f;             // evd.cpp:723-727
                 else {
                     // ---------------- phase reference (evd.cpp:738-749) -----------------
-                    float2* xv = s_vec + buf * 32;
-                    buf ^= 1;
-                    xv[lane] = x;
-                    __syncwarp();
-                    const float2 ref = xv[k0];
+                    const int ref_lane = (k0 & 3) * 8 + (k0 >> 2);            // owner of row k0
+                    const float2 ref = make_float2(__shfl_sync(FULLMASK, x.x, ref_lane), __shfl_sync(FULLMASK, x.y, ref_lane));
                     {
                         float ux = x.x * ref.x + x.y * ref.y, uy = x.y * ref.x - x.x * ref.y;
                         const float mm = ux * ux + uy * uy;
@@ -376,42 +389,44 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
                             const float rr = rsqrtf(ref.x * ref.x + ref.y * ref.y);
                             ux = ref.x * rr; uy = -ref.y * rr;
                         } else { const float rr = fast_rsqrt(mm); ux *= rr; uy *= rr; }
-                        if (lane == k0) { ux = 1.f; uy = 0.f; }
-                        o = make_float2(ux * live, uy * live);
+                        if (myrow == k0) { ux = 1.f; uy = 0.f; }
+                        o = (myrow < N) ? make_float2(ux, uy) : make_float2(0.f, 0.f);
                     }
                     // ---------------- compressed SLC (evd.cpp:755-762) ------------------
                     float cr = 0.f, ci = 0.f;
-                    if (lane < N && lane >= k0) {
-                        const float2 z = __ldg(&a.zpix[pg * NPAD + lane]);
+                    if (myrow < N && myrow >= k0) {
+                        const float2 z = __ldg(&a.zpix[pg * NPAD + myrow]);
                         cr = z.x * o.x + z.y * o.y;
                         ci = z.y * o.x - z.x * o.y;
                     }
                     // ---------------- temporal coherence (evd.cpp:770-786) --------------
-                    float2* ov = s_vec + buf * 32;
-                    buf ^= 1;
-                    ov[lane] = o;
-                    __syncwarp();
-                    float wr = 0.f, wi = 0.f;
-                    const float4* ov4 = reinterpret_cast<const float4*>(ov);
+                    // sum over my sub-block of  e_ij * conj(o_i) * o_j,  e = C_ij/|C_ij| (arg(0) = 0)
+                    float2 oc[4];
 #pragma unroll
-                    for (int j = 0; j < NPAD; ++j) {
-                        // pairs (lane, j) with j > lane, inside the matrix and (STBAS) the band;
-                        // e = C_ij / |C_ij| (arg(0) = 0 as in the reference)
-                        const bool use = (usemask >> j) & 1u;
-                        const float m2 = fmaf(c[j].x, c[j].x, c[j].y * c[j].y);
-                        const float rr = use ? fast_rsqrt(m2) : 0.f;
-                        const float ex = (m2 > 0.f) ? c[j].x * rr : (use ? 1.f : 0.f);
-                        const float ey = (m2 > 0.f) ? c[j].y * rr : 0.f;
-                        float2 oj;
-                        if (NPAD % 2 == 0) {
-                            const float4 q = ov4[j >> 1];
-                            oj = (j & 1) ? make_float2(q.z, q.w) : make_float2(q.x, q.y);
-                        } else oj = ov[j];
-                        wr = fmaf(ex, oj.x, wr); wr = fmaf(-ey, oj.y, wr);
-                        wi = fmaf(ex, oj.y, wi); wi = fmaf(ey, oj.x, wi);
+                    for (int t = 0; t < 4; ++t) {
+                        oc[t].x = __shfl_sync(FULLMASK, o.x, t * 8 + cj);
+                        oc[t].y = __shfl_sync(FULLMASK, o.y, t * 8 + cj);
                     }
-                    // conj(o_r) * w_r
-                    float sr = o.x * wr + o.y * wi, si = o.x * wi - o.y * wr;
+                    float sr = 0.f, si = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float2 ork = make_float2(__shfl_sync(FULLMASK, o.x, ri * 8 + k), __shfl_sync(FULLMASK, o.y, ri * 8 + k));
+                        float wr = 0.f, wi = 0.f;
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const bool use = (usemask >> (k * 4 + t)) & 1u;
+                            const float cx = c[k][t].x, cy = c[k][t].y;
+                            const float m2 = fmaf(cx, cx, cy * cy);
+                            const float rr = use ? fast_rsqrt(m2) : 0.f;
+                            const float ex = (m2 > 0.f) ? cx * rr : (use ? 1.f : 0.f);
+                            const float ey = (m2 > 0.f) ? cy * rr : 0.f;
+                            wr = fmaf(ex, oc[t].x, wr); wr = fmaf(-ey, oc[t].y, wr);
+                            wi = fmaf(ex, oc[t].y, wi); wi = fmaf(ey, oc[t].x, wi);
+                        }
+                        // conj(o_row) * w
+                        sr += ork.x * wr + ork.y * wi;
+                        si += ork.x * wi - ork.y * wr;
+                    }
 #pragma unroll
                     for (int s = 16; s > 0; s >>= 1) {
                         sr += __shfl_xor_sync(FULLMASK, sr, s);
@@ -424,7 +439,7 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
                     cmp = make_float2(cr * invn, ci * invn);
                 }
             }
-            if (lane < N) a.out[(long)lane * npix_block + pg] = o;
+            if (myrow < N) a.out[(long)myrow * npix_block + pg] = o;
             if (lane == 0) { a.tcorr[pg] = tc; a.comp[pg] = cmp; }
             __syncwarp();
         }
@@ -465,7 +480,7 @@ int evd_fast_padded_bands(int bands) {
     return 5 * (B < 2 ? 2 : B);
 }
 
-int evd_fast_block(int) { return 0; }      // this kernel reads the interleaved complex pixel-major layout
+int evd_fast_block(int) { return 0; }      // interleaved complex pixel-major layout
 
 bool evd_fast_supported(const EvdArgs& a) {
     return a.variant == 0 && (a.method == 0 || a.method == 2) && evd_fast_padded_bands(a.bands) > 0 &&
