@@ -37,7 +37,7 @@ struct fringe_ctx {
     std::string err;
     int64_t launches = 0;
     // workspaces reused across blocks
-    DevBuf amp, valid, zpix, adtab, alpha, stats;
+    DevBuf amp, valid, zpix, adtab, alpha, stats, scratch;
     DevBuf in_slc, in_mask, in_wts, o_count, o_wts, o_out, o_tcorr, o_comp;
     // cached AD2 table key
     int adtab_bands = -1;
@@ -223,7 +223,7 @@ int fringe_destroy(fringe_ctx* c) {
     if (!c) return FRINGE_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf* all[] = {&c->amp, &c->valid, &c->zpix, &c->adtab, &c->alpha, &c->stats, &c->in_slc, &c->in_mask,
+    DevBuf* all[] = {&c->amp, &c->valid, &c->zpix, &c->adtab, &c->alpha, &c->stats, &c->scratch, &c->in_slc, &c->in_mask,
                      &c->in_wts, &c->o_count, &c->o_wts, &c->o_out, &c->o_tcorr, &c->o_comp};
     for (DevBuf* b : all) b->release();
     for (int k = 0; k < FRINGE_KERNEL_COUNT; ++k)
@@ -513,7 +513,16 @@ int evd_launch_rows(fringe_ctx* ctx, const EvdPlan& plan, const float* slc, cons
     a.variant = variant; a.min_neighbors = min_neighbors;
     a.out = (float2*)out; a.tcorr = tcorr; a.comp = (float2*)comp;
     a.stats = (unsigned long long*)ctx->stats.p;
-    a.zblock = plan.zblock; a.tile_pairs = 0;
+    a.zblock = plan.zblock; a.tile_pairs = 0; a.scratch = nullptr;
+    if (!fringe::evd_fast_supported(a) || plan.generic) {
+        int gw; long gg; size_t gs; bool use_scratch;
+        fringe::evd_generic_plan(a, &gw, &gg, &gs, &use_scratch);
+        if (use_scratch) {
+            const bool dp = (method == FRINGE_EVD_MLE) || (variant == FRINGE_VARIANT_PHASE_LINK);
+            CU(ctx->scratch.ensure((size_t)gg * gw * fringe::evd_generic_workspace_bytes(bands, dp)));
+            a.scratch = (unsigned char*)ctx->scratch.p;
+        }
+    }
     a.force_generic = (plan.generic ? 1 : 0) | (getenv("FRINGE_EVD_DEBUG_SHORT") ? (atoi(getenv("FRINGE_EVD_DEBUG_SHORT")) << 1) : 0);
     int nl = 0;
     CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_EVD][0], st));

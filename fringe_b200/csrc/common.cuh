@@ -53,10 +53,15 @@ struct EvdArgs {
     float2* comp;            // [npix]
     unsigned long long* stats;   // [4] device counters
     int force_generic;           // debug: bit 0 bypasses the register-blocked kernel, upper bits cap iterations
+    unsigned char* scratch;      // generic kernel, large bands: per-warp workspaces in global memory (else NULL)
     int tile_pairs;              // set by the fast kernel's launcher: pixel pairs per CTA tile
     int zblock;                  // 0: zpix is interleaved complex; B > 0: de-interleaved per block of B samples
 };
 int evd_max_bands(int method, int variant);
+// launch geometry of the generic kernel; *use_scratch = the per-warp workspace does not fit shared
+// memory and EvdArgs::scratch must provide grid * warps * evd_generic_workspace_bytes() bytes
+void evd_generic_plan(const EvdArgs& a, int* warps, long* grid, size_t* smem, bool* use_scratch);
+size_t evd_generic_workspace_bytes(int bands, bool dp);
 cudaError_t launch_evd(const EvdArgs& a, cudaStream_t st, int* n_launches);
 
 // ---- evd_fast.cu ----------------------------------------------------------------------

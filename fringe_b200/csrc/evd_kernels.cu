@@ -94,17 +94,28 @@ __device__ __forceinline__ double2 cmulc(double2 a, double2 b) {   // a * conj(b
     return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
 }
 
+template <int HR>
+__device__ __forceinline__ double pick(const double (&v)[HR], int idx) {
+    double r = v[0];
+#pragma unroll
+    for (int h = 1; h < HR; ++h) r = (idx == h) ? v[h] : r;
+    return r;
+}
+
 // ======================================================================================
-// FP64 shared-memory linear algebra, one warp per matrix.  Row r is owned by lane r%32.
+// FP64 linear algebra on matrices in shared (or, for large N, global scratch) memory, one warp
+// per matrix.  Row r is owned by lane r%32; HR = rows per lane = ceil(n/32).
 // ======================================================================================
 // Lower Cholesky of the Hermitian matrix held in the lower triangle of F (row-major, stride
 // ld), in place; dinv[k] = 1/L[k][k].  Returns false (warp-uniform) on a non-positive pivot,
 // the same failure LAPACK zpotrf reports.
+template <int HR>
 __device__ bool chol_c(double2* F, double* dinv, int n, int ld, int lane) {
     for (int k = 0; k < n; ++k) {
-        double2 acc[2];
+        double2 acc[HR];
+        double accx[HR];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < HR; ++h) {
             const int i = lane + 32 * h;
             acc[h] = make_double2(0.0, 0.0);
             if (i >= k && i < n) {
@@ -115,13 +126,14 @@ __device__ bool chol_c(double2* F, double* dinv, int n, int ld, int lane) {
                 }
                 acc[h] = s;
             }
+            accx[h] = acc[h].x;
         }
-        const double d = __shfl_sync(FULL, (k < 32) ? acc[0].x : acc[1].x, k & 31);
+        const double d = __shfl_sync(FULL, pick<HR>(accx, k >> 5), k & 31);
         if (!(d > 0.0)) return false;
         const double rs = 1.0 / sqrt(d);
         __syncwarp();
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < HR; ++h) {
             const int i = lane + 32 * h;
             if (i > k && i < n) F[i * ld + k] = make_double2(acc[h].x * rs, acc[h].y * rs);
             if (i == k) { F[i * ld + k] = make_double2(d * rs, 0.0); dinv[k] = rs; }
@@ -131,11 +143,12 @@ __device__ bool chol_c(double2* F, double* dinv, int n, int ld, int lane) {
     return true;
 }
 
+template <int HR>
 __device__ bool chol_r(double* A, double* dinv, int n, int ld, int lane) {
     for (int k = 0; k < n; ++k) {
-        double acc[2];
+        double acc[HR];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < HR; ++h) {
             const int i = lane + 32 * h;
             acc[h] = 0.0;
             if (i >= k && i < n) {
@@ -144,12 +157,12 @@ __device__ bool chol_r(double* A, double* dinv, int n, int ld, int lane) {
                 acc[h] = s;
             }
         }
-        const double d = __shfl_sync(FULL, (k < 32) ? acc[0] : acc[1], k & 31);
+        const double d = __shfl_sync(FULL, pick<HR>(acc, k >> 5), k & 31);
         if (!(d > 0.0)) return false;
         const double rs = 1.0 / sqrt(d);
         __syncwarp();
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < HR; ++h) {
             const int i = lane + 32 * h;
             if (i > k && i < n) A[i * ld + k] = acc[h] * rs;
             if (i == k) { A[i * ld + k] = d * rs; dinv[k] = rs; }
@@ -160,17 +173,23 @@ __device__ bool chol_r(double* A, double* dinv, int n, int ld, int lane) {
 }
 
 // x <- (L L^H)^-1 x for the factor produced by chol_c; x[h] is element lane+32h.
+template <int HR>
 __device__ void chol_solve_c(const double2* F, const double* dinv, int n, int ld, int lane,
-                             double2 x[2]) {
+                             double2 (&x)[HR]) {
     for (int k = 0; k < n; ++k) {                       // L y = x
         const int src = k & 31;
         double2 xk;
-        xk.x = __shfl_sync(FULL, (k < 32) ? x[0].x : x[1].x, src);
-        xk.y = __shfl_sync(FULL, (k < 32) ? x[0].y : x[1].y, src);
+        {
+            double xs[HR], ys[HR];
+#pragma unroll
+            for (int h = 0; h < HR; ++h) { xs[h] = x[h].x; ys[h] = x[h].y; }
+            xk.x = __shfl_sync(FULL, pick<HR>(xs, k >> 5), src);
+            xk.y = __shfl_sync(FULL, pick<HR>(ys, k >> 5), src);
+        }
         const double dk = dinv[k];
         xk.x *= dk; xk.y *= dk;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < HR; ++h) {
             const int i = lane + 32 * h;
             if (i == k) x[h] = xk;
             else if (i > k && i < n) {
@@ -182,12 +201,17 @@ __device__ void chol_solve_c(const double2* F, const double* dinv, int n, int ld
     for (int k = n - 1; k >= 0; --k) {                  // L^H z = y
         const int src = k & 31;
         double2 xk;
-        xk.x = __shfl_sync(FULL, (k < 32) ? x[0].x : x[1].x, src);
-        xk.y = __shfl_sync(FULL, (k < 32) ? x[0].y : x[1].y, src);
+        {
+            double xs[HR], ys[HR];
+#pragma unroll
+            for (int h = 0; h < HR; ++h) { xs[h] = x[h].x; ys[h] = x[h].y; }
+            xk.x = __shfl_sync(FULL, pick<HR>(xs, k >> 5), src);
+            xk.y = __shfl_sync(FULL, pick<HR>(ys, k >> 5), src);
+        }
         const double dk = dinv[k];
         xk.x *= dk; xk.y *= dk;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < HR; ++h) {
             const int i = lane + 32 * h;
             if (i == k) x[h] = xk;
             else if (i < k) {
@@ -201,9 +225,10 @@ __device__ void chol_solve_c(const double2* F, const double* dinv, int n, int ld
 
 // A (lower Cholesky factor from chol_r, dinv) -> full symmetric inverse written back to A.
 // X is scratch (n x ld doubles).
+template <int HR>
 __device__ void chol_inverse_r(double* A, double* X, const double* dinv, int n, int ld, int lane) {
     // column c of L^-1, one column per lane (private forward substitution)
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < HR; ++h) {
         const int c = lane + 32 * h;
         if (c < n) {
             for (int i = 0; i < n; ++i) {
@@ -218,7 +243,7 @@ __device__ void chol_inverse_r(double* A, double* X, const double* dinv, int n, 
     }
     __syncwarp();
     // inv = X^T X ; row i per lane
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < HR; ++h) {
         const int i = lane + 32 * h;
         if (i < n) {
             for (int j = 0; j < n; ++j) {
@@ -278,18 +303,22 @@ __device__ inline WarpSmem carve(unsigned char* base, int n, bool dp) {
 
 // Dominant eigenpair of the FP32 coherence matrix by power iteration (lane owns rows
 // lane, lane+32).  v[] receives the unit eigenvector; returns the eigenvalue.
+template <int HR>
 __device__ float power_iteration(const WarpSmem& w, int n, int ldc, int lane, int start_col,
-                                 float2 v[2], int* iters, bool* capped) {
-    float2 x[2];
+                                 float2 (&v)[HR], int* iters, bool* capped) {
+    float2 x[HR];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < HR; ++h) {
         const int i = lane + 32 * h;
         x[h] = (i < n) ? w.C[i * ldc + start_col] : make_float2(0.f, 0.f);
     }
-    float nrm = warp_sum(x[0].x * x[0].x + x[0].y * x[0].y + x[1].x * x[1].x + x[1].y * x[1].y);
+    float nrm = 0.f;
+#pragma unroll
+    for (int h = 0; h < HR; ++h) nrm += x[h].x * x[h].x + x[h].y * x[h].y;
+    nrm = warp_sum(nrm);
     float sc = rsqrtf(nrm);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) { x[h].x *= sc; x[h].y *= sc; }
+    for (int h = 0; h < HR; ++h) { x[h].x *= sc; x[h].y *= sc; }
     float lam = 0.f;
     int it = 0;
     const int kMaxIter = 3000;
@@ -298,11 +327,11 @@ __device__ float power_iteration(const WarpSmem& w, int n, int ldc, int lane, in
     for (; it < kMaxIter; ++it) {
         __syncwarp();
 #pragma unroll
-        for (int h = 0; h < 2; ++h) { const int i = lane + 32 * h; if (i < n) w.xv[i] = x[h]; }
+        for (int h = 0; h < HR; ++h) { const int i = lane + 32 * h; if (i < n) w.xv[i] = x[h]; }
         __syncwarp();
-        float2 y[2];
+        float2 y[HR];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < HR; ++h) {
             const int i = lane + 32 * h;
             float yr = 0.f, yi = 0.f;
             if (i < n) {
@@ -316,10 +345,13 @@ __device__ float power_iteration(const WarpSmem& w, int n, int ldc, int lane, in
             }
             y[h] = make_float2(yr, yi);
         }
-        lam = warp_sum(x[0].x * y[0].x + x[0].y * y[0].y + x[1].x * y[1].x + x[1].y * y[1].y);
+        lam = 0.f;
+#pragma unroll
+        for (int h = 0; h < HR; ++h) lam += x[h].x * y[h].x + x[h].y * y[h].y;
+        lam = warp_sum(lam);
         float r2 = 0.f, n2 = 0.f;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < HR; ++h) {
             const float rx = y[h].x - lam * x[h].x, ry = y[h].y - lam * x[h].y;
             r2 += rx * rx + ry * ry;
             n2 += y[h].x * y[h].x + y[h].y * y[h].y;
@@ -328,11 +360,12 @@ __device__ float power_iteration(const WarpSmem& w, int n, int ldc, int lane, in
         n2 = warp_sum(n2);
         sc = rsqrtf(n2);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) { x[h].x = y[h].x * sc; x[h].y = y[h].y * sc; }
+        for (int h = 0; h < HR; ++h) { x[h].x = y[h].x * sc; x[h].y = y[h].y * sc; }
         if (r2 <= tol2 * lam * lam) { *capped = false; ++it; break; }
     }
     *iters = it;
-    v[0] = x[0]; v[1] = x[1];
+#pragma unroll
+    for (int h = 0; h < HR; ++h) v[h] = x[h];
     return lam;
 }
 
@@ -345,20 +378,20 @@ __device__ float power_iteration(const WarpSmem& w, int n, int ldc, int lane, in
 // MODE 1: M = n*I - C  (C PSD, trace n)      -> its smallest eigenvector is the DOMINANT
 //         eigenvector of C: the FP64 route for the EVD fallback of phase_link.cpp:586-600,
 //         *lam then receives the eigenvalue of C.
-template <int MODE>
+template <int MODE, int HR>
 __device__ bool smallest_eigen_mle(const WarpSmem& w, int n, int ldc, int ld, int lane,
-                                   double2 v[2], double* lam) {
+                                   double2 (&v)[HR], double* lam) {
     // scale = max diagonal of M (diag(C) = 1 so diag(Ainv o C) = diag(Ainv))
     double dmax = (double)n;
     if (MODE == 0) {
         dmax = 0.0;
-        for (int h = 0; h < 2; ++h) { const int i = lane + 32 * h; if (i < n) dmax = fmax(dmax, fabs(w.A[i * ld + i])); }
+        for (int h = 0; h < HR; ++h) { const int i = lane + 32 * h; if (i < n) dmax = fmax(dmax, fabs(w.A[i * ld + i])); }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(FULL, dmax, o));
     }
 
     auto assemble = [&](double sigma) {
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < HR; ++h) {
             const int i = lane + 32 * h;
             if (i < n) {
                 for (int j = 0; j <= i; ++j) {
@@ -372,11 +405,11 @@ __device__ bool smallest_eigen_mle(const WarpSmem& w, int n, int ldc, int ld, in
         }
         __syncwarp();
     };
-    auto matvec = [&](const double2 x[2], double2 y[2]) {      // y = M x
+    auto matvec = [&](const double2 (&x)[HR], double2 (&y)[HR]) {      // y = M x
         __syncwarp();
-        for (int h = 0; h < 2; ++h) { const int i = lane + 32 * h; if (i < n) w.xd[i] = x[h]; }
+        for (int h = 0; h < HR; ++h) { const int i = lane + 32 * h; if (i < n) w.xd[i] = x[h]; }
         __syncwarp();
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < HR; ++h) {
             const int i = lane + 32 * h;
             double2 s = make_double2(0.0, 0.0);
             if (i < n) {
@@ -401,14 +434,14 @@ __device__ bool smallest_eigen_mle(const WarpSmem& w, int n, int ldc, int ld, in
     for (int attempt = 0; attempt < 6 && !ok; ++attempt) {
         sigma = -back;
         assemble(sigma);
-        ok = chol_c(w.F, w.dinv, n, ld, lane);
+        ok = chol_c<HR>(w.F, w.dinv, n, ld, lane);
         back *= 1e3;
     }
     if (!ok) return false;
     double sigma_ok = sigma;
 
-    double2 x[2];
-    for (int h = 0; h < 2; ++h) {
+    double2 x[HR];
+    for (int h = 0; h < HR; ++h) {
         const int i = lane + 32 * h;
         x[h] = (i < n) ? make_double2(1.0, 0.0) : make_double2(0.0, 0.0);
         if (MODE == 1 && i < n) x[h] = v[h];          // caller-provided start (a column of C)
@@ -416,15 +449,19 @@ __device__ bool smallest_eigen_mle(const WarpSmem& w, int n, int ldc, int ld, in
     double rho = 0.0, res = 0.0;
     int since_shift = 0;
     for (int it = 0; it < 200; ++it) {
-        chol_solve_c(w.F, w.dinv, n, ld, lane, x);
-        double n2 = warp_sum(x[0].x * x[0].x + x[0].y * x[0].y + x[1].x * x[1].x + x[1].y * x[1].y);
+        chol_solve_c<HR>(w.F, w.dinv, n, ld, lane, x);
+        double n2 = 0.0;
+        for (int h = 0; h < HR; ++h) n2 += x[h].x * x[h].x + x[h].y * x[h].y;
+        n2 = warp_sum(n2);
         const double sc = 1.0 / sqrt(n2);
-        for (int h = 0; h < 2; ++h) { x[h].x *= sc; x[h].y *= sc; }
-        double2 y[2];
+        for (int h = 0; h < HR; ++h) { x[h].x *= sc; x[h].y *= sc; }
+        double2 y[HR];
         matvec(x, y);
-        rho = warp_sum(x[0].x * y[0].x + x[0].y * y[0].y + x[1].x * y[1].x + x[1].y * y[1].y);
+        rho = 0.0;
+        for (int h = 0; h < HR; ++h) rho += x[h].x * y[h].x + x[h].y * y[h].y;
+        rho = warp_sum(rho);
         double r2 = 0.0;
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < HR; ++h) {
             const double rx = y[h].x - rho * x[h].x, ry = y[h].y - rho * x[h].y;
             r2 += rx * rx + ry * ry;
         }
@@ -435,44 +472,49 @@ __device__ bool smallest_eigen_mle(const WarpSmem& w, int n, int ldc, int ld, in
         const double prop = rho - 2.0 * res;
         if (since_shift >= 2 && res > 1e-8 * dmax && prop > sigma_ok + 0.25 * (rho - sigma_ok)) {
             assemble(prop);
-            if (chol_c(w.F, w.dinv, n, ld, lane)) { sigma_ok = prop; }
+            if (chol_c<HR>(w.F, w.dinv, n, ld, lane)) { sigma_ok = prop; }
             else {                                  // prop >= lambda_min: bisect back
                 const double mid = 0.5 * (sigma_ok + prop);
                 assemble(mid);
-                if (chol_c(w.F, w.dinv, n, ld, lane)) sigma_ok = mid;
-                else { assemble(sigma_ok); if (!chol_c(w.F, w.dinv, n, ld, lane)) return false; }
+                if (chol_c<HR>(w.F, w.dinv, n, ld, lane)) sigma_ok = mid;
+                else { assemble(sigma_ok); if (!chol_c<HR>(w.F, w.dinv, n, ld, lane)) return false; }
             }
             since_shift = 0;
         }
     }
-    v[0] = x[0]; v[1] = x[1];
+    for (int h = 0; h < HR; ++h) v[h] = x[h];
     *lam = (MODE == 0) ? rho : (double)n - rho;
     return true;
 }
 
-template <int SLOTS, bool DP>
+template <int HR, bool DP>
 __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
     const int WARPS = blockDim.x >> 5;
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = a.bands, NP = a.NP;
     const int ldc = N | 1, ld = N | 1;
-    const WarpSmem w = carve(s_raw + (size_t)warp * evd_warp_smem_bytes(N, DP), N, DP);
+    // per-warp workspace: shared memory, or (large N) a slice of the global scratch buffer
+    unsigned char* wbase = a.scratch ? a.scratch + ((size_t)blockIdx.x * WARPS + warp) * evd_warp_smem_bytes(N, DP)
+                                     : s_raw + (size_t)warp * evd_warp_smem_bytes(N, DP);
+    const WarpSmem w = carve(wbase, N, DP);
     const long npix_block = (long)a.cols * a.lines;
 
-    // entry -> (ti,tj), ti <= tj, row-major over the upper triangle incl. diagonal
+    // Upper-triangle entries (row-major, diagonal included) are dealt to the lanes in chunks of
+    // CH*32: entry e = chunk*CH*32 + s*32 + lane.  One chunk covers bands <= 31; larger matrices
+    // run the SHP loop once per chunk (the neighbour vectors come from L1/L2 again).
+    constexpr int CH = 16;
     const int E = N * (N + 1) / 2;
-    unsigned short eti[SLOTS], etj[SLOTS];
-    {
-        int ti = 0, tj = 0, e = 0;
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-            const int target = s * 32 + lane;
-            while (e < target && ti < N) { ++e; if (++tj >= N) { ++ti; tj = ti; } }
-            eti[s] = (target < E) ? ti : 0xffff;
-            etj[s] = (target < E) ? tj : 0xffff;
-        }
-    }
+    const int nchunks = (E + CH * 32 - 1) / (CH * 32);
+    auto row_off = [N](int t) { return t * N - ((t * (t - 1)) >> 1); };
+    auto entry_of = [&](int e, int& ti, int& tj) {
+        const float b = (float)(2 * N + 1);
+        int t = (int)((b - sqrtf(fmaxf(b * b - 8.0f * (float)e, 0.f))) * 0.5f);
+        t = max(0, min(t, N - 1));
+        while (t + 1 < N && row_off(t + 1) <= e) ++t;
+        while (t > 0 && row_off(t) > e) --t;
+        ti = t; tj = t + (e - row_off(t));
+    };
 
     const int WX = 2 * a.Nx + 1, W = WX * (2 * a.Ny + 1), center = a.Ny * WX + a.Nx;
     const int k0 = a.mini_stack_count - 1;
@@ -492,7 +534,9 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
         const uint32_t cword = __shfl_sync(FULL, myword, center >> 5);
         float tc = 0.f;
         bool have_vec = false;
-        float2 vf[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        float2 vf[HR];
+#pragma unroll
+        for (int h = 0; h < HR; ++h) vf[h] = make_float2(0.f, 0.f);
 
         if ((cword >> (center & 31)) & 1u) {
             // ---------------- covariance accumulation (evd.cpp:537-564) ----------------
@@ -501,83 +545,99 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
             // term as libgcc's complex multiply does, double accumulation in raster order
             // (evd.cpp:557-559) -- because inv(|C|) amplifies covariance rounding differences.
             typedef typename std::conditional<DP, double2, float2>::type acc_t;
-            acc_t acc[SLOTS];
+            double pwd[HR];
 #pragma unroll
-            for (int s = 0; s < SLOTS; ++s) { acc[s].x = 0; acc[s].y = 0; }
-            double pwd[2] = {0.0, 0.0};
+            for (int h = 0; h < HR; ++h) pwd[h] = 0.0;
             int npix = 0;
-            int dy = -a.Ny, dx = -a.Nx;
-            for (int f = 0; f < W; ++f) {
-                const uint32_t wd = __shfl_sync(FULL, myword, f >> 5);
-                const int yy = ci + dy, xx = cj + dx;
-                if (((wd >> (f & 31)) & 1u) && yy >= 0 && yy < a.lines && xx >= 0 && xx < a.cols) {
-                    ++npix;
-                    const float2* zq = a.zpix + ((long)yy * a.cols + xx) * NP;
-#pragma unroll
-                    for (int s = 0; s < SLOTS; ++s) {
-                        if (eti[s] != 0xffff) {
-                            const float2 zi = __ldg(zq + eti[s]);
-                            const float2 zj = __ldg(zq + etj[s]);
-                            if (DP) {
-                                const float pr = __fadd_rn(__fmul_rn(zi.x, zj.x), __fmul_rn(zi.y, zj.y));
-                                const float pi = __fsub_rn(__fmul_rn(zi.y, zj.x), __fmul_rn(zi.x, zj.y));
-                                acc[s].x += pr; acc[s].y += pi;
-                            } else {
-                                acc[s].x = fmaf(zi.x, zj.x, acc[s].x); acc[s].x = fmaf(zi.y, zj.y, acc[s].x);
-                                acc[s].y = fmaf(zi.y, zj.x, acc[s].y); acc[s].y = fmaf(-zi.x, zj.y, acc[s].y);
-                            }
-                        }
-                    }
-                    if (DP) {                  // |z|^2: float hypot, squared and summed in double (:558)
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int t = lane + 32 * h;
-                            if (t < N) {
-                                const float2 z = __ldg(zq + t);
-                                const float hy = (float)__dsqrt_rn(__dadd_rn(__dmul_rn((double)z.x, (double)z.x),
-                                                                             __dmul_rn((double)z.y, (double)z.y)));
-                                pwd[h] += (double)hy * (double)hy;
-                            }
-                        }
-                    }
-                }
-                if (++dx > a.Nx) { dx = -a.Nx; ++dy; }
-            }
             const int need = (a.variant == 0) ? 2 : a.min_neighbors;
+            __syncwarp();
+#pragma unroll 1
+            for (int chunk = 0; chunk < nchunks; ++chunk) {
+                unsigned short eti[CH], etj[CH];
+#pragma unroll
+                for (int s = 0; s < CH; ++s) {
+                    const int e = (chunk * CH + s) * 32 + lane;
+                    int ti = 0xffff, tj = 0xffff;
+                    if (e < E) entry_of(e, ti, tj);
+                    eti[s] = (unsigned short)ti; etj[s] = (unsigned short)tj;
+                }
+                acc_t acc[CH];
+#pragma unroll
+                for (int s = 0; s < CH; ++s) { acc[s].x = 0; acc[s].y = 0; }
+                int cnt = 0;
+                int dy = -a.Ny, dx = -a.Nx;
+                for (int f = 0; f < W; ++f) {
+                    const uint32_t wd = __shfl_sync(FULL, myword, f >> 5);
+                    const int yy = ci + dy, xx = cj + dx;
+                    if (((wd >> (f & 31)) & 1u) && yy >= 0 && yy < a.lines && xx >= 0 && xx < a.cols) {
+                        ++cnt;
+                        const float2* zq = a.zpix + ((long)yy * a.cols + xx) * NP;
+#pragma unroll
+                        for (int s = 0; s < CH; ++s) {
+                            if (eti[s] != 0xffff) {
+                                const float2 zi = __ldg(zq + eti[s]);
+                                const float2 zj = __ldg(zq + etj[s]);
+                                if (DP) {
+                                    const float pr = __fadd_rn(__fmul_rn(zi.x, zj.x), __fmul_rn(zi.y, zj.y));
+                                    const float pi = __fsub_rn(__fmul_rn(zi.y, zj.x), __fmul_rn(zi.x, zj.y));
+                                    acc[s].x += pr; acc[s].y += pi;
+                                } else {
+                                    acc[s].x = fmaf(zi.x, zj.x, acc[s].x); acc[s].x = fmaf(zi.y, zj.y, acc[s].x);
+                                    acc[s].y = fmaf(zi.y, zj.x, acc[s].y); acc[s].y = fmaf(-zi.x, zj.y, acc[s].y);
+                                }
+                            }
+                        }
+                        if (DP && chunk == 0) {    // |z|^2: float hypot, squared and summed in double (:558)
+#pragma unroll
+                            for (int h = 0; h < HR; ++h) {
+                                const int t = lane + 32 * h;
+                                if (t < N) {
+                                    const float2 z = __ldg(zq + t);
+                                    const float hy = (float)__dsqrt_rn(__dadd_rn(__dmul_rn((double)z.x, (double)z.x),
+                                                                                 __dmul_rn((double)z.y, (double)z.y)));
+                                    pwd[h] += (double)hy * (double)hy;
+                                }
+                            }
+                        }
+                    }
+                    if (++dx > a.Nx) { dx = -a.Nx; ++dy; }
+                }
+                npix = cnt;
+                if (npix < need) break;
+                // park the raw sums (upper triangle); the diagonal gives the FP32 powers
+#pragma unroll
+                for (int s = 0; s < CH; ++s) {
+                    if (eti[s] == 0xffff) continue;
+                    const int ti = eti[s], tj = etj[s];
+                    if (DP) { if (ti != tj) w.Cd[ti * ld + tj] = make_double2((double)acc[s].x, (double)acc[s].y); }
+                    else if (ti == tj) w.pw[ti] = sqrtf((float)acc[s].x);
+                    else w.C[ti * ldc + tj] = make_float2((float)acc[s].x, (float)acc[s].y);
+                }
+            }
             if (npix >= need) {
                 // ---------------- coherence matrix (evd.cpp:569-582) -------------------
+                if (DP) { for (int h = 0; h < HR; ++h) { const int t = lane + 32 * h; if (t < N) w.dinv[t] = pwd[h]; } }
                 __syncwarp();
-                if (DP) {
-                    for (int h = 0; h < 2; ++h) { const int t = lane + 32 * h; if (t < N) w.dinv[t] = pwd[h]; }
-                    __syncwarp();
-#pragma unroll
-                    for (int s = 0; s < SLOTS; ++s) {
-                        if (eti[s] == 0xffff) continue;
-                        const int ti = eti[s], tj = etj[s];
-                        if (ti == tj) {
-                            w.C[ti * ldc + ti] = make_float2(1.f, 0.f);
-                            w.Cd[ti * ld + ti] = make_double2(1.0, 0.0);
-                            continue;
-                        }
+                for (int e = lane; e < E; e += 32) {
+                    int ti, tj;
+                    entry_of(e, ti, tj);
+                    if (ti == tj) {
+                        w.C[ti * ldc + ti] = make_float2(1.f, 0.f);
+                        if (DP) w.Cd[ti * ld + ti] = make_double2(1.0, 0.0);
+                        continue;
+                    }
+                    if (DP) {
+                        const double2 raw = w.Cd[ti * ld + tj];
                         const double den = sqrt(w.dinv[ti] * w.dinv[tj]);      // evd.cpp:577
-                        const double2 c = make_double2((double)acc[s].x / den, (double)acc[s].y / den);
+                        const double2 c = make_double2(raw.x / den, raw.y / den);
                         w.Cd[ti * ld + tj] = c;
                         w.Cd[tj * ld + ti] = make_double2(c.x, -c.y);
                         w.C[ti * ldc + tj] = make_float2((float)c.x, (float)c.y);
                         w.C[tj * ldc + ti] = make_float2((float)c.x, -(float)c.y);
-                    }
-                } else {
-#pragma unroll
-                    for (int s = 0; s < SLOTS; ++s)
-                        if (eti[s] != 0xffff && eti[s] == etj[s]) w.pw[eti[s]] = sqrtf((float)acc[s].x);
-                    __syncwarp();
-#pragma unroll
-                    for (int s = 0; s < SLOTS; ++s) {
-                        if (eti[s] == 0xffff) continue;
-                        const int ti = eti[s], tj = etj[s];
-                        if (ti == tj) { w.C[ti * ldc + ti] = make_float2(1.f, 0.f); continue; }
+                    } else {
+                        const float2 raw = w.C[ti * ldc + tj];
                         const float inv = 1.0f / (w.pw[ti] * w.pw[tj]);
-                        float2 c = make_float2((float)acc[s].x * inv, (float)acc[s].y * inv);
+                        const float2 c = make_float2(raw.x * inv, raw.y * inv);
                         w.C[ti * ldc + tj] = c;
                         w.C[tj * ldc + ti] = make_float2(c.x, -c.y);
                     }
@@ -591,19 +651,19 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
                     ++st_dp;
                     // ---- gate 1 (evd.cpp MLE only): lambda_min(C) >= 1e-6 -------------
                     if (a.variant == 0) {
-                        for (int h = 0; h < 2; ++h) {
+                        for (int h = 0; h < HR; ++h) {
                             const int r = lane + 32 * h;
                             if (r < N) for (int j = 0; j <= r; ++j) {
                                 w.F[r * ld + j] = (j == r) ? make_double2(1.0 - 1.0e-6, 0.0) : w.Cd[r * ld + j];
                             }
                         }
                         __syncwarp();
-                        if (!chol_c(w.F, w.dinv, N, ld, lane)) { tc = -2.f; failed = true; }
+                        if (!chol_c<HR>(w.F, w.dinv, N, ld, lane)) { tc = -2.f; failed = true; }
                     }
                     // ---- |C| and its inverse -------------------------------------------
                     if (!failed) {
                         auto fill_abs = [&](double dshift) {
-                            for (int h = 0; h < 2; ++h) {
+                            for (int h = 0; h < HR; ++h) {
                                 const int r = lane + 32 * h;
                                 if (r < N) for (int j = 0; j <= r; ++j) {
                                     const double2 c = w.Cd[r * ld + j];
@@ -614,18 +674,18 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
                         };
                         if (a.variant == 0) {               // gate 2: lambda_min(|C|) >= 1e-6
                             fill_abs(1.0e-6);
-                            if (!chol_r(w.A, w.dinv, N, ld, lane)) { tc = -4.f; failed = true; }
+                            if (!chol_r<HR>(w.A, w.dinv, N, ld, lane)) { tc = -4.f; failed = true; }
                         }
                         if (!failed) {
                             fill_abs(0.0);
-                            if (!chol_r(w.A, w.dinv, N, ld, lane)) {
+                            if (!chol_r<HR>(w.A, w.dinv, N, ld, lane)) {
                                 if (a.variant == 0) { tc = -5.f; failed = true; }
                                 else run_evd = true;
                             } else {
-                                chol_inverse_r(w.A, reinterpret_cast<double*>(w.F), w.dinv, N, ld, lane);
-                                double2 vd[2];
+                                chol_inverse_r<HR>(w.A, reinterpret_cast<double*>(w.F), w.dinv, N, ld, lane);
+                                double2 vd[HR];
                                 double lam = 0.0;
-                                if (!smallest_eigen_mle<0>(w, N, ldc, ld, lane, vd, &lam)) {
+                                if (!smallest_eigen_mle<0, HR>(w, N, ldc, ld, lane, vd, &lam)) {
                                     if (a.variant == 0) { tc = -6.f; failed = true; }
                                     else run_evd = true;
                                 } else if (a.variant == 0 && lam < 1.0e-6) { tc = -7.f; failed = true; }
@@ -633,11 +693,11 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
                                     // rotate in double so that the reference component is real
                                     // positive, then hand the FP32 copy to the post-processing
                                     __syncwarp();
-                                    for (int h = 0; h < 2; ++h) { const int r = lane + 32 * h; if (r < N) w.xd[r] = vd[h]; }
+                                    for (int h = 0; h < HR; ++h) { const int r = lane + 32 * h; if (r < N) w.xd[r] = vd[h]; }
                                     __syncwarp();
                                     const double2 ref = w.xd[k0];
                                     const double rn = 1.0 / fmax(hypot(ref.x, ref.y), 1e-300);
-                                    for (int h = 0; h < 2; ++h) {
+                                    for (int h = 0; h < HR; ++h) {
                                         const double2 u = cmulc(vd[h], make_double2(ref.x * rn, ref.y * rn));
                                         vf[h] = make_float2((float)u.x, (float)u.y);
                                     }
@@ -650,7 +710,7 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
                 if (run_evd && !failed) {
                     // ---------------- EVD / STBAS (evd.cpp:689-732) --------------------
                     if (isstbas && a.variant == 0) {
-                        for (int h = 0; h < 2; ++h) {
+                        for (int h = 0; h < HR; ++h) {
                             const int r = lane + 32 * h;
                             if (r < N) for (int j = 0; j < N; ++j)
                                 if (abs(j - r) > BW) w.C[r * ldc + j] = make_float2(0.f, 0.f);
@@ -661,19 +721,19 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
                     if (DP && a.variant == 1) {
                         // phase_link's EVD fallback in FP64 (the exact covariance is already in
                         // w.Cd): certified inverse iteration on n*I - C
-                        double2 vd[2];
-                        for (int h = 0; h < 2; ++h) {
+                        double2 vd[HR];
+                        for (int h = 0; h < HR; ++h) {
                             const int r = lane + 32 * h;
                             vd[h] = (r < N) ? w.Cd[r * ld + k0] : make_double2(0.0, 0.0);
                         }
                         double lamd = 0.0;
-                        if (smallest_eigen_mle<1>(w, N, ldc, ld, lane, vd, &lamd)) {
+                        if (smallest_eigen_mle<1, HR>(w, N, ldc, ld, lane, vd, &lamd)) {
                             __syncwarp();
-                            for (int h = 0; h < 2; ++h) { const int r = lane + 32 * h; if (r < N) w.xd[r] = vd[h]; }
+                            for (int h = 0; h < HR; ++h) { const int r = lane + 32 * h; if (r < N) w.xd[r] = vd[h]; }
                             __syncwarp();
                             const double2 ref = w.xd[k0];
                             const double rn = 1.0 / fmax(hypot(ref.x, ref.y), 1e-300);
-                            for (int h = 0; h < 2; ++h) {
+                            for (int h = 0; h < HR; ++h) {
                                 const double2 u = cmulc(vd[h], make_double2(ref.x * rn, ref.y * rn));
                                 vf[h] = make_float2((float)u.x, (float)u.y);
                             }
@@ -684,7 +744,7 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
                     if (!done) {
                         int iters = 0;
                         bool capped = false;
-                        const float lam = power_iteration(w, N, ldc, lane, k0, vf, &iters, &capped);
+                        const float lam = power_iteration<HR>(w, N, ldc, lane, k0, vf, &iters, &capped);
                         st_it += iters;
                         st_cap += capped ? 1 : 0;
                         if (a.variant == 0 && lam < 1.0e-6f) { tc = -7.f; }
@@ -695,15 +755,17 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
         }
 
         // -------- phase reference, compression, temporal coherence (evd.cpp:738-786) --
-        float2 o[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        float2 o[HR];
+#pragma unroll
+        for (int h = 0; h < HR; ++h) o[h] = make_float2(0.f, 0.f);
         float2 cmp = make_float2(0.f, 0.f);
         if (have_vec) {
             __syncwarp();
-            for (int h = 0; h < 2; ++h) { const int r = lane + 32 * h; if (r < N) w.xv[r] = vf[h]; }
+            for (int h = 0; h < HR; ++h) { const int r = lane + 32 * h; if (r < N) w.xv[r] = vf[h]; }
             __syncwarp();
             const float2 ref = w.xv[k0];
             float cr = 0.f, cim = 0.f;
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < HR; ++h) {
                 const int r = lane + 32 * h;
                 if (r < N) {
                     float ux = vf[h].x * ref.x + vf[h].y * ref.y;      // v * conj(ref)
@@ -726,14 +788,14 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
             const float invn = 1.0f / (float)(N - a.mini_stack_count + 1);
             cmp = make_float2(cr * invn, cim * invn);
             __syncwarp();
-            for (int h = 0; h < 2; ++h) { const int r = lane + 32 * h; if (r < N) w.xv[r] = o[h]; }
+            for (int h = 0; h < HR; ++h) { const int r = lane + 32 * h; if (r < N) w.xv[r] = o[h]; }
             __syncwarp();
             float sr = 0.f, si = 0.f;
             int cnt = 0;
-#pragma unroll
-            for (int s = 0; s < SLOTS; ++s) {
-                if (eti[s] == 0xffff || eti[s] == etj[s]) continue;
-                const int ti = eti[s], tj = etj[s];
+            for (int e = lane; e < E; e += 32) {
+                int ti, tj;
+                entry_of(e, ti, tj);
+                if (ti == tj) continue;
                 if (isstbas && (tj - ti) > BW) continue;
                 // upper entry was possibly zeroed for STBAS only outside the band -> untouched here
                 const float2 c = w.C[ti * ldc + tj];
@@ -751,7 +813,7 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
             cnt = __reduce_add_sync(FULL, cnt);
             tc = sqrtf(sr * sr + si * si) / (float)cnt;
         }
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < HR; ++h) {
             const int r = lane + 32 * h;
             if (r < N) a.out[(long)r * npix_block + p] = o[h];
         }
@@ -767,42 +829,54 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
     }
 }
 
-int evd_max_bands(int, int) { return 64; }
+int evd_max_bands(int, int) { return 128; }
 
-template <int SLOTS, bool DP>
-static cudaError_t launch_evd_t(const EvdArgs& a, cudaStream_t st, int WARPS) {
-    const size_t smem = evd_warp_smem_bytes(a.bands, DP) * WARPS;
-    cudaError_t e = cudaFuncSetAttribute(k_evd<SLOTS, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+size_t evd_generic_workspace_bytes(int bands, bool dp) { return evd_warp_smem_bytes(bands, dp); }
+
+// grid x warps chosen so that the (optional) global scratch stays bounded
+template <int HR, bool DP>
+static cudaError_t launch_evd_t(const EvdArgs& a, cudaStream_t st, int WARPS, long grid, size_t smem) {
+    cudaError_t e = cudaFuncSetAttribute(k_evd<HR, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    int dev = 0, nsm = 148, occ = 1;
+    k_evd<HR, DP><<<(unsigned)grid, WARPS * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+void evd_generic_plan(const EvdArgs& a, int* warps, long* grid, size_t* smem, bool* use_scratch) {
+    const bool dp = (a.method == 1) || (a.variant == 1);
+    const size_t per_warp = evd_warp_smem_bytes(a.bands, dp);
+    const size_t budget = 200 * 1024;
+    int w = (int)(budget / per_warp);
+    *use_scratch = (w < 1);
+    if (w < 1) w = 4;                 // workspace in global memory: no shared-memory limit
+    if (w > 8) w = 8;
+    if (a.bands > 31 && w > 4) w = 4;
+    int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_evd<SLOTS, DP>, WARPS * 32, smem);
-    if (occ < 1) occ = 1;
     const long total = (long)a.n_lines * a.cols;
-    long grid = (long)nsm * occ * 4;                 // a few chunks per resident CTA slot
-    const long maxgrid = (total + WARPS * 8 - 1) / (WARPS * 8);
-    if (grid > maxgrid) grid = maxgrid;
-    if (grid < 1) grid = 1;
-    k_evd<SLOTS, DP><<<(unsigned)grid, WARPS * 32, smem, st>>>(a);
-    return cudaGetLastError();
+    long g = (long)nsm * (*use_scratch ? 2 : 4);
+    const long maxgrid = (total + w * 8 - 1) / (w * 8);
+    if (g > maxgrid) g = maxgrid;
+    if (g < 1) g = 1;
+    *warps = w; *grid = g;
+    *smem = *use_scratch ? 0 : per_warp * w;
 }
 
 template <bool DP>
 static cudaError_t launch_evd_dp(const EvdArgs& a, cudaStream_t st) {
-    const int E = a.bands * (a.bands + 1) / 2;
-    const int slots = (E + 31) / 32;
-    const size_t per_warp = evd_warp_smem_bytes(a.bands, DP);
-    const size_t budget = 200 * 1024;
-    int warps = (int)(budget / per_warp);
-    if (warps < 1) return cudaErrorInvalidValue;
-    if (warps > 8) warps = 8;
-    if (slots > 16 && warps > 4) warps = 4;
-    if (slots <= 4)  return launch_evd_t<4, DP>(a, st, warps);
-    if (slots <= 8)  return launch_evd_t<8, DP>(a, st, warps);
-    if (slots <= 16) return launch_evd_t<16, DP>(a, st, warps);
-    if (slots <= 33) return launch_evd_t<33, DP>(a, st, warps);
-    if (slots <= 65) return launch_evd_t<65, DP>(a, st, warps);
+    int warps; long grid; size_t smem; bool use_scratch;
+    evd_generic_plan(a, &warps, &grid, &smem, &use_scratch);
+    if (use_scratch && !a.scratch) return cudaErrorInvalidValue;
+    EvdArgs b = a;
+    if (!use_scratch) b.scratch = nullptr;
+    const int hr = (a.bands + 31) / 32;
+    switch (hr) {
+        case 1: return launch_evd_t<1, DP>(b, st, warps, grid, smem);
+        case 2: return launch_evd_t<2, DP>(b, st, warps, grid, smem);
+        case 3: return launch_evd_t<3, DP>(b, st, warps, grid, smem);
+        case 4: return launch_evd_t<4, DP>(b, st, warps, grid, smem);
+    }
     return cudaErrorInvalidValue;
 }
 

@@ -135,3 +135,18 @@ def test_argument_errors(ctx):
         ctx.evd_block(slc, wts, 1, 1, method="STBAS", bandwidth=-1)       # evd.cpp:77 -> rc 101
     with pytest.raises(FringeError):
         ctx.evd_block(slc, wts, 1, 1, method="EVD", mini_stack_count=9)
+
+
+@pytest.mark.parametrize("bands,method,variant", [(40, "EVD", 0), (40, "MLE", 0), (64, "EVD", 0), (70, "MLE", 1),
+                                                   (100, "EVD", 0), (100, "MLE", 1), (31, "EVD", 0), (33, "STBAS", 0)])
+def test_large_band_counts_generic_kernel(ctx, oracle_lib, bands, method, variant):
+    """Bands beyond the register-blocked kernel (<= 30) go through the generic kernel: several
+    entry chunks, up to 4 matrix rows per lane and, from ~70 bands on, per-warp workspaces in global
+    memory.  bands=100 with the phase_link flow is BASELINE.json configs[2] in miniature."""
+    slc = synth.make_stack(bands, 14, 40, seed=bands, region=16)
+    wts = _nmap(oracle_lib, slc, 5, 2)
+    code = {"EVD": 0, "MLE": 1, "STBAS": 2}[method]
+    kw = dict(method=code, variant=variant, min_neighbors=5, bandwidth=7)
+    ref = oracle_lib.evd_block(slc, wts, 5, 2, **kw)
+    gpu = ctx.evd_block(slc, wts, 5, 2, method=method, variant=variant, min_neighbors=5, bandwidth=7)
+    _compare(ref, gpu, borderline=3)
