@@ -53,8 +53,9 @@ struct FastCfg {
     static constexpr int WARPS = 4;
     // per warp: two full matrices, two broadcast vectors (double buffered), powers
     static constexpr int MAT = NPAD * NPAD;             // float2 elements per matrix
+    // ... and the SHP index lists of the two pixels (2 x 64 ints)
     static constexpr int SMEM_PER_WARP =
-        (((2 * MAT + 2 * 32) * (int)sizeof(float2) + 2 * NPAD * (int)sizeof(float)) + 15) & ~15;
+        (((2 * MAT + 2 * 32) * (int)sizeof(float2) + 2 * NPAD * (int)sizeof(float) + 128 * (int)sizeof(int)) + 15) & ~15;
 };
 
 // One SHP's operands for a lane's block: rows B*bi.. and columns B*bj.. of the sample vector.
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
     float2* s_mat = reinterpret_cast<float2*>(base);                       // [2][NPAD][NPAD]
     float2* s_vec = s_mat + 2 * Cfg::MAT;                                  // [2][32]
     float* s_pw = reinterpret_cast<float*>(s_vec + 64);                    // [2][NPAD]
+    int* s_list = reinterpret_cast<int*>(s_pw + 2 * NPAD);                 // [2][64]
 
     // block coordinates of this lane inside its pixel group
     int bi = 0, bj = 0;
@@ -124,6 +126,7 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
         bj = bi + k;
     }
     const bool blk_active = (l < 15);
+    if (!blk_active) { bi = 0; bj = 0; }           // lanes 15 / 31 shadow block (0,0); their results are never stored
     const int oa = B * bi, ob = B * bj;
 
     const int k0 = a.mini_stack_count - 1;
@@ -142,7 +145,6 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
         inv_pairs = 1.0f / (float)cnt;
     }
     const long npix_block = (long)a.cols * a.lines;
-    const float2* zero_row = a.zpix + npix_block * NPAD;    // one all-zero sample vector
 
     const int pairs_per_row = (a.cols + 1) >> 1;
     const long total_pairs = (long)a.n_lines * pairs_per_row;
@@ -159,7 +161,6 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
         const int col0 = 2 * (int)(pr % pairs_per_row);
         const int mycol = col0 + grp;
         const bool pix_exists = mycol < a.cols;
-        const long p = (long)row * a.cols + mycol;
 
         // ------------------------- covariance (evd.cpp:537-564) -------------------------
         float2 acc[B][B];
@@ -167,34 +168,55 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
         for (int i = 0; i < B; ++i)
 #pragma unroll
             for (int j = 0; j < B; ++j) acc[i][j] = make_float2(0.f, 0.f);
-        int npix = 0;
-        bool center_on = false;
-        if (pix_exists) center_on = (__ldg(&a.wts[p * a.nulong + (center >> 5)]) >> (center & 31)) & 1u;
+        // SHP address lists.  All 32 lanes turn one 32-bit mask word of one pixel into sample-vector
+        // indices at once (bit -> window offset -> bounds check, ballot + popcount for the
+        // compacted slot) and park them in shared memory; the accumulation loop below then costs
+        // one shared-memory read and one multiply per SHP instead of ~30 integer instructions
+        // (ncu: the dispatch stalls of this phase sat on exactly those instructions).  Lists are
+        // built for two mask words (64 window positions) at a time.
+        int npix = 0;                                 // group-uniform count of usable SHPs
+        const long p0 = (long)row * a.cols + col0;
+        const bool ex1 = (col0 + 1) < a.cols;
+        const bool con0 = (__ldg(&a.wts[p0 * a.nulong + (center >> 5)]) >> (center & 31)) & 1u;
+        const bool con1 = ex1 && ((__ldg(&a.wts[(p0 + 1) * a.nulong + (center >> 5)]) >> (center & 31)) & 1u);
+        const bool center_on = grp ? con1 : con0;
+        const int zero_idx = (int)npix_block;         // index of the all-zero sample vector
 #pragma unroll 1
-        for (int w = 0; w < a.nulong; ++w) {
-            uint32_t m = (pix_exists && center_on && blk_active) ? __ldg(&a.wts[p * a.nulong + w]) : 0u;
-            // uniform trip count: the longer of the two pixels' bit lists in this word
-            const int trips = __reduce_max_sync(FULLMASK, __popc(m));
-            // address of the next SHP's sample vector (zero row when exhausted / outside block)
-            auto next_ptr = [&]() -> const float2* {
-                const bool on = (m != 0u);
-                const int f = w * 32 + (on ? (__ffs(m) - 1) : 0);
-                m &= (m - 1u);
-                const short2 d = s_off[f];
-                const int yy = row + d.x, xx = mycol + d.y;
-                const bool inb = on && yy >= 0 && yy < a.lines && xx >= 0 && xx < a.cols;
-                npix += inb ? 1 : 0;
-                return inb ? a.zpix + ((long)yy * a.cols + xx) * NPAD : zero_row;
-            };
+        for (int w0 = 0; w0 < a.nulong; w0 += 2) {
+            int n0 = 0, n1 = 0;                       // list lengths of the two pixels (warp-uniform)
+            __syncwarp();
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int w = w0 + c;
+                    const bool live = (w < a.nulong) && (g ? con1 : con0);
+                    const uint32_t word = live ? __ldg(&a.wts[(p0 + g) * a.nulong + w]) : 0u;
+                    const short2 d = s_off[min(w, a.nulong - 1) * 32 + lane];
+                    const int yy = row + d.x, xx = col0 + g + d.y;
+                    const bool ok = ((word >> lane) & 1u) && yy >= 0 && yy < a.lines && xx >= 0 && xx < a.cols;
+                    const uint32_t V = __ballot_sync(FULLMASK, ok);
+                    int& n = g ? n1 : n0;
+                    if (ok) s_list[g * 64 + n + __popc(V & ((1u << lane) - 1u))] = yy * a.cols + xx;
+                    n += __popc(V);
+                }
+            }
+            const int trips = (max(n0, n1) + 1) & ~1;   // SHPs are consumed two at a time
+            // pad the shorter list(s) with the zero vector
+            for (int k = n0 + lane; k < trips; k += 32) s_list[k] = zero_idx;
+            for (int k = n1 + lane; k < trips; k += 32) s_list[64 + k] = zero_idx;
+            __syncwarp();
+            npix += grp ? n1 : n0;
+            const int* lst = s_list + grp * 64;
             // two-stage software pipeline: while one SHP is accumulated the next one's samples
-            // are already in flight (exhausted lists read the zero row, so no tail handling)
+            // are already in flight
             Operands<B> opA, opB;
-            if (trips > 0) opA.load(next_ptr(), oa, ob);
+            if (trips > 0) opA.load(a.zpix + (long)lst[0] * NPAD, oa, ob);
 #pragma unroll 1
             for (int t = 0; t < trips; t += 2) {
-                opB.load(next_ptr(), oa, ob);
+                opB.load(a.zpix + (long)lst[t + 1] * NPAD, oa, ob);
                 accumulate<B>(acc, opA);
-                opA.load(next_ptr(), oa, ob);
+                opA.load(a.zpix + (long)lst[min(t + 2, trips - 1)] * NPAD, oa, ob);
                 accumulate<B>(acc, opB);
             }
         }
