@@ -66,6 +66,7 @@ def _load() -> C.CDLL:
     lib.fringe_evd_stats.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.fringe_last_kernel_ms.argtypes = [vp, i, C.POINTER(C.c_float)]
     lib.fringe_fp32_peak.argtypes = [vp, C.POINTER(d)]
+    lib.fringe_block_fma_rate.argtypes = [vp, C.POINTER(d)]
     for name in declared_symbols():
         getattr(lib, name)          # AttributeError here = header / library mismatch
     return lib

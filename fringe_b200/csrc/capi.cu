@@ -628,6 +628,13 @@ int fringe_fp32_peak(fringe_ctx* ctx, double* tflops) {
     return FRINGE_OK;
 }
 
+int fringe_block_fma_rate(fringe_ctx* ctx, double tflops[3]) {
+    if (!ctx || !tflops) return FRINGE_ERR_ARGUMENT;
+    CU(cudaSetDevice(ctx->device));
+    CU(fringe::measure_block_fma(ctx->stream, tflops));
+    return FRINGE_OK;
+}
+
 int fringe_evd_stats(fringe_ctx* ctx, int64_t stats[4]) {
     if (!ctx || !stats) return FRINGE_ERR_ARGUMENT;
     CU(cudaSetDevice(ctx->device));

@@ -75,5 +75,8 @@ cudaError_t launch_evd_fast(const EvdArgs& a, cudaStream_t st);
 
 // ---- microbench.cu --------------------------------------------------------------------
 cudaError_t measure_fp32_peak(cudaStream_t st, double* tflops);
+// register-resident 6x6 complex block update (144 FMAs per step, 3 CTAs/SM like the evd kernel):
+// tflops[0..2] = interleaved / de-interleaved scalar FFMA, packed f32x2
+cudaError_t measure_block_fma(cudaStream_t st, double* tflops);
 
 }  // namespace fringe

@@ -144,6 +144,9 @@ int fringe_last_kernel_ms(fringe_ctx* ctx, int kernel, float* ms);
 /* FP32 FMA throughput of the device measured with a register-resident FMA loop; the roofline
  * denominator for the covariance + eigen kernel (MEASURED_PEAKS.json carries no FP32 figure). */
 int fringe_fp32_peak(fringe_ctx* ctx, double* tflops);
+/* FP32 rate of a register-resident 6x6 complex block update (the covariance inner step with loads
+ * and address arithmetic removed): the practical ceiling of that loop, [0] interleaved and [1] de-interleaved scalar FFMA, [2] packed fma.rn.f32x2. */
+int fringe_block_fma_rate(fringe_ctx* ctx, double tflops[3]);
 
 /* Per-pixel solver statistics of the most recent evd call on this context (debug/bench):
  * stats[0] pixels solved, [1] total FP32 power iterations, [2] pixels that took the FP64
