@@ -612,6 +612,89 @@ int fringe_evd_block(fringe_ctx* ctx, const float* slc, const uint32_t* wts, int
     return FRINGE_OK;
 }
 
+// Fused host variant: one upload of the block feeds both stages.  Row chunks flow through
+// upload -> (amplitude sort, pair tests, count, re-layout, solve) -> download; the bit mask never
+// leaves the device between the stages (it is still copied out when `wts` is given).  Same results,
+// bit for bit, as fringe_nmap_block followed by fringe_evd_block on the same block.
+int fringe_nmap_evd_block(fringe_ctx* ctx, const float* slc, const uint8_t* mask, const double* alpha, int cols,
+                          int lines, int bands, int Nx, int Ny, int nmap_method, double pvalue, int first_line,
+                          int n_lines, int evd_method, int bandwidth, int mini_stack_count, int variant,
+                          int min_neighbors, int32_t* count, uint32_t* wts, float* out, float* tcorr,
+                          float* comp) {
+    if (!ctx) return FRINGE_ERR_ARGUMENT;
+    int rc = check_evd(ctx, cols, lines, bands, Nx, Ny, first_line, n_lines, evd_method, bandwidth, mini_stack_count, variant);
+    if (rc) return rc;
+    if (!slc || !out || !tcorr || !comp) return fail(ctx, FRINGE_ERR_ARGUMENT, "null pointer");
+    cudaStream_t st = ctx->stream;
+    NmapPlan nplan;
+    rc = nmap_prepare(ctx, cols, lines, bands, Nx, Ny, nmap_method, pvalue, st, &nplan);
+    if (rc) return rc;
+    EvdPlan eplan;
+    rc = evd_prepare(ctx, cols, lines, bands, evd_method, variant, st, &eplan);
+    if (rc) return rc;
+    const size_t npix = (size_t)cols * lines;
+    const int nu = fringe_nulong(Nx, Ny);
+    CU(ctx->in_slc.ensure(npix * bands * sizeof(float2)));
+    CU(ctx->o_count.ensure(npix * sizeof(int32_t)));
+    CU(ctx->o_wts.ensure(npix * nu * sizeof(uint32_t)));
+    CU(ctx->o_out.ensure(npix * bands * sizeof(float2)));
+    CU(ctx->o_tcorr.ensure(npix * sizeof(float)));
+    CU(ctx->o_comp.ensure(npix * sizeof(float2)));
+    const uint8_t* dmask = nullptr;
+    if (mask) { CU(ctx->in_mask.ensure(npix)); dmask = (const uint8_t*)ctx->in_mask.p; }
+    const double* dalpha = nullptr;
+    if (alpha) {
+        CU(ctx->alpha.ensure(bands * sizeof(double)));
+        CU(cudaMemcpyAsync(ctx->alpha.p, alpha, bands * sizeof(double), cudaMemcpyHostToDevice, st));
+        dalpha = (const double*)ctx->alpha.p;
+    }
+    CU(cudaMemsetAsync(ctx->o_wts.p, 0, npix * nu * sizeof(uint32_t), st));
+    const int step = chunk_rows(cols, bands, lines);
+    const int last = first_line + n_lines;
+    int uploaded = 0;
+    size_t ev = 0;
+    for (int r0 = 0; r0 < lines; r0 += step) {
+        const int r1 = std::min(lines, r0 + step);
+        const int need = std::min(lines, r1 + Ny);
+        const int s0 = uploaded, sn = need - uploaded;
+        if (sn > 0) {
+            const size_t off = (size_t)s0 * cols, cnt = (size_t)sn * cols;
+            CU(cudaMemcpy2DAsync((float2*)ctx->in_slc.p + off, npix * sizeof(float2), (const float2*)slc + off,
+                                 npix * sizeof(float2), cnt * sizeof(float2), bands, cudaMemcpyHostToDevice, ctx->s_in));
+            if (mask) CU(cudaMemcpyAsync((uint8_t*)ctx->in_mask.p + off, mask + off, cnt, cudaMemcpyHostToDevice, ctx->s_in));
+            uploaded = need;
+        }
+        cudaEvent_t e_in = ctx->pool_event(ev++), e_done = ctx->pool_event(ev++);
+        CU(cudaEventRecord(e_in, ctx->s_in));
+        CU(cudaStreamWaitEvent(st, e_in, 0));
+        rc = nmap_launch_rows(ctx, nplan, (const float*)ctx->in_slc.p, dmask, dalpha, cols, lines, bands, Nx, Ny,
+                              nmap_method, (int32_t*)ctx->o_count.p, (uint32_t*)ctx->o_wts.p, s0, sn, r0, r1 - r0, st);
+        if (rc) return rc;
+        // solve the part of this chunk that lies inside the requested lines; its mask rows are final
+        const int e0 = std::max(r0, first_line), e1 = std::min(r1, last);
+        rc = evd_launch_rows(ctx, eplan, (const float*)ctx->in_slc.p, (const uint32_t*)ctx->o_wts.p, cols, lines, bands,
+                             Nx, Ny, s0, sn, e0, std::max(0, e1 - e0), evd_method, bandwidth, mini_stack_count, variant,
+                             min_neighbors, (float*)ctx->o_out.p, (float*)ctx->o_tcorr.p, (float*)ctx->o_comp.p, st);
+        if (rc) return rc;
+        CU(cudaEventRecord(e_done, st));
+        CU(cudaStreamWaitEvent(ctx->s_out, e_done, 0));
+        const size_t off = (size_t)r0 * cols, cnt = (size_t)(r1 - r0) * cols;
+        if (count) CU(cudaMemcpyAsync(count + off, (int32_t*)ctx->o_count.p + off, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_out));
+        if (wts) CU(cudaMemcpyAsync(wts + off * nu, (uint32_t*)ctx->o_wts.p + off * nu, cnt * nu * sizeof(uint32_t),
+                                    cudaMemcpyDeviceToHost, ctx->s_out));
+        if (e1 > e0) {
+            const size_t eoff = (size_t)e0 * cols, ecnt = (size_t)(e1 - e0) * cols;
+            CU(cudaMemcpy2DAsync((float2*)out + eoff, npix * sizeof(float2), (float2*)ctx->o_out.p + eoff,
+                                 npix * sizeof(float2), ecnt * sizeof(float2), bands, cudaMemcpyDeviceToHost, ctx->s_out));
+            CU(cudaMemcpyAsync(tcorr + eoff, (float*)ctx->o_tcorr.p + eoff, ecnt * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_out));
+            CU(cudaMemcpyAsync((float2*)comp + eoff, (float2*)ctx->o_comp.p + eoff, ecnt * sizeof(float2), cudaMemcpyDeviceToHost, ctx->s_out));
+        }
+    }
+    CU(cudaStreamSynchronize(ctx->s_out));
+    CU(cudaStreamSynchronize(st));
+    return FRINGE_OK;
+}
+
 int fringe_last_kernel_ms(fringe_ctx* ctx, int kernel, float* ms) {
     if (!ctx || !ms || kernel < 0 || kernel >= FRINGE_KERNEL_COUNT) return FRINGE_ERR_ARGUMENT;
     if (!ctx->ev_valid[kernel]) return fail(ctx, FRINGE_ERR_ARGUMENT, "kernel has not been launched on this context");

@@ -151,6 +151,37 @@ class Context:
                                          out.ctypes.data, tcorr.ctypes.data, comp.ctypes.data))
         return out, tcorr, comp
 
+    def nmap_evd_block(self, slc, Nx, Ny, nmap_method="KS2", pvalue=0.05, mask=None, alpha=None,
+                       method="EVD", bandwidth=-1, mini_stack_count=1, variant=_lib.VARIANT_EVD,
+                       min_neighbors=2, first_line=0, n_lines=None, want_mask=True):
+        """Both stages on one upload (``fringe_nmap_evd_block``).
+        -> count, wts (None, None if not want_mask), out, tcorr, comp as nmap_block / evd_block."""
+        slc = np.ascontiguousarray(slc, np.complex64)
+        bands, lines, cols = slc.shape
+        if n_lines is None:
+            n_lines = lines - first_line
+        nu = nulong(Nx, Ny)
+        count = np.empty((lines, cols), np.int32) if want_mask else None
+        wts = np.empty((lines, cols, nu), np.uint32) if want_mask else None
+        mask_p = None
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, np.uint8)
+            mask_p = mask.ctypes.data
+        alpha_p = None
+        if alpha is not None:
+            alpha = np.ascontiguousarray(alpha, np.float64)
+            alpha_p = alpha.ctypes.data
+        out = np.zeros((bands, lines, cols), np.complex64)
+        tcorr = np.zeros((lines, cols), np.float32)
+        comp = np.zeros((lines, cols), np.complex64)
+        self._check(lib.fringe_nmap_evd_block(
+            self._h, slc.ctypes.data, mask_p, alpha_p, cols, lines, bands, Nx, Ny,
+            _method(METHODS_NMAP, nmap_method), float(pvalue), first_line, n_lines,
+            _method(METHODS_EVD, method), int(bandwidth), int(mini_stack_count), int(variant),
+            int(min_neighbors), count.ctypes.data if want_mask else None,
+            wts.ctypes.data if want_mask else None, out.ctypes.data, tcorr.ctypes.data, comp.ctypes.data))
+        return count, wts, out, tcorr, comp
+
     # ---- device tensors (torch) ------------------------------------------------------------
     @staticmethod
     def _stream():

@@ -127,6 +127,19 @@ int fringe_evd_block_device(fringe_ctx* ctx, const float* slc, const uint32_t* w
                             int min_neighbors, float* out, float* tcorr, float* comp,
                             void* stream);
 
+/* ---- both stages on one upload -----------------------------------------------------------
+ * fringe_nmap_block followed by fringe_evd_block on the same block, with the block uploaded once
+ * and the bit mask kept on the device between the stages: what nmap.py -> evd.py do through the
+ * weights file (src/nmap/nmap.cpp:487-559 writes it, src/evd/evd.cpp:470-480 reads it back).
+ * Results are bit-identical to the two separate calls.  `count` and `wts` cover all `lines` and
+ * may each be NULL when the caller does not want them copied back; out / tcorr / comp as in
+ * fringe_evd_block.  Host pointers (pinned preferred). */
+int fringe_nmap_evd_block(fringe_ctx* ctx, const float* slc, const uint8_t* mask, const double* alpha,
+                          int cols, int lines, int bands, int Nx, int Ny, int nmap_method,
+                          double pvalue, int first_line, int n_lines, int evd_method, int bandwidth,
+                          int mini_stack_count, int variant, int min_neighbors, int32_t* count,
+                          uint32_t* wts, float* out, float* tcorr, float* comp);
+
 /* Largest `bands` the evd kernels accept for the given method. */
 int fringe_evd_max_bands(int method, int variant);
 
