@@ -164,6 +164,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # keep stdout to the one JSON line: NCCL_DEBUG=VERSION prints a banner there
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     lines, cols = args.lines, args.cols
@@ -290,12 +293,32 @@ def main():
         d2h = npb * 4 + npb * nu * 4 + my_pixels * (BANDS * 8 + 4 + 8)
         t_fused = time_host(step_fused)
         t_two = time_host(step_two_calls)
+        # what the host link gives this rank while every rank is copying both ways at once
+        # (explains the gap between e2e and the device-resident value at N > 1)
+        nb = min(1 << 29, h_slc.numel() * 8)
+        src = h_slc.view(torch.uint8).reshape(-1)[:nb]
+        dst = h_out.view(torch.uint8).reshape(-1)[:nb]
+        d_a = torch.empty(nb, dtype=torch.uint8, device=dev)
+        d_b = torch.empty(nb, dtype=torch.uint8, device=dev)
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def step_link():
+            with torch.cuda.stream(s_up):
+                d_a.copy_(src, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                dst.copy_(d_b, non_blocking=True)
+        t_link = time_host(step_link)
+        link_gbs = nb * args.steps / t_link * 1e-9
+        del d_a, d_b
         # headline: both stages on one upload; the mask and count still come back to the host
         e2e = {"value": total_pixels * args.steps / t_fused, "unit": "pixels/s",
                "h2d_bytes_per_step": npb * BANDS * 8, "d2h_bytes_per_step": d2h,
                "ms_per_step": t_fused * 1e3 / args.steps,
                "api": "fringe_nmap_evd_block (host pointers, pinned; count, mask, phase, tcorr, "
                       "compressed SLC all copied back), per rank",
+               "host_link": {"gbs_each_way": link_gbs, "note": "pinned copies of %d MB up and down at the same "
+                             "time on every rank, max over ranks" % (nb >> 20),
+                             "floor_ms_per_step": max(npb * BANDS * 8, d2h) / (link_gbs * 1e9) * 1e3},
                "two_calls": {"value": total_pixels * args.steps / t_two, "unit": "pixels/s",
                              "h2d_bytes_per_step": 2 * npb * BANDS * 8 + npb * nu * 4,
                              "d2h_bytes_per_step": d2h, "ms_per_step": t_two * 1e3 / args.steps,

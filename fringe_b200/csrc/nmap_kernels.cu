@@ -10,12 +10,12 @@
 //                column (bank = thread), are insertion-sorted there and written rank-major
 //                ([rank][pixel]) so later tile loads are contiguous row segments.
 //   k_nmap<M>    one CTA per tile of pixels; the sorted vectors of tile + forward halo are
-//                staged in shared memory once as integer keys ([rank][region pixel], + one
-//                all-ones sentinel rank); one thread per pixel walks the forward half of its
-//                window and runs a branch-free merge per neighbour.
-//                KS2: the p-value threshold is turned into an integer bound on
-//                     max_v |#{a<=v} - #{b<=v}| on the host (fringe_ks2_critical_count), so
-//                     the device test is exact integer arithmetic.
+//                staged in shared memory once as integer keys; one thread per pixel walks the
+//                forward half of its window.
+//                KS2: the p-value threshold is turned into an integer bound k on
+//                     max_v |#{a<=v} - #{b<=v}| on the host (fringe_ks2_critical_count); that
+//                     bound holds iff b[i-k] <= a[i] and a[i-k] <= b[i] for all i >= k, so the
+//                     device test is 2(N-k) exact integer compares, no merge (ks_within).
 //                AD2: the inner sum of AD2unique.hpp:287-303 only takes values from a
 //                     (2N-1)x(N+1) table of doubles T[j][|2m-(j+1)|]; the table is built on
 //                     the host with the reference's expression and the device adds the same
@@ -109,33 +109,38 @@ struct NmapKernelArgs {
 };
 
 // The sorted amplitudes are non-negative, NaN-free floats, so their bit patterns order like
-// unsigned integers.  The walks below therefore run on uint32 keys: comparisons are integer
-// compares, ties are equal bit patterns, and the sentinel rank is 0xFFFFFFFF -- strictly above
-// every real key including +inf -- so no index guards are needed and the loop body is a single
-// shared-memory load from a selected address (no divergent branches).
+// unsigned integers.  The tests below therefore run on uint32 keys: comparisons are integer
+// compares and ties are equal bit patterns.  The AD2 merge also keeps a sentinel rank 0xFFFFFFFF
+// -- strictly above every real key including +inf -- so it needs no index guards and its loop
+// body is a single shared-memory load from a selected address (no divergent branches).
 //
-// KS2sample.hpp:91-144 as an integer walk.  ia / ib index rank 0 of the two pixels inside
-// s_key, consecutive ranks are `stride` keys apart.  Returns max |#b - #a| sampled only where
-// every element equal to the last consumed value has been consumed on both sides (the
-// reference's tie rule).
-__device__ __forceinline__ int ks_max_count_diff(const uint32_t* __restrict__ s_key, uint32_t ia,
-                                                 uint32_t ib, int n, uint32_t stride) {
-    uint32_t va = s_key[ia], vb = s_key[ib];
-    int d = 0, kmax = 0;
-#pragma unroll 4
-    for (int s = 0; s < 2 * n; ++s) {
-        const bool ta = va <= vb;
-        const uint32_t x = min(va, vb);
-        ia += ta ? stride : 0u;
-        ib += ta ? 0u : stride;
-        d += ta ? -1 : 1;
-        const uint32_t nxt = s_key[ta ? ia : ib];
-        va = ta ? nxt : va;
-        vb = ta ? vb : nxt;
-        const bool ev = (va > x) & (vb > x);
-        kmax = ev ? max(kmax, abs(d)) : kmax;
+// KS2sample.hpp:91-144 without the merge walk.  The reference's statistic is
+//   D * n = max_v |#{a <= v} - #{b <= v}|   (v over the pooled values; ties consumed on both sides)
+// and the host has already turned the p-value threshold into "D * n <= k".  For ascending a, b:
+//   #{a <= v} - #{b <= v} <= k for all v  <=>  (i + 1) - #{b <= a[i]} <= k for all i
+//                                         <=>  b[i - k] <= a[i]          for all i >= k
+// (the binding v is a[i] itself; for tied a's the last of them is the binding index and the
+// earlier ones are weaker), and the mirrored inequality gives a[i - k] <= b[i].  So the pair is
+// accepted iff  b[i-k] <= a[i] and a[i-k] <= b[i]  for every i in [k, n): 2 (n - k) integer
+// compares on keys each pixel keeps contiguously ([pixel][rank], odd stride), instead of a 2n-step
+// merge.  pa / pb point at rank 0 of the two pixels.
+__device__ __forceinline__ bool ks_within(const uint32_t* __restrict__ pa, const uint32_t* __restrict__ pb,
+                                          int n, int k) {
+    const uint32_t* __restrict__ ah = pa + k;
+    const uint32_t* __restrict__ bh = pb + k;
+    const int m = n - k;
+    bool bad = false;                     // no short circuit: all loads of a step issue together
+    int i = 0;
+#pragma unroll 1
+    for (; i + 4 <= m; i += 4) {
+        uint32_t a_hi[4], a_lo[4], b_hi[4], b_lo[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { a_hi[u] = ah[i + u]; a_lo[u] = pa[i + u]; b_hi[u] = bh[i + u]; b_lo[u] = pb[i + u]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) bad |= (b_lo[u] > a_hi[u]) | (a_lo[u] > b_hi[u]);
     }
-    return kmax;
+    for (; i < m; ++i) bad |= (pb[i] > ah[i]) | (pa[i] > bh[i]);
+    return !bad;
 }
 
 // AD2unique.hpp:211-303: merge (on equality the element of B goes first) and table sum.
@@ -177,23 +182,27 @@ __global__ void k_nmap(const NmapKernelArgs a) {
     const long npix = (long)a.cols * a.lines;
 
     // carve: [double table (optional)] [uint32 keys (N+1)*RP] [uint8 valid RP]
+    // key layout: AD2 [rank][region pixel] + sentinel rank; KS2 [region pixel][rank], odd stride KS
     double* s_tab = reinterpret_cast<double*>(s_raw);
     const int tab_elems = (METHOD == 1 && a.table_in_smem) ? (2 * N - 1) * (N + 1) : 0;
     uint32_t* s_key = reinterpret_cast<uint32_t*>(s_tab + tab_elems);
     uint8_t* s_valid = reinterpret_cast<uint8_t*>(s_key + (size_t)(N + 1) * RP);
+    const int KS = N | 1;
 
     const int x0 = blockIdx.x * TW - Nx, y0 = a.row0 + blockIdx.y * TH;
     for (int rp = tid; rp < RP; rp += nthr) {
         const int gy = y0 + rp / RW, gx = x0 + rp % RW;
         const bool inb = (gy < a.lines) && (gx >= 0) && (gx < a.cols);
         s_valid[rp] = inb ? a.valid[(long)gy * a.cols + gx] : 0;
-        s_key[(size_t)N * RP + rp] = 0xFFFFFFFFu;
+        if (METHOD == 1) s_key[(size_t)N * RP + rp] = 0xFFFFFFFFu;
     }
     for (int idx = tid; idx < N * RP; idx += nthr) {
         const int k = idx / RP, rp = idx - k * RP;
         const int gy = y0 + rp / RW, gx = x0 + rp % RW;
         const bool inb = (gy < a.lines) && (gx >= 0) && (gx < a.cols);
-        s_key[idx] = inb ? __float_as_uint(__ldg(&a.amp[(long)k * npix + (long)gy * a.cols + gx])) : 0u;
+        const uint32_t key = inb ? __float_as_uint(__ldg(&a.amp[(long)k * npix + (long)gy * a.cols + gx])) : 0u;
+        if (METHOD == 1) s_key[idx] = key;
+        else s_key[rp * KS + k] = key;
     }
     for (int i = tid; i < tab_elems; i += nthr) s_tab[i] = a.ad_table[i];
     __syncthreads();
@@ -207,6 +216,7 @@ __global__ void k_nmap(const NmapKernelArgs a) {
     const double* T = (METHOD == 1) ? (a.table_in_smem ? s_tab : a.ad_table) : nullptr;
     const int WX = 2 * Nx + 1, W = WX * (2 * Ny + 1), center = Ny * WX + Nx;
     uint32_t word = 1u << (center & 31);            // a valid pixel is always its own neighbour
+    const int kc = min(max(a.kcrit, 0), N);         // k >= N accepts every pair, k < 0 none
     int dy = 0, dx = 1;
     for (int f = center + 1; f < W; ++f) {
         if (dx > Nx) { dx = -Nx; ++dy; }
@@ -214,7 +224,7 @@ __global__ void k_nmap(const NmapKernelArgs a) {
         const int rq = rp + dy * RW + dx;
         if (s_valid[rq]) {
             bool similar;
-            if (METHOD == 0) similar = ks_max_count_diff(s_key, rp, rq, N, RP) <= a.kcrit;
+            if (METHOD == 0) similar = (a.kcrit >= 0) && ks_within(s_key + rp * KS, s_key + rq * KS, N, kc);
             else similar = ad_inner_sum(s_key, rp, rq, N, RP, T) <= a.scrit;
             if (similar) {
                 word |= (1u << (f & 31));
