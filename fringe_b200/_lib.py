@@ -65,6 +65,7 @@ def _load() -> C.CDLL:
     lib.fringe_evd_block_device.argtypes = evd_args + [vp]
     lib.fringe_nmap_evd_block.argtypes = [vp, vp, vp, vp] + [i] * 6 + [d] + [i] * 7 + [vp] * 5
     lib.fringe_evd_stats.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.fringe_evd_phase_cycles.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.fringe_last_kernel_ms.argtypes = [vp, i, C.POINTER(C.c_float)]
     lib.fringe_fp32_peak.argtypes = [vp, C.POINTER(d)]
     lib.fringe_block_fma_rate.argtypes = [vp, C.POINTER(d)]

@@ -39,7 +39,7 @@ def _run(cmd: list[str]) -> None:
     subprocess.check_call(cmd)
 
 
-def build_cuda(force: bool = False, verbose_ptxas: bool = False) -> str:
+def build_cuda(force: bool = False, verbose_ptxas: bool = False, phase_clocks: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     srcs = [os.path.join(CSRC, s) for s in CUDA_SOURCES]
     deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "fringe_b200.h"),
@@ -49,6 +49,8 @@ def build_cuda(force: bool = False, verbose_ptxas: bool = False) -> str:
         flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
         if verbose_ptxas:
             flags += ["-Xptxas", "-v"]
+        if phase_clocks:                     # profiling build: fringe_evd_phase_cycles
+            flags += ["-DFRINGE_PHASE_CLOCKS"]
         objdir = os.path.join(LIBDIR, "obj")
         os.makedirs(objdir, exist_ok=True)
         procs = []
@@ -66,8 +68,8 @@ def build_cuda(force: bool = False, verbose_ptxas: bool = False) -> str:
     return CUDA_LIB
 
 
-def build_all(force: bool = False) -> None:
-    build_cuda(force)
+def build_all(force: bool = False, phase_clocks: bool = False) -> None:
+    build_cuda(force or phase_clocks, phase_clocks=phase_clocks)
     try:
         from . import build_host
     except ImportError:
@@ -76,4 +78,4 @@ def build_all(force: bool = False) -> None:
 
 
 if __name__ == "__main__":
-    build_all(force="--force" in sys.argv)
+    build_all(force="--force" in sys.argv, phase_clocks="--phase-clocks" in sys.argv)

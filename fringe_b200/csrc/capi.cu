@@ -489,8 +489,8 @@ int evd_prepare(fringe_ctx* ctx, int cols, int lines, int bands, int method, int
     // exhausted / out-of-block SHP slots at it instead of branching
     CU(ctx->zpix.ensure((npix + 1) * plan->NP * sizeof(float2)));
     CU(cudaMemsetAsync((float2*)ctx->zpix.p + npix * plan->NP, 0, plan->NP * sizeof(float2), st));
-    CU(ctx->stats.ensure(4 * sizeof(unsigned long long)));
-    CU(cudaMemsetAsync(ctx->stats.p, 0, 4 * sizeof(unsigned long long), st));
+    CU(ctx->stats.ensure(12 * sizeof(unsigned long long)));      // 4 counters + 8 phase clocks
+    CU(cudaMemsetAsync(ctx->stats.p, 0, 12 * sizeof(unsigned long long), st));
     return FRINGE_OK;
 }
 
@@ -715,6 +715,16 @@ int fringe_block_fma_rate(fringe_ctx* ctx, double tflops[3]) {
     if (!ctx || !tflops) return FRINGE_ERR_ARGUMENT;
     CU(cudaSetDevice(ctx->device));
     CU(fringe::measure_block_fma(ctx->stream, tflops));
+    return FRINGE_OK;
+}
+
+int fringe_evd_phase_cycles(fringe_ctx* ctx, int64_t cycles[8]) {
+    if (!ctx || !cycles) return FRINGE_ERR_ARGUMENT;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    unsigned long long h[12] = {0};
+    if (ctx->stats.p) CU(cudaMemcpy(h, ctx->stats.p, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 8; ++i) cycles[i] = (int64_t)h[4 + i];
     return FRINGE_OK;
 }
 

@@ -64,9 +64,9 @@ struct FastCfg {
     static constexpr int WARPS = 4;
     // per warp: two full matrices, two broadcast vectors (double buffered), powers
     static constexpr int MAT = NPAD * NPAD;             // float2 elements per matrix
-    // ... and the SHP index lists of the two pixels (2 x 64 ints)
+    // ... and the SHP index lists (shared halves 2 x 32, exclusive 2 x 64 ints)
     static constexpr int SMEM_PER_WARP =
-        (((2 * MAT + 2 * 32) * (int)sizeof(float2) + 2 * NPAD * (int)sizeof(float) + 128 * (int)sizeof(int)) + 15) & ~15;
+        (((2 * MAT + 2 * 32) * (int)sizeof(float2) + 2 * NPAD * (int)sizeof(float) + 192 * (int)sizeof(int)) + 15) & ~15;
 };
 
 // One SHP's operands for a lane's block: rows B*bi.. and columns B*bj.. of the sample vector.
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
     float2* s_mat = reinterpret_cast<float2*>(base);                       // [2][NPAD][NPAD]
     float2* s_vec = s_mat + 2 * Cfg::MAT;                                  // [2][32]
     float* s_pw = reinterpret_cast<float*>(s_vec + 64);                    // [2][NPAD]
-    int* s_list = reinterpret_cast<int*>(s_pw + 2 * NPAD);                 // [2][64]
+    int* s_list = reinterpret_cast<int*>(s_pw + 2 * NPAD);                 // shared [2][32], exclusive [2][64]
 
     // block coordinates of this lane inside its pixel group
     int bi = 0, bj = 0;
@@ -167,6 +167,14 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
     bool have_warm = false;
     PHASE_DECL
 
+    auto load_mask_words = [&](long pr2) -> uint32_t {
+        const int w = lane & 15;
+        if (pr2 >= end || w >= a.nulong) return 0u;
+        const int row2 = a.first_line + (int)(pr2 / pairs_per_row);
+        const int col2 = 2 * (int)(pr2 % pairs_per_row) + (lane >> 4);
+        return (col2 < a.cols) ? __ldg(&a.wts[((long)row2 * a.cols + col2) * a.nulong + w]) : 0u;
+    };
+    uint32_t mw_next = load_mask_words(beg + warp);
 #pragma unroll 1
     for (long pr = beg + warp; pr < end; pr += Cfg::WARPS) {
         const int row = a.first_line + (int)(pr / pairs_per_row);
@@ -180,59 +188,109 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
         for (int i = 0; i < B; ++i)
 #pragma unroll
             for (int j = 0; j < B; ++j) acc[i][j] = make_float2(0.f, 0.f);
-        // SHP address lists.  All 32 lanes turn one 32-bit mask word of one pixel into sample-vector
-        // indices at once (bit -> window offset -> bounds check, ballot + popcount for the
-        // compacted slot) and park them in shared memory; the accumulation loop below then costs
-        // one shared-memory read and one multiply per SHP instead of ~30 integer instructions
-        // (ncu: the dispatch stalls of this phase sat on exactly those instructions).  Lists are
-        // built for two mask words (64 window positions) at a time.
+        // SHP address lists.  All 32 lanes turn one 32-bit mask word of both pixels into
+        // sample-vector indices at once (bit -> window offset -> bounds check, ballot + popcount
+        // for the compacted slot) and park them in shared memory; the accumulation loop below then
+        // costs one shared-memory read and one multiply per SHP.  Lists are built for two mask
+        // words (64 window positions) at a time.
+        //
+        // The two pixels of a warp are neighbours, so most of their SHPs are the same samples
+        // (window position f of pixel 0 is position f-1 of pixel 1).  Pass 0 accumulates those
+        // shared samples once, half of them in each 16-lane group, and the groups then add each
+        // other's partial sums; pass 1 adds each pixel's exclusive samples.  Every outer product
+        // in the intersection is thus computed once instead of twice.
         int npix = 0;                                 // group-uniform count of usable SHPs
         const long p0 = (long)row * a.cols + col0;
-        const bool ex1 = (col0 + 1) < a.cols;
-        const bool con0 = (__ldg(&a.wts[p0 * a.nulong + (center >> 5)]) >> (center & 31)) & 1u;
-        const bool con1 = ex1 && ((__ldg(&a.wts[(p0 + 1) * a.nulong + (center >> 5)]) >> (center & 31)) & 1u);
+        // mask words of this pair were fetched one pair ahead (lane 16 g + w holds word w of
+        // pixel g); fetch the next pair's now so that their latency hides behind this pair's work
+        const uint32_t mw = mw_next;
+        mw_next = load_mask_words(pr + Cfg::WARPS);
+        const bool in_regs = a.nulong <= 16;
+        auto mask_word = [&](int g, int w) -> uint32_t {          // g, w warp-uniform
+            if (w < 0 || w >= a.nulong || col0 + g >= a.cols) return 0u;
+            return in_regs ? __shfl_sync(FULLMASK, mw, g * 16 + w) : __ldg(&a.wts[(p0 + g) * a.nulong + w]);
+        };
+        const bool con0 = (mask_word(0, center >> 5) >> (center & 31)) & 1u;
+        const bool con1 = (mask_word(1, center >> 5) >> (center & 31)) & 1u;
         const bool center_on = grp ? con1 : con0;
         const int zero_idx = (int)npix_block;         // index of the all-zero sample vector
+        const uint32_t lt_mask = (1u << lane) - 1u;
+        int* l_sh = s_list;                           // [2][32] shared SHPs, alternating between the groups
+        int* l_ex = s_list + 64;                      // [2][64] exclusive SHPs of pixel 0 / pixel 1
+        const bool one_round = a.nulong <= 2;
+        int nshared = 0, ns = 0, n0 = 0, n1 = 0;
 #pragma unroll 1
-        for (int w0 = 0; w0 < a.nulong; w0 += 2) {
-            int n0 = 0, n1 = 0;                       // list lengths of the two pixels (warp-uniform)
-            __syncwarp();
+        for (int pass = (con0 && con1) ? 0 : 1; pass < 2; ++pass) {
+#pragma unroll 1
+            for (int w0 = 0; w0 < a.nulong; w0 += 2) {
+                __syncwarp();
+                if (!(one_round && pass == 1 && con0 && con1)) {      // a single round's lists survive pass 0
+                    ns = 0; n0 = 0; n1 = 0;
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const int w = w0 + c;
-                    const bool live = (w < a.nulong) && (g ? con1 : con0);
-                    const uint32_t word = live ? __ldg(&a.wts[(p0 + g) * a.nulong + w]) : 0u;
-                    const short2 d = s_off[min(w, a.nulong - 1) * 32 + lane];
-                    const int yy = row + d.x, xx = col0 + g + d.y;
-                    const bool ok = ((word >> lane) & 1u) && yy >= 0 && yy < a.lines && xx >= 0 && xx < a.cols;
-                    const uint32_t V = __ballot_sync(FULLMASK, ok);
-                    int& n = g ? n1 : n0;
-                    if (ok) s_list[g * 64 + n + __popc(V & ((1u << lane) - 1u))] = yy * a.cols + xx;
-                    n += __popc(V);
+                    for (int c = 0; c < 2; ++c) {
+                        const int w = w0 + c;
+                        const uint32_t m0 = con0 ? mask_word(0, w) : 0u;
+                        const uint32_t m1 = con1 ? mask_word(1, w) : 0u;
+                        const uint32_t m0n = con0 ? mask_word(0, w + 1) : 0u;
+                        const uint32_t m1p = con1 ? mask_word(1, w - 1) : 0u;
+                        const uint32_t m1_prev = __funnelshift_l(m1p, m1, 1);   // bit i: pixel 1, position 32w+i-1
+                        const uint32_t m0_next = __funnelshift_r(m0, m0n, 1);   // bit i: pixel 0, position 32w+i+1
+                        const short2 d = s_off[min(w, a.nulong - 1) * 32 + lane];
+                        const int yy = row + d.x, xx = col0 + d.y;
+                        const bool rowok = yy >= 0 && yy < a.lines;
+                        const bool ok0 = ((m0 >> lane) & 1u) && rowok && xx >= 0 && xx < a.cols;
+                        const bool ok1 = ((m1 >> lane) & 1u) && rowok && xx + 1 >= 0 && xx + 1 < a.cols;
+                        const bool sh0 = ok0 && (d.y > -a.Nx) && ((m1_prev >> lane) & 1u);
+                        const bool sh1 = ok1 && (d.y < a.Nx) && ((m0_next >> lane) & 1u);
+                        const int idx0 = yy * a.cols + xx;
+                        const uint32_t VS = __ballot_sync(FULLMASK, sh0);
+                        const uint32_t V0 = __ballot_sync(FULLMASK, ok0 && !sh0);
+                        const uint32_t V1 = __ballot_sync(FULLMASK, ok1 && !sh1);
+                        const int sl = ns + __popc(VS & lt_mask);
+                        if (sh0) l_sh[(sl & 1) * 32 + (sl >> 1)] = idx0;
+                        if (ok0 && !sh0) l_ex[n0 + __popc(V0 & lt_mask)] = idx0;
+                        if (ok1 && !sh1) l_ex[64 + n1 + __popc(V1 & lt_mask)] = idx0 + 1;
+                        ns += __popc(VS);
+                        n0 += __popc(V0);
+                        n1 += __popc(V1);
+                    }
+                    if (pass == 1 || one_round) npix += ns + (grp ? n1 : n0);      // each round counted once
+                    // pad every list to an even length with the zero vector (SHPs are consumed two at a time)
+                    const int hs = (ns + 1) >> 1, ts = (hs + 1) & ~1, te = (max(n0, n1) + 1) & ~1;
+                    if (lane < 4) {                              // the last two slots of each group's half
+                        const int g = lane & 1, k = ts - 1 - (lane >> 1);
+                        if (k >= (g ? (ns >> 1) : hs)) l_sh[g * 32 + k] = zero_idx;
+                    }
+                    for (int k = n0 + lane; k < te; k += 32) l_ex[k] = zero_idx;
+                    for (int k = n1 + lane; k < te; k += 32) l_ex[64 + k] = zero_idx;
+                    __syncwarp();
                 }
-            }
-            const int trips = (max(n0, n1) + 1) & ~1;   // SHPs are consumed two at a time
-            // pad the shorter list(s) with the zero vector
-            for (int k = n0 + lane; k < trips; k += 32) s_list[k] = zero_idx;
-            for (int k = n1 + lane; k < trips; k += 32) s_list[64 + k] = zero_idx;
-            __syncwarp();
-            PHASE_MARK(0)
-            npix += grp ? n1 : n0;
-            const int* lst = s_list + grp * 64;
-            // two-stage software pipeline: while one SHP is accumulated the next one's samples
-            // are already in flight
-            Operands<B> opA, opB;
-            if (trips > 0) opA.load(a.zpix + (long)lst[0] * NPAD, oa, ob);
+                PHASE_MARK(0)
+                const int* lst = (pass == 0) ? (l_sh + grp * 32) : (l_ex + grp * 64);
+                const int trips = (pass == 0) ? ((((ns + 1) >> 1) + 1) & ~1) : ((max(n0, n1) + 1) & ~1);
+                if (pass == 0) nshared += ns;
+                // two-stage software pipeline: while one SHP is accumulated the next one's samples
+                // are already in flight
+                Operands<B> opA, opB;
+                if (trips > 0) opA.load(a.zpix + (long)lst[0] * NPAD, oa, ob);
 #pragma unroll 1
-            for (int t = 0; t < trips; t += 2) {
-                opB.load(a.zpix + (long)lst[t + 1] * NPAD, oa, ob);
-                accumulate<B>(acc, opA);
-                opA.load(a.zpix + (long)lst[min(t + 2, trips - 1)] * NPAD, oa, ob);
-                accumulate<B>(acc, opB);
+                for (int t = 0; t < trips; t += 2) {
+                    opB.load(a.zpix + (long)lst[t + 1] * NPAD, oa, ob);
+                    accumulate<B>(acc, opA);
+                    opA.load(a.zpix + (long)lst[min(t + 2, trips - 1)] * NPAD, oa, ob);
+                    accumulate<B>(acc, opB);
+                }
+                PHASE_MARK(1)
             }
-            PHASE_MARK(1)
+            if (pass == 0 && nshared > 0) {           // both groups now hold the full shared sum
+#pragma unroll
+                for (int i = 0; i < B; ++i)
+#pragma unroll
+                    for (int j = 0; j < B; ++j) {
+                        acc[i][j].x += __shfl_xor_sync(FULLMASK, acc[i][j].x, 16);
+                        acc[i][j].y += __shfl_xor_sync(FULLMASK, acc[i][j].y, 16);
+                    }
+            }
         }
         // group-uniform: enough SHPs?  (evd.cpp:566 hard-codes 2).  Collective first: no
         // short-circuit evaluation around a warp shuffle.
@@ -315,11 +373,6 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
                     const float2 v = s_mat[g * Cfg::MAT + k0 * NPAD + r];
                     const float keep = (isstbas && abs(k0 - lane) > BW) ? 0.f : live;
                     x = have_warm ? xwarm : make_float2(v.x * keep, -v.y * keep);
-                    {   // unit-modulus start: the dominant eigenvector of a coherence matrix has nearly uniform magnitudes
-                        const float m2 = x.x * x.x + x.y * x.y;
-                        const float rs = (m2 > 0.f) ? fast_rsqrt(m2) : 0.f;
-                        x.x *= rs; x.y *= rs;
-                    }
                     float n2 = x.x * x.x + x.y * x.y;
 #pragma unroll
                     for (int s = 16; s > 0; s >>= 1) n2 += __shfl_xor_sync(FULLMASK, n2, s);

@@ -165,6 +165,12 @@ int fringe_block_fma_rate(fringe_ctx* ctx, double tflops[3]);
  * stats[0] pixels solved, [1] total FP32 power iterations, [2] pixels that took the FP64
  * certified path, [3] pixels that hit an iteration cap.  Synchronises the context. */
 int fringe_evd_stats(fringe_ctx* ctx, int64_t stats[4]);
+/* Per-phase warp cycles of the most recent register-blocked evd launch (summed over warps):
+ * [0] SHP lists, [1] covariance accumulation, [2] normalisation + hand-off to shared memory,
+ * [3] row load + start vector, [4] power iteration, [5] epilogue, [6..7] spare.  All zero unless
+ * the library was built with -DFRINGE_PHASE_CLOCKS (python -m fringe_b200.build --phase-clocks);
+ * a profiling build, not for timing. */
+int fringe_evd_phase_cycles(fringe_ctx* ctx, int64_t cycles[8]);
 
 #ifdef __cplusplus
 }
