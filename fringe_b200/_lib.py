@@ -69,6 +69,7 @@ def _load() -> C.CDLL:
     lib.fringe_last_kernel_ms.argtypes = [vp, i, C.POINTER(C.c_float)]
     lib.fringe_fp32_peak.argtypes = [vp, C.POINTER(d)]
     lib.fringe_block_fma_rate.argtypes = [vp, C.POINTER(d)]
+    lib.fringe_mma_tf32_rate.argtypes = [vp, C.POINTER(d)]
     for name in declared_symbols():
         getattr(lib, name)          # AttributeError here = header / library mismatch
     return lib

@@ -485,6 +485,12 @@ int evd_prepare(fringe_ctx* ctx, int cols, int lines, int bands, int method, int
         plan->NP = fringe::evd_fast_padded_bands(bands);
         plan->zblock = fringe::evd_fast_block(bands);
     }
+    if (!plan->generic && variant == FRINGE_VARIANT_EVD && method != FRINGE_EVD_MLE &&
+        fringe::evd_mma_order(bands) > 0 && getenv("FRINGE_EVD_FP32") == nullptr)   // debug switch: FP32-FMA covariance kernel
+    {
+        plan->NP = 64;                        // 128 floats per pixel: TF32 hi and lo parts of 32 bands
+        plan->zblock = -1;
+    }
     // one extra, all-zero sample vector behind the image: the register-blocked kernel points
     // exhausted / out-of-block SHP slots at it instead of branching
     CU(ctx->zpix.ensure((npix + 1) * plan->NP * sizeof(float2)));
@@ -501,8 +507,12 @@ int evd_launch_rows(fringe_ctx* ctx, const EvdPlan& plan, const float* slc, cons
                     float* out, float* tcorr, float* comp, cudaStream_t st) {
     const size_t npix = (size_t)cols * lines;
     CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_TRANSPOSE][0], st));
-    CU(fringe::launch_transpose((const float2*)slc, (long)npix, (long)t0 * cols, (long)tn * cols, bands, plan.NP,
-                                plan.zblock, (float2*)ctx->zpix.p, st));
+    if (plan.zblock < 0)
+        CU(fringe::launch_transpose_mma((const float2*)slc, (long)npix, (long)t0 * cols, (long)tn * cols, bands,
+                                        (float2*)ctx->zpix.p, st));
+    else
+        CU(fringe::launch_transpose((const float2*)slc, (long)npix, (long)t0 * cols, (long)tn * cols, bands, plan.NP,
+                                    plan.zblock, (float2*)ctx->zpix.p, st));
     CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_TRANSPOSE][1], st));
     fringe::EvdArgs a;
     a.zpix = (const float2*)ctx->zpix.p; a.slc = (const float2*)slc; a.wts = wts;
@@ -715,6 +725,13 @@ int fringe_block_fma_rate(fringe_ctx* ctx, double tflops[3]) {
     if (!ctx || !tflops) return FRINGE_ERR_ARGUMENT;
     CU(cudaSetDevice(ctx->device));
     CU(fringe::measure_block_fma(ctx->stream, tflops));
+    return FRINGE_OK;
+}
+
+int fringe_mma_tf32_rate(fringe_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) return FRINGE_ERR_ARGUMENT;
+    CU(cudaSetDevice(ctx->device));
+    CU(fringe::measure_mma_tf32(ctx->stream, tflops));
     return FRINGE_OK;
 }
 

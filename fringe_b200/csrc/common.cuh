@@ -72,11 +72,19 @@ int evd_fast_padded_bands(int bands);
 int evd_fast_block(int bands);
 bool evd_fast_supported(const EvdArgs& a);
 cudaError_t launch_evd_fast(const EvdArgs& a, cudaStream_t st);
+// tensor-pipe variant (evd_mma.cu): its own pixel-major layout (zblock = -1, NP = 64: 128 floats per
+// pixel, TF32 hi and lo parts) and eigen order evd_mma_order(bands) (0 = not eligible, bands <= 32)
+int evd_mma_order(int bands);
+cudaError_t launch_transpose_mma(const float2* slc, long npix, long first, long count, int bands, float2* zpix,
+                                 cudaStream_t st);
+cudaError_t launch_evd_mma(const EvdArgs& a, cudaStream_t st);
 
 // ---- microbench.cu --------------------------------------------------------------------
 cudaError_t measure_fp32_peak(cudaStream_t st, double* tflops);
 // register-resident 6x6 complex block update (144 FMAs per step, 3 CTAs/SM like the evd kernel):
 // tflops[0..2] = interleaved / de-interleaved scalar FFMA, packed f32x2
 cudaError_t measure_block_fma(cudaStream_t st, double* tflops);
+// dense TFLOP/s of mma.sync.m16n8k8 TF32 (legacy warp-level tensor path), 12 accumulator tiles per warp
+cudaError_t measure_mma_tf32(cudaStream_t st, double* tflops);
 
 }  // namespace fringe

@@ -514,11 +514,14 @@ int evd_fast_padded_bands(int bands) {
 int evd_fast_block(int) { return 0; }      // this kernel reads the interleaved complex pixel-major layout
 
 bool evd_fast_supported(const EvdArgs& a) {
+    if (a.zblock < 0)                           // tensor-pipe layout (evd_mma.cu)
+        return a.variant == 0 && (a.method == 0 || a.method == 2) && a.NP == 64 && evd_mma_order(a.bands) > 0;
     return a.variant == 0 && (a.method == 0 || a.method == 2) && evd_fast_padded_bands(a.bands) > 0 &&
            a.NP == evd_fast_padded_bands(a.bands);
 }
 
 cudaError_t launch_evd_fast(const EvdArgs& a, cudaStream_t st) {
+    if (a.zblock < 0) return launch_evd_mma(a, st);
     switch (a.NP / 5) {
         case 2: return launch_fast_t<2>(a, st);
         case 3: return launch_fast_t<3>(a, st);

@@ -1,0 +1,540 @@
+// Tensor-pipe covariance (3xTF32 mma.sync) + in-register power iteration (sm_100a), bands <= 32.
+//
+// Same arithmetic contract and the same eigen solve / epilogue as evd_fast.cu (EVD / STBAS,
+// evd.cpp control flow); only the masked Gram product C = sum_k z_k z_k^H moves from FP32 FMAs
+// to the warp-level tensor path:
+//
+//   layout      k_transpose_mma splits every sample into a TF32 "hi" part and a TF32 "lo"
+//               remainder (x = hi + lo to ~2^-22) and stores a pixel's 32 (zero padded) bands as
+//               128 floats: hi[g][q][re,im] for g = 0..7, q = 0..3 (band = g + 8 q), then lo in
+//               the same order.  Lane (g, t) of a warp therefore fetches everything it needs of
+//               one SHP with four 16-byte loads, and the eight lanes that share t read the SHP's
+//               512 bytes contiguously.
+//   covariance  One warp per pixel.  Four SHPs form one k-chunk of m16n8k8: k = 0..3 are the real
+//               parts of the four samples, k = 4..7 their imaginary parts, so
+//                   Re C = [Zr|Zi] [Zr|Zi]^T          Im C = [Zr|Zi] [-Zi|Zr]^T
+//               and the B fragments of the second product are the first one's with the two
+//               registers swapped and one sign flipped.  Only the 6 of 8 16x8 tiles that touch the
+//               upper triangle are computed: 12 accumulator tiles (48 registers) x 3 products
+//               (hi*hi + hi*lo + lo*hi) = 36 mma.sync per 4 SHPs.  The next chunk's operands are
+//               loaded while the current chunk is multiplied.
+//   hand-off    accumulator fragments -> coherence -> one full Hermitian matrix in shared memory.
+//   eigen, epilogue: as in evd_fast.cu (lane = row, vector broadcast from shared memory,
+//               heavy-ball momentum, phase reference / compressed SLC / temporal coherence).
+#include <math_constants.h>
+
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace fringe {
+
+#define FULLMASK 0xffffffffu
+
+#ifdef FRINGE_PHASE_CLOCKS
+#define PHASE_DECL long long ph_t = clock64(); unsigned long long ph[6] = {0, 0, 0, 0, 0, 0};
+#define PHASE_MARK(k) { const long long ph_n = clock64(); ph[k] += (unsigned long long)(ph_n - ph_t); ph_t = ph_n; }
+#define PHASE_FLUSH if (a.stats && lane == 0) { for (int k = 0; k < 6; ++k) atomicAdd(&a.stats[4 + k], ph[k]); }
+#else
+#define PHASE_DECL
+#define PHASE_MARK(k)
+#define PHASE_FLUSH
+#endif
+
+namespace {
+
+__device__ __forceinline__ float fast_rsqrt(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+// D(16x8) += A(16x8, row) * B(8x8, col), TF32 inputs, FP32 accumulate
+__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// One SHP's share of a lane: bands g, g+8, g+16, g+24 as (re, im) pairs, hi and lo parts.
+struct MmaOperands {
+    uint32_t h[8], l[8];
+    __device__ __forceinline__ void load(const float* __restrict__ zq, int g) {
+        const uint4* p = reinterpret_cast<const uint4*>(zq) + 2 * g;
+        const uint4 h0 = __ldg(p), h1 = __ldg(p + 1), l0 = __ldg(p + 16), l1 = __ldg(p + 17);
+        h[0] = h0.x; h[1] = h0.y; h[2] = h0.z; h[3] = h0.w; h[4] = h1.x; h[5] = h1.y; h[6] = h1.z; h[7] = h1.w;
+        l[0] = l0.x; l[1] = l0.y; l[2] = l0.z; l[3] = l0.w; l[4] = l1.x; l[5] = l1.y; l[6] = l1.z; l[7] = l1.w;
+    }
+};
+
+// tiles (I, J) on or above the diagonal of the 2 x 4 grid of 16 x 8 tiles
+__device__ __forceinline__ constexpr int tile_i(int tl) { return tl < 4 ? 0 : 1; }
+__device__ __forceinline__ constexpr int tile_j(int tl) { return tl < 4 ? tl : tl - 2; }
+
+// 4 SHPs (one per t) into the 6 real and 6 imaginary accumulator tiles: 36 mma.sync
+__device__ __forceinline__ void mma_chunk(float (&cre)[6][4], float (&cim)[6][4], const MmaOperands& o) {
+    uint32_t nh[4], nl[4];                       // -im of bands q (hi, lo): sign bit flip
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { nh[q] = o.h[2 * q + 1] ^ 0x80000000u; nl[q] = o.l[2 * q + 1] ^ 0x80000000u; }
+    // products outermost: the 12 accumulator tiles are independent, so consecutive mma.sync never
+    // wait for each other (with the tile loop outermost every instruction would depend on the one
+    // issued two slots earlier and the tensor pipe would idle for the mma latency)
+#pragma unroll
+    for (int prod = 0; prod < 3; ++prod) {
+#pragma unroll
+        for (int tl = 0; tl < 6; ++tl) {
+            const int I = tile_i(tl), J = tile_j(tl);
+            // A fragment of row block I: (re_2I, re_2I+1, im_2I, im_2I+1); hi for products 0, 1, lo for 2
+            const uint32_t* av = (prod == 2) ? o.l : o.h;
+            const uint32_t a0 = av[4 * I], a1 = av[4 * I + 2], a2 = av[4 * I + 1], a3 = av[4 * I + 3];
+            // B fragments of column block J: real product (re_J, im_J), imaginary product (-im_J, re_J);
+            // lo for product 1
+            const uint32_t* bv = (prod == 1) ? o.l : o.h;
+            const uint32_t* nv = (prod == 1) ? nl : nh;
+            mma_tf32(cre[tl], a0, a1, a2, a3, bv[2 * J], bv[2 * J + 1]);
+            mma_tf32(cim[tl], a0, a1, a2, a3, nv[J], bv[2 * J]);
+        }
+    }
+}
+
+template <int NE>
+struct MmaCfg {
+    static constexpr int WARPS = 4;
+    static constexpr int MAT = NE * NE;                 // float2 elements of the coherence matrix
+    // per warp: matrix, two broadcast vectors (double buffered), 32 powers, 64 list slots
+    static constexpr int SMEM_PER_WARP =
+        (((MAT + 2 * 32) * (int)sizeof(float2) + 32 * (int)sizeof(float) + 64 * (int)sizeof(int)) + 15) & ~15;
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// re-layout: [bands][npix] -> [npix][hi 64 | lo 64] floats (see the header of this file)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_transpose_mma(const float2* __restrict__ slc, long npix, long first,
+                                                       long pend, int bands, float* __restrict__ zf) {
+    const int pix = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const long p = first + (long)blockIdx.x * 32 + pix;
+    if (p >= pend) return;
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int b = g + 8 * q;
+        float2 v = make_float2(0.f, 0.f);
+        if (b < bands) v = __ldg(&slc[(long)b * npix + p]);
+        const uint32_t hx = to_tf32(v.x), hy = to_tf32(v.y);
+        const float rx = v.x - __uint_as_float(hx), ry = v.y - __uint_as_float(hy);
+        h[2 * q] = hx; h[2 * q + 1] = hy;
+        l[2 * q] = isfinite(rx) ? to_tf32(rx) : 0u;
+        l[2 * q + 1] = isfinite(ry) ? to_tf32(ry) : 0u;
+    }
+    uint4* o = reinterpret_cast<uint4*>(zf + p * 128) + 2 * g;
+    o[0] = make_uint4(h[0], h[1], h[2], h[3]);
+    o[1] = make_uint4(h[4], h[5], h[6], h[7]);
+    o[16] = make_uint4(l[0], l[1], l[2], l[3]);
+    o[17] = make_uint4(l[4], l[5], l[6], l[7]);
+}
+
+cudaError_t launch_transpose_mma(const float2* slc, long npix, long first, long count, int bands, float2* zpix,
+                                 cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    k_transpose_mma<<<(unsigned)((count + 31) / 32), 256, 0, st>>>(slc, npix, first, first + count, bands,
+                                                                  reinterpret_cast<float*>(zpix));
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+template <int NE>
+__global__ void __launch_bounds__(128, 3) k_evd_mma(const EvdArgs a) {
+    typedef MmaCfg<NE> Cfg;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int N = a.bands;                      // <= NE <= 32
+
+    // CTA-wide table: window bit index -> (dy, dx)
+    short2* s_off = reinterpret_cast<short2*>(s_raw);
+    const int WX = 2 * a.Nx + 1, W = WX * (2 * a.Ny + 1), center = a.Ny * WX + a.Nx;
+    for (int f = threadIdx.x; f < a.nulong * 32; f += blockDim.x) {
+        const int fy = f / WX;
+        s_off[f] = (f < W) ? make_short2((short)(fy - a.Ny), (short)(f - fy * WX - a.Nx))
+                           : make_short2((short)-30000, (short)-30000);   // never in bounds
+    }
+    __syncthreads();
+    const int lut_bytes = ((a.nulong * 32 * (int)sizeof(short2)) + 15) & ~15;
+
+    unsigned char* base = s_raw + lut_bytes + (size_t)warp * Cfg::SMEM_PER_WARP;
+    float2* s_mat = reinterpret_cast<float2*>(base);                       // [NE][NE]
+    float2* s_vec = s_mat + Cfg::MAT;                                      // [2][32]
+    float* s_pw = reinterpret_cast<float*>(s_vec + 64);                    // [32]
+    int* s_list = reinterpret_cast<int*>(s_pw + 32);                       // [64]
+
+    const int k0 = a.mini_stack_count - 1;
+    const bool isstbas = (a.method == 2);
+    const int BW = a.bandwidth;
+    // bit j set: the pair (lane, j) enters the temporal-coherence sum (j > lane, inside the
+    // matrix and, for STBAS, inside the band)
+    uint32_t usemask = 0u;
+    for (int j = 0; j < N; ++j)
+        if (j > lane && (!isstbas || (j - lane) <= BW)) usemask |= (1u << j);
+    float inv_pairs;                             // 1 / number of (i<j) pairs (evd.cpp:773-784)
+    {
+        int cnt = 0;
+        for (int i = 0; i < N; ++i) cnt += isstbas ? min(BW, N - 1 - i) : (N - 1 - i);
+        inv_pairs = 1.0f / (float)cnt;
+    }
+    const long npix_block = (long)a.cols * a.lines;
+    const float* zf = reinterpret_cast<const float*>(a.zpix);
+
+    const long total = (long)a.n_lines * a.cols;
+    const long chunk = (total + gridDim.x - 1) / gridDim.x;
+    const long beg = (long)blockIdx.x * chunk;
+    const long end = min(total, beg + chunk);
+    unsigned long long st_pix = 0, st_it = 0, st_cap = 0;
+    PHASE_DECL
+
+    const bool in_regs = a.nulong <= 32;
+    auto load_mask_word = [&](long px) -> uint32_t {          // lane w keeps word w of the pixel's mask
+        if (px >= end || lane >= a.nulong) return 0u;
+        const long pp = (long)a.first_line * a.cols + px;
+        return __ldg(&a.wts[pp * a.nulong + lane]);
+    };
+    uint32_t mw_next = load_mask_word(beg + warp);
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int zero_idx = (int)npix_block;         // index of the all-zero sample vector
+
+#pragma unroll 1
+    for (long px = beg + warp; px < end; px += Cfg::WARPS) {
+        const int row = a.first_line + (int)(px / a.cols);
+        const int col = (int)(px % a.cols);
+        const long pg = (long)row * a.cols + col;
+        const uint32_t mw = mw_next;
+        mw_next = load_mask_word(px + Cfg::WARPS);
+        auto mask_word = [&](int w) -> uint32_t {               // w warp-uniform
+            if (w >= a.nulong) return 0u;
+            return in_regs ? __shfl_sync(FULLMASK, mw, w) : __ldg(&a.wts[pg * a.nulong + w]);
+        };
+        const bool center_on = (mask_word(center >> 5) >> (center & 31)) & 1u;
+
+        // ------------------------- covariance (evd.cpp:537-564) -------------------------
+        float cre[6][4], cim[6][4];
+#pragma unroll
+        for (int tl = 0; tl < 6; ++tl)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { cre[tl][e] = 0.f; cim[tl][e] = 0.f; }
+        int npix = 0;
+#pragma unroll 1
+        for (int w0 = 0; w0 < a.nulong; w0 += 2) {
+            int n = 0;
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int w = w0 + c;
+                const uint32_t word = center_on ? mask_word(w) : 0u;
+                const short2 d = s_off[min(w, a.nulong - 1) * 32 + lane];
+                const int yy = row + d.x, xx = col + d.y;
+                const bool ok = ((word >> lane) & 1u) && yy >= 0 && yy < a.lines && xx >= 0 && xx < a.cols;
+                const uint32_t V = __ballot_sync(FULLMASK, ok);
+                if (ok) s_list[n + __popc(V & lt_mask)] = yy * a.cols + xx;
+                n += __popc(V);
+            }
+            npix += n;
+            const int chunks = ((n + 7) >> 3) << 1;            // 4 SHPs per chunk, chunks consumed in pairs
+            if (lane < 8 && n + lane < 4 * chunks) s_list[n + lane] = zero_idx;
+            __syncwarp();
+            PHASE_MARK(0)
+            MmaOperands opA, opB;
+            if (chunks > 0) opA.load(zf + (long)s_list[t] * 128, g);
+#pragma unroll 1
+            for (int c = 0; c < chunks; c += 2) {
+                opB.load(zf + (long)s_list[4 * (c + 1) + t] * 128, g);
+                mma_chunk(cre, cim, opA);
+                opA.load(zf + (long)s_list[4 * min(c + 2, chunks - 1) + t] * 128, g);
+                mma_chunk(cre, cim, opB);
+            }
+            PHASE_MARK(1)
+        }
+        const bool solve = center_on && (npix >= 2);         // evd.cpp:566 hard-codes 2
+
+        // ------------------------- coherence (evd.cpp:569-582) --------------------------
+        // accumulator fragment of tile (I, J): element e is row 16 I + g + 8 (e >> 1), column 8 J + 2 t + (e & 1)
+        __syncwarp();
+        if (g == 2 * t || g == 2 * t + 1) {
+            const bool odd = (g != 2 * t);              // selects, not a runtime index: keeps the tiles in registers
+            const float p0 = odd ? cre[0][1] : cre[0][0], p1 = odd ? cre[1][3] : cre[1][2];
+            const float p2 = odd ? cre[4][1] : cre[4][0], p3 = odd ? cre[5][3] : cre[5][2];
+            // padded bands get +inf so that their scaled entries come out as exact zeros
+            s_pw[g] = (g < N) ? sqrtf(p0) : CUDART_INF_F;
+            s_pw[g + 8] = (g + 8 < N) ? sqrtf(p1) : CUDART_INF_F;
+            s_pw[g + 16] = (g + 16 < N) ? sqrtf(p2) : CUDART_INF_F;
+            s_pw[g + 24] = (g + 24 < N) ? sqrtf(p3) : CUDART_INF_F;
+        }
+        __syncwarp();
+        {
+            float ir[4], ic[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ir[q] = fast_rcp(s_pw[g + 8 * q]);
+#pragma unroll
+            for (int J = 0; J < 4; ++J) { ic[2 * J] = fast_rcp(s_pw[8 * J + 2 * t]); ic[2 * J + 1] = fast_rcp(s_pw[8 * J + 2 * t + 1]); }
+#pragma unroll
+            for (int tl = 0; tl < 6; ++tl) {
+                const int I = tile_i(tl), J = tile_j(tl);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int r = 16 * I + g + 8 * (e >> 1), c = 8 * J + 2 * t + (e & 1);
+                    const float s = ir[2 * I + (e >> 1)] * ic[2 * J + (e & 1)];
+                    if (c > r && c < NE) {                   // strict upper entry and its mirror
+                        const float2 v = make_float2(cre[tl][e] * s, cim[tl][e] * s);
+                        s_mat[r * NE + c] = v;
+                        s_mat[c * NE + r] = make_float2(v.x, -v.y);
+                    }
+                }
+            }
+            if (lane < NE) s_mat[lane * NE + lane] = make_float2((lane < N) ? 1.f : 0.f, 0.f);
+        }
+        __syncwarp();
+        PHASE_MARK(2)
+
+        // ------------------------- eigen + epilogue --------------------------------------
+        float2 o = make_float2(0.f, 0.f);
+        float tc = 0.f;
+        float2 cmp = make_float2(0.f, 0.f);
+        if (solve) {
+            ++st_pix;
+            const int r = (lane < NE) ? lane : (NE - 1);
+            float2 c[NE];
+            {
+                const float4* rowp = reinterpret_cast<const float4*>(s_mat + r * NE);
+#pragma unroll
+                for (int j = 0; j < NE; j += 2) {
+                    const float4 v = rowp[j >> 1];
+                    c[j] = make_float2(v.x, v.y); c[j + 1] = make_float2(v.z, v.w);
+                }
+            }
+            // rows >= N of the padded matrix are exact zeros; only lanes beyond the padded
+            // order (which re-read the last row) have to be silenced
+            const float live = (lane < NE) ? 1.f : 0.f;
+            if (isstbas) {                                   // evd.cpp:695-706 band limit
+#pragma unroll
+                for (int j = 0; j < NE; ++j)
+                    if (abs(j - lane) > BW) c[j] = make_float2(0.f, 0.f);
+            }
+            // start vector: column k0 of C reduced to unit modulus (the dominant eigenvector of a
+            // coherence matrix has nearly uniform magnitudes)
+            float2 x;
+            {
+                const float2 v = s_mat[k0 * NE + r];
+                const float keep = (isstbas && abs(k0 - lane) > BW) ? 0.f : live;
+                x = make_float2(v.x * keep, -v.y * keep);
+                const float m2 = x.x * x.x + x.y * x.y;
+                const float rs = (m2 > 0.f) ? fast_rsqrt(m2) : 0.f;
+                x.x *= rs; x.y *= rs;
+                float n2 = x.x * x.x + x.y * x.y;
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) n2 += __shfl_xor_sync(FULLMASK, n2, s);
+                const float sc = rsqrtf(n2);
+                x.x *= sc; x.y *= sc;
+            }
+            PHASE_MARK(3)
+            // Power iteration with heavy-ball momentum (see evd_fast.cu): x+ = C x / lambda - beta x-
+            float lam = 1.f, inv_lam = 1.f, beta = 0.f, rho_prev = -1.f;
+            float2 xp = make_float2(0.f, 0.f);
+            int it = 0, buf = 0;
+            bool conv = false;
+            const int kMaxIter = (a.force_generic >> 1) ? (a.force_generic >> 1) : 1000;   // upper bits: timing experiment only
+            const float tol2 = 4.0e-12f;
+#pragma unroll 1
+            for (; it < kMaxIter; ++it) {
+                float2* xv = s_vec + buf * 32;
+                buf ^= 1;
+                xv[lane] = x;
+                __syncwarp();
+                float r0 = 0.f, r1 = 0.f, r2a = 0.f, r3 = 0.f, i0 = 0.f, i1 = 0.f, i2 = 0.f, i3 = 0.f;
+                const float4* xv4 = reinterpret_cast<const float4*>(xv);
+#pragma unroll
+                for (int j = 0; j + 1 < NE; j += 2) {
+                    const float4 q = xv4[j >> 1];
+                    r0 = fmaf(c[j].x, q.x, r0); r1 = fmaf(-c[j].y, q.y, r1);
+                    i0 = fmaf(c[j].x, q.y, i0); i1 = fmaf(c[j].y, q.x, i1);
+                    r2a = fmaf(c[j + 1].x, q.z, r2a); r3 = fmaf(-c[j + 1].y, q.w, r3);
+                    i2 = fmaf(c[j + 1].x, q.w, i2); i3 = fmaf(c[j + 1].y, q.z, i3);
+                }
+                const float yr = ((r0 + r1) + (r2a + r3)) * live, yi = ((i0 + i1) + (i2 + i3)) * live;
+                const int ph4 = it & 3;
+                if (ph4 < 2) {
+                    const float2 xn = make_float2(fmaf(-beta, xp.x, yr * inv_lam), fmaf(-beta, xp.y, yi * inv_lam));
+                    xp = x; x = xn;
+                } else if (ph4 == 2) {
+                    // Rayleigh quotient one iteration ahead of the residual test, so that the two warp
+                    // reductions are separate single rounds (the quotient's error is second order in the
+                    // residual, one iteration of staleness is far below the tolerance); renormalise here
+                    float xy = x.x * yr + x.y * yi, xx = x.x * x.x + x.y * x.y;
+#pragma unroll
+                    for (int s = 16; s > 0; s >>= 1) {
+                        xy += __shfl_xor_sync(FULLMASK, xy, s);
+                        xx += __shfl_xor_sync(FULLMASK, xx, s);
+                    }
+                    const float ixx = fast_rcp(xx);
+                    lam = xy * ixx;
+                    inv_lam = fast_rcp(lam);
+                    const float sc = fast_rsqrt(xx);
+                    const float2 xn = make_float2(fmaf(-beta, xp.x, yr * inv_lam) * sc, fmaf(-beta, xp.y, yi * inv_lam) * sc);
+                    xp = make_float2(x.x * sc, x.y * sc);
+                    x = xn;
+                } else {
+                    // residual against the quotient of the previous iteration
+                    const float rx = yr - lam * x.x, ry = yi - lam * x.y;
+                    float rr2 = rx * rx + ry * ry, y2 = yr * yr + yi * yi, xx = x.x * x.x + x.y * x.y;
+#pragma unroll
+                    for (int s = 16; s > 0; s >>= 1) {
+                        rr2 += __shfl_xor_sync(FULLMASK, rr2, s);
+                        y2 += __shfl_xor_sync(FULLMASK, y2, s);
+                        xx += __shfl_xor_sync(FULLMASK, xx, s);
+                    }
+                    const float rho2 = rr2 * fast_rcp(lam * lam * xx);   // relative residual^2
+                    conv = (rho2 <= tol2);
+                    if (conv) {                                          // final vector: one more plain step
+                        const float sc = rsqrtf(y2);
+                        x.x = yr * sc; x.y = yi * sc;
+                        ++it; break;
+                    }
+                    if (beta == 0.f && rho_prev > 0.f && rho2 < rho_prev) {
+                        const float rr = sqrtf(sqrtf(sqrtf(rho2 * fast_rcp(rho_prev))));   // (rho2 ratio)^(1/8): per-iteration rate
+                        const float hb = 0.475f * rr;
+                        beta = hb * hb;
+                    }
+                    rho_prev = rho2;
+                    const float2 xn = make_float2(fmaf(-beta, xp.x, yr * inv_lam), fmaf(-beta, xp.y, yi * inv_lam));
+                    xp = x; x = xn;
+                }
+            }
+            PHASE_MARK(4)
+            st_it += it;
+            st_cap += conv ? 0 : 1;
+            if (lam < 1.0e-6f) tc = -7.f;             // evd.cpp:723-727
+            else {
+                // ---------------- phase reference (evd.cpp:738-749) -----------------
+                float2* xv = s_vec + buf * 32;
+                buf ^= 1;
+                xv[lane] = x;
+                __syncwarp();
+                const float2 ref = xv[k0];
+                {
+                    float ux = x.x * ref.x + x.y * ref.y, uy = x.y * ref.x - x.x * ref.y;
+                    const float mm = ux * ux + uy * uy;
+                    if (mm == 0.f) {                  // arg(0) = 0 in the reference
+                        const float rr = rsqrtf(ref.x * ref.x + ref.y * ref.y);
+                        ux = ref.x * rr; uy = -ref.y * rr;
+                    } else { const float rr = fast_rsqrt(mm); ux *= rr; uy *= rr; }
+                    if (lane == k0) { ux = 1.f; uy = 0.f; }
+                    o = make_float2(ux * live, uy * live);
+                }
+                // ---------------- compressed SLC (evd.cpp:755-762) ------------------
+                float cr = 0.f, ci = 0.f;
+                if (lane < N && lane >= k0) {
+                    const float2 z = __ldg(&a.slc[(long)lane * npix_block + pg]);
+                    cr = z.x * o.x + z.y * o.y;
+                    ci = z.y * o.x - z.x * o.y;
+                }
+                // ---------------- temporal coherence (evd.cpp:770-786) --------------
+                float2* ov = s_vec + buf * 32;
+                buf ^= 1;
+                ov[lane] = o;
+                __syncwarp();
+                float wr = 0.f, wi = 0.f;
+                const float4* ov4 = reinterpret_cast<const float4*>(ov);
+#pragma unroll
+                for (int j = 0; j < NE; ++j) {
+                    const bool use = (usemask >> j) & 1u;
+                    const float m2 = fmaf(c[j].x, c[j].x, c[j].y * c[j].y);
+                    const float rr = use ? fast_rsqrt(m2) : 0.f;
+                    const float ex = (m2 > 0.f) ? c[j].x * rr : (use ? 1.f : 0.f);
+                    const float ey = (m2 > 0.f) ? c[j].y * rr : 0.f;
+                    const float4 q = ov4[j >> 1];
+                    const float2 oj = (j & 1) ? make_float2(q.z, q.w) : make_float2(q.x, q.y);
+                    wr = fmaf(ex, oj.x, wr); wr = fmaf(-ey, oj.y, wr);
+                    wi = fmaf(ex, oj.y, wi); wi = fmaf(ey, oj.x, wi);
+                }
+                float sr = o.x * wr + o.y * wi, si = o.x * wi - o.y * wr;      // conj(o_r) * w_r
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) {
+                    sr += __shfl_xor_sync(FULLMASK, sr, s);
+                    si += __shfl_xor_sync(FULLMASK, si, s);
+                    cr += __shfl_xor_sync(FULLMASK, cr, s);
+                    ci += __shfl_xor_sync(FULLMASK, ci, s);
+                }
+                tc = sqrtf(sr * sr + si * si) * inv_pairs;
+                const float invn = 1.0f / (float)(N - a.mini_stack_count + 1);
+                cmp = make_float2(cr * invn, ci * invn);
+            }
+        }
+        if (lane < N) a.out[(long)lane * npix_block + pg] = o;
+        if (lane == 0) { a.tcorr[pg] = tc; a.comp[pg] = cmp; }
+        __syncwarp();
+        PHASE_MARK(5)
+    }
+    PHASE_FLUSH
+    if (a.stats && lane == 0) {
+        atomicAdd(&a.stats[0], st_pix);
+        atomicAdd(&a.stats[1], st_it);
+        atomicAdd(&a.stats[3], st_cap);
+    }
+}
+
+template <int NE>
+static cudaError_t launch_mma_t(const EvdArgs& a, cudaStream_t st) {
+    typedef MmaCfg<NE> Cfg;
+    const size_t lut = ((size_t)a.nulong * 32 * sizeof(short2) + 15) & ~(size_t)15;
+    const size_t smem = lut + (size_t)Cfg::SMEM_PER_WARP * Cfg::WARPS;
+    cudaError_t e = cudaFuncSetAttribute(k_evd_mma<NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, nsm = 148, occ = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_evd_mma<NE>, Cfg::WARPS * 32, smem);
+    if (occ < 1) occ = 1;
+    const long total = (long)a.n_lines * a.cols;
+    int mult = 8;
+    if (const char* ev = getenv("FRINGE_EVD_CHUNKS")) { const int v = atoi(ev); if (v > 0) mult = v; }
+    long grid = (long)nsm * occ * mult;
+    const long maxgrid = (total + Cfg::WARPS * 8 - 1) / (Cfg::WARPS * 8);
+    if (grid > maxgrid) grid = maxgrid;
+    if (grid < 1) grid = 1;
+    k_evd_mma<NE><<<(unsigned)grid, Cfg::WARPS * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+// eigen-phase order: the smallest instantiated even order >= bands
+int evd_mma_order(int bands) {
+    static const int orders[] = {8, 12, 16, 20, 24, 28, 30, 32};
+    if (bands < 2) return 0;
+    for (int o : orders) if (bands <= o) return o;
+    return 0;
+}
+
+cudaError_t launch_evd_mma(const EvdArgs& a, cudaStream_t st) {
+    switch (evd_mma_order(a.bands)) {
+        case 8: return launch_mma_t<8>(a, st);
+        case 12: return launch_mma_t<12>(a, st);
+        case 16: return launch_mma_t<16>(a, st);
+        case 20: return launch_mma_t<20>(a, st);
+        case 24: return launch_mma_t<24>(a, st);
+        case 28: return launch_mma_t<28>(a, st);
+        case 30: return launch_mma_t<30>(a, st);
+        case 32: return launch_mma_t<32>(a, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace fringe

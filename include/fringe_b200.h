@@ -160,6 +160,9 @@ int fringe_fp32_peak(fringe_ctx* ctx, double* tflops);
 /* FP32 rate of a register-resident 6x6 complex block update (the covariance inner step with loads
  * and address arithmetic removed): the practical ceiling of that loop, [0] interleaved and [1] de-interleaved scalar FFMA, [2] packed fma.rn.f32x2. */
 int fringe_block_fma_rate(fringe_ctx* ctx, double tflops[3]);
+/* Dense TF32 TFLOP/s of the warp-level mma.sync.m16n8k8 path (12 independent accumulator tiles per
+ * warp): the tensor-pipe alternative the covariance was weighed against. */
+int fringe_mma_tf32_rate(fringe_ctx* ctx, double* tflops);
 
 /* Per-pixel solver statistics of the most recent evd call on this context (debug/bench):
  * stats[0] pixels solved, [1] total FP32 power iterations, [2] pixels that took the FP64
