@@ -6,8 +6,8 @@
 //
 //   layout      k_transpose_mma splits every sample into a TF32 "hi" part and a TF32 "lo"
 //               remainder (x = hi + lo to ~2^-22) and stores a pixel's 32 (zero padded) bands as
-//               128 floats: hi[g][q][re,im] for g = 0..7, q = 0..3 (band = g + 8 q), then lo in
-//               the same order.  Lane (g, t) of a warp therefore fetches everything it needs of
+//               128 floats: for g = 0..7 two quads (re, re', im, im') of bands (g, g+8) and
+//               (g+16, g+24) -- each quad is an A fragment as loaded -- then lo in the same order.  Lane (g, t) of a warp therefore fetches everything it needs of
 //               one SHP with four 16-byte loads, and the eight lanes that share t read the SHP's
 //               512 bytes contiguously.
 //   covariance  One warp per pixel.  Four SHPs form one k-chunk of m16n8k8: k = 0..3 are the real
@@ -67,14 +67,14 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// One SHP's share of a lane: bands g, g+8, g+16, g+24 as (re, im) pairs, hi and lo parts.
+// One SHP's share of a lane: bands g, g+8, g+16, g+24, hi and lo parts, stored so that each
+// 16-byte load is an A fragment as it stands: quad I = (re, re', im, im') of bands 16 I + g and
+// 16 I + g + 8.
 struct MmaOperands {
-    uint32_t h[8], l[8];
+    uint4 ah[2], al[2];
     __device__ __forceinline__ void load(const float* __restrict__ zq, int g) {
         const uint4* p = reinterpret_cast<const uint4*>(zq) + 2 * g;
-        const uint4 h0 = __ldg(p), h1 = __ldg(p + 1), l0 = __ldg(p + 16), l1 = __ldg(p + 17);
-        h[0] = h0.x; h[1] = h0.y; h[2] = h0.z; h[3] = h0.w; h[4] = h1.x; h[5] = h1.y; h[6] = h1.z; h[7] = h1.w;
-        l[0] = l0.x; l[1] = l0.y; l[2] = l0.z; l[3] = l0.w; l[4] = l1.x; l[5] = l1.y; l[6] = l1.z; l[7] = l1.w;
+        ah[0] = __ldg(p); ah[1] = __ldg(p + 1); al[0] = __ldg(p + 16); al[1] = __ldg(p + 17);
     }
 };
 
@@ -84,9 +84,20 @@ __device__ __forceinline__ constexpr int tile_j(int tl) { return tl < 4 ? tl : t
 
 // 4 SHPs (one per t) into the 6 real and 6 imaginary accumulator tiles: 36 mma.sync
 __device__ __forceinline__ void mma_chunk(float (&cre)[6][4], float (&cim)[6][4], const MmaOperands& o) {
-    uint32_t nh[4], nl[4];                       // -im of bands q (hi, lo): sign bit flip
+    // B fragments of column block J (band 8 J + g), every role in its own register pair so that the
+    // pairs stay put across the instructions that use them: real product (re, im), imaginary
+    // product (-im, re); hi and lo
+    uint32_t bh[4][2], bl[4][2], nh[4][2], nl[4][2];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { nh[q] = o.h[2 * q + 1] ^ 0x80000000u; nl[q] = o.l[2 * q + 1] ^ 0x80000000u; }
+    for (int I = 0; I < 2; ++I) {
+        bh[2 * I][0] = o.ah[I].x; bh[2 * I][1] = o.ah[I].z; bh[2 * I + 1][0] = o.ah[I].y; bh[2 * I + 1][1] = o.ah[I].w;
+        bl[2 * I][0] = o.al[I].x; bl[2 * I][1] = o.al[I].z; bl[2 * I + 1][0] = o.al[I].y; bl[2 * I + 1][1] = o.al[I].w;
+    }
+#pragma unroll
+    for (int J = 0; J < 4; ++J) {
+        nh[J][0] = bh[J][1] ^ 0x80000000u; nh[J][1] = bh[J][0];
+        nl[J][0] = bl[J][1] ^ 0x80000000u; nl[J][1] = bl[J][0];
+    }
     // products outermost: the 12 accumulator tiles are independent, so consecutive mma.sync never
     // wait for each other (with the tile loop outermost every instruction would depend on the one
     // issued two slots earlier and the tensor pipe would idle for the mma latency)
@@ -95,15 +106,11 @@ __device__ __forceinline__ void mma_chunk(float (&cre)[6][4], float (&cim)[6][4]
 #pragma unroll
         for (int tl = 0; tl < 6; ++tl) {
             const int I = tile_i(tl), J = tile_j(tl);
-            // A fragment of row block I: (re_2I, re_2I+1, im_2I, im_2I+1); hi for products 0, 1, lo for 2
-            const uint32_t* av = (prod == 2) ? o.l : o.h;
-            const uint32_t a0 = av[4 * I], a1 = av[4 * I + 2], a2 = av[4 * I + 1], a3 = av[4 * I + 3];
-            // B fragments of column block J: real product (re_J, im_J), imaginary product (-im_J, re_J);
-            // lo for product 1
-            const uint32_t* bv = (prod == 1) ? o.l : o.h;
-            const uint32_t* nv = (prod == 1) ? nl : nh;
-            mma_tf32(cre[tl], a0, a1, a2, a3, bv[2 * J], bv[2 * J + 1]);
-            mma_tf32(cim[tl], a0, a1, a2, a3, nv[J], bv[2 * J]);
+            const uint4 av = (prod == 2) ? o.al[I] : o.ah[I];            // hi * hi, hi * lo, lo * hi
+            const uint32_t* bv = (prod == 1) ? bl[J] : bh[J];
+            const uint32_t* nv = (prod == 1) ? nl[J] : nh[J];
+            mma_tf32(cre[tl], av.x, av.y, av.z, av.w, bv[0], bv[1]);
+            mma_tf32(cim[tl], av.x, av.y, av.z, av.w, nv[0], nv[1]);
         }
     }
 }
@@ -111,11 +118,32 @@ __device__ __forceinline__ void mma_chunk(float (&cre)[6][4], float (&cim)[6][4]
 template <int NE>
 struct MmaCfg {
     static constexpr int WARPS = 4;
-    static constexpr int MAT = NE * NE;                 // float2 elements of the coherence matrix
-    // per warp: matrix, two broadcast vectors (double buffered), 32 powers, 64 list slots
+    // coherence matrix in shared memory: real and imaginary planes, rows NS floats apart;
+    // NS = 4 (mod 8) keeps rows 16-byte aligned and spreads the hand-off stores over the banks
+    static constexpr int NS = ((NE + 3) / 4 * 4) % 8 == 4 ? (NE + 3) / 4 * 4 : (NE + 3) / 4 * 4 + 4;
+    static constexpr int PLANE = NE * NS;               // floats per plane
+    // per warp: two planes, two broadcast vectors (double buffered, re | im planes of 32),
+    // 32 powers, 64 list slots
     static constexpr int SMEM_PER_WARP =
-        (((MAT + 2 * 32) * (int)sizeof(float2) + 32 * (int)sizeof(float) + 64 * (int)sizeof(int)) + 15) & ~15;
+        (((2 * PLANE + 2 * 64 + 32) * (int)sizeof(float) + 64 * (int)sizeof(int)) + 15) & ~15;
 };
+
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {       // two FP32 FMAs in one instruction
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ float2 unpack2(u64 v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ u64 pack2(float x, float y) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
 
 }  // namespace
 
@@ -127,6 +155,7 @@ __global__ void __launch_bounds__(256) k_transpose_mma(const float2* __restrict_
     const int pix = threadIdx.x & 31, g = threadIdx.x >> 5;
     const long p = first + (long)blockIdx.x * 32 + pix;
     if (p >= pend) return;
+    // quad I = (re, re', im, im') of bands 16 I + g and 16 I + g + 8
     uint32_t h[8], l[8];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -135,9 +164,10 @@ __global__ void __launch_bounds__(256) k_transpose_mma(const float2* __restrict_
         if (b < bands) v = __ldg(&slc[(long)b * npix + p]);
         const uint32_t hx = to_tf32(v.x), hy = to_tf32(v.y);
         const float rx = v.x - __uint_as_float(hx), ry = v.y - __uint_as_float(hy);
-        h[2 * q] = hx; h[2 * q + 1] = hy;
-        l[2 * q] = isfinite(rx) ? to_tf32(rx) : 0u;
-        l[2 * q + 1] = isfinite(ry) ? to_tf32(ry) : 0u;
+        const int k = 4 * (q >> 1) + (q & 1);
+        h[k] = hx; h[k + 2] = hy;
+        l[k] = isfinite(rx) ? to_tf32(rx) : 0u;
+        l[k + 2] = isfinite(ry) ? to_tf32(ry) : 0u;
     }
     uint4* o = reinterpret_cast<uint4*>(zf + p * 128) + 2 * g;
     o[0] = make_uint4(h[0], h[1], h[2], h[3]);
@@ -175,9 +205,11 @@ __global__ void __launch_bounds__(128, 3) k_evd_mma(const EvdArgs a) {
     const int lut_bytes = ((a.nulong * 32 * (int)sizeof(short2)) + 15) & ~15;
 
     unsigned char* base = s_raw + lut_bytes + (size_t)warp * Cfg::SMEM_PER_WARP;
-    float2* s_mat = reinterpret_cast<float2*>(base);                       // [NE][NE]
-    float2* s_vec = s_mat + Cfg::MAT;                                      // [2][32]
-    float* s_pw = reinterpret_cast<float*>(s_vec + 64);                    // [32]
+    constexpr int NS = Cfg::NS;
+    float* s_re = reinterpret_cast<float*>(base);                          // [NE][NS]
+    float* s_im = s_re + Cfg::PLANE;                                       // [NE][NS]
+    float* s_vec = s_im + Cfg::PLANE;                                      // [2][re 32 | im 32]
+    float* s_pw = s_vec + 128;                                             // [32]
     int* s_list = reinterpret_cast<int*>(s_pw + 32);                       // [64]
 
     const int k0 = a.mini_stack_count - 1;
@@ -250,19 +282,21 @@ __global__ void __launch_bounds__(128, 3) k_evd_mma(const EvdArgs a) {
                 n += __popc(V);
             }
             npix += n;
-            const int chunks = ((n + 7) >> 3) << 1;            // 4 SHPs per chunk, chunks consumed in pairs
-            if (lane < 8 && n + lane < 4 * chunks) s_list[n + lane] = zero_idx;
+            const int chunks = (n + 3) >> 2;                   // 4 SHPs per chunk
+            if (lane < 4 && n + lane < 4 * chunks) s_list[n + lane] = zero_idx;
             __syncwarp();
             PHASE_MARK(0)
             MmaOperands opA, opB;
             if (chunks > 0) opA.load(zf + (long)s_list[t] * 128, g);
+            int c = 0;
 #pragma unroll 1
-            for (int c = 0; c < chunks; c += 2) {
+            for (; c + 2 <= chunks; c += 2) {                  // chunk c+1 loads while chunk c multiplies, and so on
                 opB.load(zf + (long)s_list[4 * (c + 1) + t] * 128, g);
                 mma_chunk(cre, cim, opA);
                 opA.load(zf + (long)s_list[4 * min(c + 2, chunks - 1) + t] * 128, g);
                 mma_chunk(cre, cim, opB);
             }
+            if (c < chunks) mma_chunk(cre, cim, opA);          // odd count: the last chunk is already in opA
             PHASE_MARK(1)
         }
         const bool solve = center_on && (npix >= 2);         // evd.cpp:566 hard-codes 2
@@ -295,13 +329,13 @@ __global__ void __launch_bounds__(128, 3) k_evd_mma(const EvdArgs a) {
                     const int r = 16 * I + g + 8 * (e >> 1), c = 8 * J + 2 * t + (e & 1);
                     const float s = ir[2 * I + (e >> 1)] * ic[2 * J + (e & 1)];
                     if (c > r && c < NE) {                   // strict upper entry and its mirror
-                        const float2 v = make_float2(cre[tl][e] * s, cim[tl][e] * s);
-                        s_mat[r * NE + c] = v;
-                        s_mat[c * NE + r] = make_float2(v.x, -v.y);
+                        const float vr = cre[tl][e] * s, vi = cim[tl][e] * s;
+                        s_re[r * NS + c] = vr; s_im[r * NS + c] = vi;
+                        s_re[c * NS + r] = vr; s_im[c * NS + r] = -vi;
                     }
                 }
             }
-            if (lane < NE) s_mat[lane * NE + lane] = make_float2((lane < N) ? 1.f : 0.f, 0.f);
+            if (lane < NE) { s_re[lane * NS + lane] = (lane < N) ? 1.f : 0.f; s_im[lane * NS + lane] = 0.f; }
         }
         __syncwarp();
         PHASE_MARK(2)
@@ -313,13 +347,20 @@ __global__ void __launch_bounds__(128, 3) k_evd_mma(const EvdArgs a) {
         if (solve) {
             ++st_pix;
             const int r = (lane < NE) ? lane : (NE - 1);
-            float2 c[NE];
+            // row r of the matrix as pairs of consecutive columns: cr2[k] = (Re C[r][2k], Re C[r][2k+1])
+            constexpr int NP2 = NE / 2;
+            u64 cr2[NP2], ci2[NP2];
             {
-                const float4* rowp = reinterpret_cast<const float4*>(s_mat + r * NE);
+                const ulonglong2* pr = reinterpret_cast<const ulonglong2*>(s_re + r * NS);
+                const ulonglong2* pi = reinterpret_cast<const ulonglong2*>(s_im + r * NS);
 #pragma unroll
-                for (int j = 0; j < NE; j += 2) {
-                    const float4 v = rowp[j >> 1];
-                    c[j] = make_float2(v.x, v.y); c[j + 1] = make_float2(v.z, v.w);
+                for (int k = 0; k + 1 < NP2; k += 2) {
+                    const ulonglong2 vr = pr[k >> 1], vi = pi[k >> 1];
+                    cr2[k] = vr.x; cr2[k + 1] = vr.y; ci2[k] = vi.x; ci2[k + 1] = vi.y;
+                }
+                if (NP2 & 1) {
+                    cr2[NP2 - 1] = *reinterpret_cast<const u64*>(s_re + r * NS + NE - 2);
+                    ci2[NP2 - 1] = *reinterpret_cast<const u64*>(s_im + r * NS + NE - 2);
                 }
             }
             // rows >= N of the padded matrix are exact zeros; only lanes beyond the padded
@@ -327,14 +368,18 @@ __global__ void __launch_bounds__(128, 3) k_evd_mma(const EvdArgs a) {
             const float live = (lane < NE) ? 1.f : 0.f;
             if (isstbas) {                                   // evd.cpp:695-706 band limit
 #pragma unroll
-                for (int j = 0; j < NE; ++j)
-                    if (abs(j - lane) > BW) c[j] = make_float2(0.f, 0.f);
+                for (int k = 0; k < NP2; ++k) {
+                    float2 vr = unpack2(cr2[k]), vi = unpack2(ci2[k]);
+                    if (abs(2 * k - lane) > BW) { vr.x = 0.f; vi.x = 0.f; }
+                    if (abs(2 * k + 1 - lane) > BW) { vr.y = 0.f; vi.y = 0.f; }
+                    cr2[k] = pack2(vr.x, vr.y); ci2[k] = pack2(vi.x, vi.y);
+                }
             }
             // start vector: column k0 of C reduced to unit modulus (the dominant eigenvector of a
             // coherence matrix has nearly uniform magnitudes)
             float2 x;
             {
-                const float2 v = s_mat[k0 * NE + r];
+                const float2 v = make_float2(s_re[k0 * NS + r], s_im[k0 * NS + r]);
                 const float keep = (isstbas && abs(k0 - lane) > BW) ? 0.f : live;
                 x = make_float2(v.x * keep, -v.y * keep);
                 const float m2 = x.x * x.x + x.y * x.y;
@@ -350,32 +395,45 @@ __global__ void __launch_bounds__(128, 3) k_evd_mma(const EvdArgs a) {
             // Power iteration with heavy-ball momentum (see evd_fast.cu): x+ = C x / lambda - beta x-
             float lam = 1.f, inv_lam = 1.f, beta = 0.f, rho_prev = -1.f;
             float2 xp = make_float2(0.f, 0.f);
-            int it = 0, buf = 0;
+            int it = 0, buf = 0, next_chk = 3, gap = 4;
             bool conv = false;
             const int kMaxIter = (a.force_generic >> 1) ? (a.force_generic >> 1) : 1000;   // upper bits: timing experiment only
             const float tol2 = 4.0e-12f;
 #pragma unroll 1
             for (; it < kMaxIter; ++it) {
-                float2* xv = s_vec + buf * 32;
+                float* xv = s_vec + buf * 64;
                 buf ^= 1;
-                xv[lane] = x;
+                xv[lane] = x.x; xv[32 + lane] = x.y;
                 __syncwarp();
-                float r0 = 0.f, r1 = 0.f, r2a = 0.f, r3 = 0.f, i0 = 0.f, i1 = 0.f, i2 = 0.f, i3 = 0.f;
-                const float4* xv4 = reinterpret_cast<const float4*>(xv);
+                // y = C x on column pairs with packed FMAs: Re y = sum cr*xr - sum ci*xi,
+                // Im y = sum cr*xi + sum ci*xr; 8 independent accumulator pairs
+                u64 A0 = 0ull, A1 = 0ull, B0 = 0ull, B1 = 0ull, C0 = 0ull, C1 = 0ull, D0 = 0ull, D1 = 0ull;
+                const ulonglong2* xr4 = reinterpret_cast<const ulonglong2*>(xv);
+                const ulonglong2* xi4 = reinterpret_cast<const ulonglong2*>(xv + 32);
 #pragma unroll
-                for (int j = 0; j + 1 < NE; j += 2) {
-                    const float4 q = xv4[j >> 1];
-                    r0 = fmaf(c[j].x, q.x, r0); r1 = fmaf(-c[j].y, q.y, r1);
-                    i0 = fmaf(c[j].x, q.y, i0); i1 = fmaf(c[j].y, q.x, i1);
-                    r2a = fmaf(c[j + 1].x, q.z, r2a); r3 = fmaf(-c[j + 1].y, q.w, r3);
-                    i2 = fmaf(c[j + 1].x, q.w, i2); i3 = fmaf(c[j + 1].y, q.z, i3);
+                for (int k = 0; k + 1 < NP2; k += 2) {
+                    const ulonglong2 qr = xr4[k >> 1], qi = xi4[k >> 1];
+                    A0 = fma2(cr2[k], qr.x, A0); B0 = fma2(ci2[k], qi.x, B0);
+                    C0 = fma2(cr2[k], qi.x, C0); D0 = fma2(ci2[k], qr.x, D0);
+                    A1 = fma2(cr2[k + 1], qr.y, A1); B1 = fma2(ci2[k + 1], qi.y, B1);
+                    C1 = fma2(cr2[k + 1], qi.y, C1); D1 = fma2(ci2[k + 1], qr.y, D1);
                 }
-                const float yr = ((r0 + r1) + (r2a + r3)) * live, yi = ((i0 + i1) + (i2 + i3)) * live;
-                const int ph4 = it & 3;
-                if (ph4 < 2) {
+                if (NP2 & 1) {
+                    const u64 qr = *reinterpret_cast<const u64*>(xv + NE - 2), qi = *reinterpret_cast<const u64*>(xv + 32 + NE - 2);
+                    A0 = fma2(cr2[NP2 - 1], qr, A0); B0 = fma2(ci2[NP2 - 1], qi, B0);
+                    C0 = fma2(cr2[NP2 - 1], qi, C0); D0 = fma2(ci2[NP2 - 1], qr, D0);
+                }
+                float yr, yi;
+                {
+                    const float2 a0 = unpack2(A0), a1 = unpack2(A1), b0 = unpack2(B0), b1 = unpack2(B1);
+                    const float2 c0 = unpack2(C0), c1 = unpack2(C1), d0 = unpack2(D0), d1 = unpack2(D1);
+                    yr = (((a0.x + a0.y) + (a1.x + a1.y)) - ((b0.x + b0.y) + (b1.x + b1.y))) * live;
+                    yi = (((c0.x + c0.y) + (c1.x + c1.y)) + ((d0.x + d0.y) + (d1.x + d1.y))) * live;
+                }
+                if (it < next_chk - 1) {
                     const float2 xn = make_float2(fmaf(-beta, xp.x, yr * inv_lam), fmaf(-beta, xp.y, yi * inv_lam));
                     xp = x; x = xn;
-                } else if (ph4 == 2) {
+                } else if (it == next_chk - 1) {
                     // Rayleigh quotient one iteration ahead of the residual test, so that the two warp
                     // reductions are separate single rounds (the quotient's error is second order in the
                     // residual, one iteration of staleness is far below the tolerance); renormalise here
@@ -409,10 +467,26 @@ __global__ void __launch_bounds__(128, 3) k_evd_mma(const EvdArgs a) {
                         x.x = yr * sc; x.y = yi * sc;
                         ++it; break;
                     }
-                    if (beta == 0.f && rho_prev > 0.f && rho2 < rho_prev) {
-                        const float rr = sqrtf(sqrtf(sqrtf(rho2 * fast_rcp(rho_prev))));   // (rho2 ratio)^(1/8): per-iteration rate
-                        const float hb = 0.475f * rr;
-                        beta = hb * hb;
+                    // Next test where the residual is predicted to reach the tolerance (at least 2
+                    // iterations ahead: the Rayleigh quotient needs the one before).  Observed
+                    // per-iteration decay of the residual over the last gap; when the momentum term is
+                    // switched on, its asymptotic rate r / (1 + sqrt(1 - r^2)) instead.
+                    float rate_l2 = -0.15f;                               // log2 of the expected decay, unknown: ~0.9
+                    if (rho_prev > 0.f && rho2 < rho_prev) {
+                        const float l2 = __log2f(rho2 * fast_rcp(rho_prev)) * (0.5f / (float)gap);   // log2(rate) < 0
+                        rate_l2 = l2;
+                        if (beta == 0.f) {
+                            const float rr = exp2f(l2);
+                            const float hb = 0.475f * rr;
+                            beta = hb * hb;
+                            rate_l2 = __log2f(rr * fast_rcp(1.f + sqrtf(fmaxf(1.f - rr * rr, 0.f))));
+                        }
+                    }
+                    {
+                        const float need = 0.5f * __log2f(tol2 * fast_rcp(rho2));     // log2 of the factor still missing (< 0)
+                        const float m = 1.1f * need * fast_rcp(fminf(rate_l2, -0.01f)) + 0.5f;
+                        gap = (rho_prev > 0.f) ? min(max((int)m, 2), 12) : 4;      // first interval: 4, as the rate estimate wants
+                        next_chk = it + gap;
                     }
                     rho_prev = rho2;
                     const float2 xn = make_float2(fmaf(-beta, xp.x, yr * inv_lam), fmaf(-beta, xp.y, yi * inv_lam));
@@ -425,11 +499,11 @@ __global__ void __launch_bounds__(128, 3) k_evd_mma(const EvdArgs a) {
             if (lam < 1.0e-6f) tc = -7.f;             // evd.cpp:723-727
             else {
                 // ---------------- phase reference (evd.cpp:738-749) -----------------
-                float2* xv = s_vec + buf * 32;
+                float* xv = s_vec + buf * 64;
                 buf ^= 1;
-                xv[lane] = x;
+                xv[lane] = x.x; xv[32 + lane] = x.y;
                 __syncwarp();
-                const float2 ref = xv[k0];
+                const float2 ref = make_float2(xv[k0], xv[32 + k0]);
                 {
                     float ux = x.x * ref.x + x.y * ref.y, uy = x.y * ref.x - x.x * ref.y;
                     const float mm = ux * ux + uy * uy;
@@ -448,23 +522,32 @@ __global__ void __launch_bounds__(128, 3) k_evd_mma(const EvdArgs a) {
                     ci = z.y * o.x - z.x * o.y;
                 }
                 // ---------------- temporal coherence (evd.cpp:770-786) --------------
-                float2* ov = s_vec + buf * 32;
+                float* ov = s_vec + buf * 64;
                 buf ^= 1;
-                ov[lane] = o;
+                ov[lane] = o.x; ov[32 + lane] = o.y;
                 __syncwarp();
                 float wr = 0.f, wi = 0.f;
-                const float4* ov4 = reinterpret_cast<const float4*>(ov);
+                const float2* ovr2 = reinterpret_cast<const float2*>(ov);
+                const float2* ovi2 = reinterpret_cast<const float2*>(ov + 32);
 #pragma unroll
-                for (int j = 0; j < NE; ++j) {
-                    const bool use = (usemask >> j) & 1u;
-                    const float m2 = fmaf(c[j].x, c[j].x, c[j].y * c[j].y);
-                    const float rr = use ? fast_rsqrt(m2) : 0.f;
-                    const float ex = (m2 > 0.f) ? c[j].x * rr : (use ? 1.f : 0.f);
-                    const float ey = (m2 > 0.f) ? c[j].y * rr : 0.f;
-                    const float4 q = ov4[j >> 1];
-                    const float2 oj = (j & 1) ? make_float2(q.z, q.w) : make_float2(q.x, q.y);
-                    wr = fmaf(ex, oj.x, wr); wr = fmaf(-ey, oj.y, wr);
-                    wi = fmaf(ex, oj.y, wi); wi = fmaf(ey, oj.x, wi);
+                for (int k = 0; k < NP2; ++k) {
+                    const float2 vr = unpack2(cr2[k]), vi = unpack2(ci2[k]);
+                    const float2 qr = ovr2[k], qi = ovi2[k];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int j = 2 * k + h;
+                        const float cx = h ? vr.y : vr.x, cy = h ? vi.y : vi.x;
+                        const float ojx = h ? qr.y : qr.x, ojy = h ? qi.y : qi.x;
+                        // pairs (lane, j) with j > lane, inside the matrix and (STBAS) the band;
+                        // e = C_ij / |C_ij| (arg(0) = 0 as in the reference)
+                        const bool use = (usemask >> j) & 1u;
+                        const float m2 = fmaf(cx, cx, cy * cy);
+                        const float rr = use ? fast_rsqrt(m2) : 0.f;
+                        const float ex = (m2 > 0.f) ? cx * rr : (use ? 1.f : 0.f);
+                        const float ey = (m2 > 0.f) ? cy * rr : 0.f;
+                        wr = fmaf(ex, ojx, wr); wr = fmaf(-ey, ojy, wr);
+                        wi = fmaf(ex, ojy, wi); wi = fmaf(ey, ojx, wi);
+                    }
                 }
                 float sr = o.x * wr + o.y * wi, si = o.x * wi - o.y * wr;      // conj(o_r) * w_r
 #pragma unroll
