@@ -16,8 +16,7 @@
 //               and the B fragments of the second product are the first one's with the two
 //               registers swapped and one sign flipped.  Only the 6 of 8 16x8 tiles that touch the
 //               upper triangle are computed: 12 accumulator tiles (48 registers) x 3 products
-//               (hi*hi + hi*lo + lo*hi) = 36 mma.sync per 4 SHPs.  The next chunk's operands are
-//               loaded while the current chunk is multiplied.
+//               (hi*hi + hi*lo + lo*hi) = 36 mma.sync per 4 SHPs.
 //   hand-off    accumulator fragments -> coherence -> one full Hermitian matrix in shared memory.
 //   eigen, epilogue: as in evd_fast.cu (lane = row, vector broadcast from shared memory,
 //               heavy-ball momentum, phase reference / compressed SLC / temporal coherence).
@@ -117,7 +116,8 @@ __device__ __forceinline__ void mma_chunk(float (&cre)[6][4], float (&cim)[6][4]
 
 template <int NE>
 struct MmaCfg {
-    static constexpr int WARPS = 4;
+    static constexpr int WARPS = 16;                    // one CTA per SM: its warps share one moving window in L1
+    static constexpr int BAND = 4;                      // rows of a CTA's pixel band
     // coherence matrix in shared memory: real and imaginary planes, rows NS floats apart;
     // NS = 4 (mod 8) keeps rows 16-byte aligned and spreads the hand-off stores over the banks
     static constexpr int NS = ((NE + 3) / 4 * 4) % 8 == 4 ? (NE + 3) / 4 * 4 : (NE + 3) / 4 * 4 + 4;
@@ -186,7 +186,7 @@ cudaError_t launch_transpose_mma(const float2* slc, long npix, long first, long 
 
 // ---------------------------------------------------------------------------------------
 template <int NE>
-__global__ void __launch_bounds__(128, 3) k_evd_mma(const EvdArgs a) {
+__global__ void __launch_bounds__(512, 1) k_evd_mma(const EvdArgs a) {
     typedef MmaCfg<NE> Cfg;
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -229,30 +229,49 @@ __global__ void __launch_bounds__(128, 3) k_evd_mma(const EvdArgs a) {
     const long npix_block = (long)a.cols * a.lines;
     const float* zf = reinterpret_cast<const float*>(a.zpix);
 
-    const long total = (long)a.n_lines * a.cols;
-    const long chunk = (total + gridDim.x - 1) / gridDim.x;
-    const long beg = (long)blockIdx.x * chunk;
-    const long end = min(total, beg + chunk);
+    // Work: the CTA owns a band of BAND rows x a segment of columns and its warps draw pixels from
+    // a shared counter in column-major order inside the band (k -> row k % rows, column k / rows).
+    // All 16 warps therefore sit inside a ~4 x 4 pixel patch that slides along the band: the union
+    // of their windows (~14 x 8 samples, 57 kB) stays in L1 and every new column of samples is
+    // fetched once per band instead of once per row.
+    __shared__ int s_next;
+    if (threadIdx.x == 0) s_next = 0;
+    __syncthreads();
+    const int nbands = (a.n_lines + Cfg::BAND - 1) / Cfg::BAND;
+    const int band = blockIdx.x % nbands, seg = blockIdx.x / nbands;
+    const int seglen = a.tile_pairs;                          // columns per segment (set by the launcher)
+    const int c0 = seg * seglen, c1 = min(a.cols, c0 + seglen);
+    const int row0 = a.first_line + band * Cfg::BAND;
+    const int rows = min(Cfg::BAND, a.first_line + a.n_lines - row0);
+    const int total = (c1 - c0) * rows;
     unsigned long long st_pix = 0, st_it = 0, st_cap = 0;
     PHASE_DECL
 
+    auto draw = [&]() -> int {
+        int k = 0;
+        if (lane == 0) k = atomicAdd(&s_next, 1);
+        return __shfl_sync(FULLMASK, k, 0);
+    };
     const bool in_regs = a.nulong <= 32;
-    auto load_mask_word = [&](long px) -> uint32_t {          // lane w keeps word w of the pixel's mask
-        if (px >= end || lane >= a.nulong) return 0u;
-        const long pp = (long)a.first_line * a.cols + px;
+    auto load_mask_word = [&](int k) -> uint32_t {            // lane w keeps word w of the pixel's mask
+        if (k >= total || lane >= a.nulong) return 0u;
+        const long pp = (long)(row0 + k % rows) * a.cols + c0 + k / rows;
         return __ldg(&a.wts[pp * a.nulong + lane]);
     };
-    uint32_t mw_next = load_mask_word(beg + warp);
+    int k_next = draw();
+    uint32_t mw_next = load_mask_word(k_next);
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int zero_idx = (int)npix_block;         // index of the all-zero sample vector
 
 #pragma unroll 1
-    for (long px = beg + warp; px < end; px += Cfg::WARPS) {
-        const int row = a.first_line + (int)(px / a.cols);
-        const int col = (int)(px % a.cols);
+    while (k_next < total) {
+        const int k = k_next;
+        const int row = row0 + k % rows;
+        const int col = c0 + k / rows;
         const long pg = (long)row * a.cols + col;
         const uint32_t mw = mw_next;
-        mw_next = load_mask_word(px + Cfg::WARPS);
+        k_next = draw();
+        mw_next = load_mask_word(k_next);
         auto mask_word = [&](int w) -> uint32_t {               // w warp-uniform
             if (w >= a.nulong) return 0u;
             return in_regs ? __shfl_sync(FULLMASK, mw, w) : __ldg(&a.wts[pg * a.nulong + w]);
@@ -286,17 +305,17 @@ __global__ void __launch_bounds__(128, 3) k_evd_mma(const EvdArgs a) {
             if (lane < 4 && n + lane < 4 * chunks) s_list[n + lane] = zero_idx;
             __syncwarp();
             PHASE_MARK(0)
-            MmaOperands opA, opB;
-            if (chunks > 0) opA.load(zf + (long)s_list[t] * 128, g);
-            int c = 0;
+            // no register double buffering of the operands: at 126 registers four CTAs fit per SM and
+            // the other 15 warps cover the load latency (measured equal to the prefetching version at
+            // 166 registers / 3 CTAs); only the next list entry is fetched ahead
+            MmaOperands op;
+            int idx = s_list[t];
 #pragma unroll 1
-            for (; c + 2 <= chunks; c += 2) {                  // chunk c+1 loads while chunk c multiplies, and so on
-                opB.load(zf + (long)s_list[4 * (c + 1) + t] * 128, g);
-                mma_chunk(cre, cim, opA);
-                opA.load(zf + (long)s_list[4 * min(c + 2, chunks - 1) + t] * 128, g);
-                mma_chunk(cre, cim, opB);
+            for (int c = 0; c < chunks; ++c) {
+                op.load(zf + (long)idx * 128, g);
+                idx = s_list[4 * min(c + 1, chunks - 1) + t];
+                mma_chunk(cre, cim, op);
             }
-            if (c < chunks) mma_chunk(cre, cim, opA);          // odd count: the last chunk is already in opA
             PHASE_MARK(1)
         }
         const bool solve = center_on && (npix >= 2);         // evd.cpp:566 hard-codes 2
@@ -582,19 +601,23 @@ static cudaError_t launch_mma_t(const EvdArgs& a, cudaStream_t st) {
     const size_t smem = lut + (size_t)Cfg::SMEM_PER_WARP * Cfg::WARPS;
     cudaError_t e = cudaFuncSetAttribute(k_evd_mma<NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    int dev = 0, nsm = 148, occ = 1;
+    int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_evd_mma<NE>, Cfg::WARPS * 32, smem);
-    if (occ < 1) occ = 1;
-    const long total = (long)a.n_lines * a.cols;
-    int mult = 8;
+    // bands of BAND rows x column segments; segments as long as possible (less halo re-reading at
+    // their ends) while there are still >= mult CTAs per SM to even out the tail (one CTA per SM at a
+    // time: 8 per SM lost 8 % to the last partial wave, 48 and 96 measured equal)
+    int mult = 48;
     if (const char* ev = getenv("FRINGE_EVD_CHUNKS")) { const int v = atoi(ev); if (v > 0) mult = v; }
-    long grid = (long)nsm * occ * mult;
-    const long maxgrid = (total + Cfg::WARPS * 8 - 1) / (Cfg::WARPS * 8);
-    if (grid > maxgrid) grid = maxgrid;
-    if (grid < 1) grid = 1;
-    k_evd_mma<NE><<<(unsigned)grid, Cfg::WARPS * 32, smem, st>>>(a);
+    const int nbands = (a.n_lines + Cfg::BAND - 1) / Cfg::BAND;
+    int nseg = (nsm * mult + nbands - 1) / nbands;
+    if (nseg < 1) nseg = 1;
+    int seglen = (a.cols + nseg - 1) / nseg;
+    if (seglen < 32) seglen = 32;
+    nseg = (a.cols + seglen - 1) / seglen;
+    EvdArgs b = a;
+    b.tile_pairs = seglen;
+    k_evd_mma<NE><<<(unsigned)(nbands * nseg), Cfg::WARPS * 32, smem, st>>>(b);
     return cudaGetLastError();
 }
 
