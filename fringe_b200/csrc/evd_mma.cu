@@ -394,12 +394,14 @@ __global__ void __launch_bounds__(512, 1) k_evd_mma(const EvdArgs a) {
                     cr2[k] = pack2(vr.x, vr.y); ci2[k] = pack2(vi.x, vi.y);
                 }
             }
-            // start vector: column k0 of C reduced to unit modulus (the dominant eigenvector of a
-            // coherence matrix has nearly uniform magnitudes)
+            // start vector: the middle column of C reduced to unit modulus (the dominant eigenvector of
+            // a coherence matrix has nearly uniform magnitudes, and the middle date is the one most
+            // coherent with all others: half an iteration fewer than the first column in the replay)
             float2 x;
             {
-                const float2 v = make_float2(s_re[k0 * NS + r], s_im[k0 * NS + r]);
-                const float keep = (isstbas && abs(k0 - lane) > BW) ? 0.f : live;
+                const int ks = N >> 1;
+                const float2 v = make_float2(s_re[ks * NS + r], s_im[ks * NS + r]);
+                const float keep = (isstbas && abs(ks - lane) > BW) ? 0.f : live;
                 x = make_float2(v.x * keep, -v.y * keep);
                 const float m2 = x.x * x.x + x.y * x.y;
                 const float rs = (m2 > 0.f) ? fast_rsqrt(m2) : 0.f;
