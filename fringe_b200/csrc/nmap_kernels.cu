@@ -54,8 +54,8 @@ __global__ void __launch_bounds__(128) k_amp_sort(const float2* __restrict__ slc
         if (isinf(z.x) || isinf(z.y)) h = CUDART_INF_F;
         else h = (float)__dsqrt_rn(__dadd_rn(__dmul_rn((double)z.x, (double)z.x),
                                              __dmul_rn((double)z.y, (double)z.y)));
-        const double al = alpha ? alpha[b] : 1.0;
-        const float v = (float)__ddiv_rn((double)h, al);
+        // no calibration constants: (float)((double)h / 1.0) == h, skip the double division
+        const float v = alpha ? (float)__ddiv_rn((double)h, alpha[b]) : h;
         ok = ok && (v != 0.f) && !isnan(v);
         s_col[b * nt + tid] = v;
     }
