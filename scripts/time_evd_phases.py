@@ -33,7 +33,7 @@ for cap in (sys.argv[1:] or ["1", "5", "9", "0"]):
         torch.cuda.synchronize()
         ts.append(ctx.last_kernel_ms("evd"))
     st = ctx.evd_stats()
-    print("cap", cap, "evd ms", min(ts), "its/pixel", st["power_iterations"] / max(st["pixels"], 1), flush=True)
+    print("cap", cap, "evd ms", min(ts), "its/pixel", st["power_iterations"] / max(st["pixels"], 1), "capped", st["capped"], flush=True)
     import ctypes as C
     from fringe_b200._lib import lib
     cyc = (C.c_int64 * 8)()

