@@ -238,18 +238,26 @@ def main():
         except Exception:
             pass
     evd_bytes = my_pixels * (16 * BANDS + 4 * nu + 12)
-    roofline = {"kernel": "k_evd (covariance + dominant eigenvector + phase ref + tcorr + compressed SLC)",
+    # ncu --set full on a 100-line launch of the same kernel (profiles/r1_evd_mma_ncu_summary.txt):
+    # dram__bytes_read + dram__bytes_write = 2.02 GB for 2.0 M pixels -> 1012 B/pixel, scaled to this launch
+    traffic = 1012.0 * my_pixels
+    roofline = {"kernel": "k_evd_mma (masked Gram product on 3xTF32 mma.sync + FP32 dominant eigenvector + "
+                          "phase ref + tcorr + compressed SLC)",
                 "bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak if peak > 0 else None,
                 "peak_source": "FP32 FMA microbenchmark run inside this bench (fringe_fp32_peak); "
-                               "MEASURED_PEAKS.json has no FP32 figure",
+                               "MEASURED_PEAKS.json has no FP32 figure.  Algorithmic flops (SURVEY 8d) over "
+                               "the FP32 peak, although the Gram product itself runs on the tensor pipe",
                 "kernel_ms": k_ms, "algorithmic_flops_per_launch": fl,
                 "mean_shp": shp_sum / max(solved, 1), "solved_pixels": solved,
                 "hbm_view": {"achieved_gbs": evd_bytes / (k_ms * 1e-3) * 1e-9, "peak_gbs": hbm_peak,
                              "peak_source": hbm_src, "algorithmic_bytes_per_pixel": 16 * BANDS + 4 * nu + 12},
                 "nmap_kernel_ms": float(np.mean(nmap_ms)),
                 "power_iterations_per_pixel": stats["power_iterations"] / max(stats["pixels"], 1),
-                "traffic": None}
+                "traffic": traffic,
+                "traffic_note": "DRAM bytes per launch, 1012 B/pixel from the ncu capture of a 100-line launch "
+                                "(algorithmic 500 B/pixel; the excess is the 512 B/pixel hi/lo sample layout read "
+                                "through L2)"}
 
     # ---- end to end through the host C ABI --------------------------------------------------
     e2e = None
