@@ -29,6 +29,19 @@
 
 namespace fringe {
 
+// profiling build only (-DFRINGE_PHASE_CLOCKS): per-phase warp cycles into stats[4..] -- for this
+// kernel [0] covariance, [1] coherence + gate 1, [2] |C| gate + inverse, [3] smallest eigenpair,
+// [4] power iteration (EVD / fallback), [5] post-processing
+#ifdef FRINGE_PHASE_CLOCKS
+#define GPH_DECL long long gph_t = clock64(); unsigned long long gph[6] = {0, 0, 0, 0, 0, 0};
+#define GPH_MARK(k) { const long long gph_n = clock64(); gph[k] += (unsigned long long)(gph_n - gph_t); gph_t = gph_n; }
+#define GPH_FLUSH if (a.stats && lane == 0) { for (int k = 0; k < 6; ++k) atomicAdd(&a.stats[4 + k], gph[k]); }
+#else
+#define GPH_DECL
+#define GPH_MARK(k)
+#define GPH_FLUSH
+#endif
+
 // ======================================================================================
 // re-layout: [bands][npix] -> [npix][NP]
 // ======================================================================================
@@ -369,6 +382,108 @@ __device__ float power_iteration(const WarpSmem& w, int n, int ldc, int lane, in
     return lam;
 }
 
+// Dominant eigenpair of the FP64 coherence matrix w.Cd by power iteration with heavy-ball
+// momentum (same switch-on rule as k_evd_mma, see scripts/sim_power_iteration.py), everything in
+// double: the cheap route for phase_link's EVD fallback (phase_link.cpp:586-600).  v[] holds the
+// start vector on entry and the unit eigenvector on success; false = not converged to a 1e-9
+// relative residual within the cap (the caller then runs the certified inverse iteration).
+template <int HR>
+__device__ bool power_iteration_dp(const WarpSmem& w, int n, int ld, int lane, double2 (&v)[HR],
+                                   double* lam_out) {
+    double2 x[HR], xp[HR];
+    double nrm = 0.0;
+#pragma unroll
+    for (int h = 0; h < HR; ++h) { x[h] = v[h]; xp[h] = make_double2(0.0, 0.0); nrm += x[h].x * x[h].x + x[h].y * x[h].y; }
+    nrm = warp_sum(nrm);
+    if (!(nrm > 0.0)) return false;
+    double sc = 1.0 / sqrt(nrm);
+#pragma unroll
+    for (int h = 0; h < HR; ++h) { x[h].x *= sc; x[h].y *= sc; }
+    double lam = 1.0, beta = 0.0, rho_prev = -1.0;
+    int next_chk = 2, gap = 2;
+    for (int it = 0; it < 400; ++it) {
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < HR; ++h) { const int i = lane + 32 * h; if (i < n) w.xd[i] = x[h]; }
+        __syncwarp();
+        double2 y[HR];
+#pragma unroll
+        for (int h = 0; h < HR; ++h) {
+            const int i = lane + 32 * h;
+            double yr = 0.0, yi = 0.0;
+            if (i < n) {
+                const double2* row = w.Cd + i * ld;
+                for (int j = 0; j < n; ++j) {
+                    const double2 c = row[j];
+                    const double2 xj = w.xd[j];
+                    yr += c.x * xj.x - c.y * xj.y;
+                    yi += c.x * xj.y + c.y * xj.x;
+                }
+            }
+            y[h] = make_double2(yr, yi);
+        }
+        if (it == next_chk) {
+            double xy = 0.0, xx = 0.0;
+#pragma unroll
+            for (int h = 0; h < HR; ++h) { xy += x[h].x * y[h].x + x[h].y * y[h].y; xx += x[h].x * x[h].x + x[h].y * x[h].y; }
+            xy = warp_sum(xy); xx = warp_sum(xx);
+            lam = xy / xx;
+            double r2 = 0.0, y2 = 0.0;
+#pragma unroll
+            for (int h = 0; h < HR; ++h) {
+                const double rx = y[h].x - lam * x[h].x, ry = y[h].y - lam * x[h].y;
+                r2 += rx * rx + ry * ry;
+                y2 += y[h].x * y[h].x + y[h].y * y[h].y;
+            }
+            r2 = warp_sum(r2); y2 = warp_sum(y2);
+            const double rho2 = r2 / (lam * lam * xx);
+            if (rho2 <= 1.0e-18) {                                     // one more plain step, then done
+                sc = 1.0 / sqrt(y2);
+#pragma unroll
+                for (int h = 0; h < HR; ++h) v[h] = make_double2(y[h].x * sc, y[h].y * sc);
+                *lam_out = lam;
+                return true;
+            }
+            if (rho_prev > 0.0 && rho2 < rho_prev) {
+                if (beta == 0.0) {
+                    const double rr = pow(rho2 / rho_prev, 0.5 / (double)gap);
+                    beta = fmin(0.575 * rr * 0.575 * rr, 0.2);
+                }
+            } else if (rho_prev > 0.0) beta *= 0.5;
+            rho_prev = rho2;
+            next_chk = it + gap;
+            // renormalise the pair (x, x-) and step
+            sc = 1.0 / sqrt(xx);
+            const double il = 1.0 / lam;
+#pragma unroll
+            for (int h = 0; h < HR; ++h) {
+                const double2 xn = make_double2((y[h].x * il - beta * xp[h].x) * sc, (y[h].y * il - beta * xp[h].y) * sc);
+                xp[h] = make_double2(x[h].x * sc, x[h].y * sc);
+                x[h] = xn;
+            }
+        } else {
+            const double il = 1.0 / lam;
+            if (it < 2) {                                                // lambda still unknown: plain normalised steps
+                double y2 = 0.0;
+#pragma unroll
+                for (int h = 0; h < HR; ++h) y2 += y[h].x * y[h].x + y[h].y * y[h].y;
+                y2 = warp_sum(y2);
+                sc = 1.0 / sqrt(y2);
+#pragma unroll
+                for (int h = 0; h < HR; ++h) { xp[h] = make_double2(0.0, 0.0); x[h] = make_double2(y[h].x * sc, y[h].y * sc); }
+            } else {
+#pragma unroll
+                for (int h = 0; h < HR; ++h) {
+                    const double2 xn = make_double2(y[h].x * il - beta * xp[h].x, y[h].y * il - beta * xp[h].y);
+                    xp[h] = x[h];
+                    x[h] = xn;
+                }
+            }
+        }
+    }
+    return false;
+}
+
 // Smallest eigenpair of the Hermitian PSD matrix M = Ainv o C (Ainv real symmetric in w.A,
 // C FP64 in w.Cd) by inverse iteration with Cholesky-certified shifts.  Returns false when no
 // positive-definite shifted matrix could be factored (caller maps that to the sentinel / the
@@ -526,6 +641,7 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
     const long beg = (long)blockIdx.x * chunk;
     const long end = min(total, beg + chunk);
     unsigned long long st_pix = 0, st_it = 0, st_dp = 0, st_cap = 0;
+    GPH_DECL
 
     for (long i = beg + warp; i < end; i += WARPS) {
         const long p = (long)a.first_line * a.cols + i;
@@ -614,6 +730,7 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
                     else w.C[ti * ldc + tj] = make_float2((float)acc[s].x, (float)acc[s].y);
                 }
             }
+            GPH_MARK(0)
             if (npix >= need) {
                 // ---------------- coherence matrix (evd.cpp:569-582) -------------------
                 if (DP) { for (int h = 0; h < HR; ++h) { const int t = lane + 32 * h; if (t < N) w.dinv[t] = pwd[h]; } }
@@ -660,6 +777,7 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
                         __syncwarp();
                         if (!chol_c<HR>(w.F, w.dinv, N, ld, lane)) { tc = -2.f; failed = true; }
                     }
+                    GPH_MARK(1)
                     // ---- |C| and its inverse -------------------------------------------
                     if (!failed) {
                         auto fill_abs = [&](double dshift) {
@@ -683,6 +801,7 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
                                 else run_evd = true;
                             } else {
                                 chol_inverse_r<HR>(w.A, reinterpret_cast<double*>(w.F), w.dinv, N, ld, lane);
+                                GPH_MARK(2)
                                 double2 vd[HR];
                                 double lam = 0.0;
                                 if (!smallest_eigen_mle<0, HR>(w, N, ldc, ld, lane, vd, &lam)) {
@@ -707,6 +826,7 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
                         }
                     }
                 }
+                GPH_MARK(3)
                 if (run_evd && !failed) {
                     // ---------------- EVD / STBAS (evd.cpp:689-732) --------------------
                     if (isstbas && a.variant == 0) {
@@ -727,7 +847,16 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
                             vd[h] = (r < N) ? w.Cd[r * ld + k0] : make_double2(0.0, 0.0);
                         }
                         double lamd = 0.0;
-                        if (smallest_eigen_mle<1, HR>(w, N, ldc, ld, lane, vd, &lamd)) {
+                        bool got = power_iteration_dp<HR>(w, N, ld, lane, vd, &lamd);
+                        if (!got) {                         // slow or stalled: certified inverse iteration instead
+                            for (int h = 0; h < HR; ++h) {
+                                const int r = lane + 32 * h;
+                                vd[h] = (r < N) ? w.Cd[r * ld + k0] : make_double2(0.0, 0.0);
+                            }
+                            got = smallest_eigen_mle<1, HR>(w, N, ldc, ld, lane, vd, &lamd);
+                            ++st_cap;
+                        }
+                        if (got) {
                             __syncwarp();
                             for (int h = 0; h < HR; ++h) { const int r = lane + 32 * h; if (r < N) w.xd[r] = vd[h]; }
                             __syncwarp();
@@ -751,6 +880,7 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
                         else have_vec = true;
                     }
                 }
+                GPH_MARK(4)
             }
         }
 
@@ -818,7 +948,9 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
             if (r < N) a.out[(long)r * npix_block + p] = o[h];
         }
         if (lane == 0) { a.tcorr[p] = tc; a.comp[p] = cmp; }
+        GPH_MARK(5)
     }
+    GPH_FLUSH
     if (a.stats) {
         if (lane == 0) {
             atomicAdd(&a.stats[0], st_pix);
