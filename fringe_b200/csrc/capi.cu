@@ -706,6 +706,61 @@ int fringe_nmap_evd_block(fringe_ctx* ctx, const float* slc, const uint8_t* mask
     return FRINGE_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// datum adjustment (python/adjustMiniStacks.py:180-199): out = a * b, complex64
+// ---------------------------------------------------------------------------------------
+int fringe_cmul_device(fringe_ctx* ctx, const float* a, const float* b, int64_t n, float* out, void* stream) {
+    if (!ctx) return FRINGE_ERR_ARGUMENT;
+    if (n < 0 || (n > 0 && (!a || !b || !out))) return fail(ctx, FRINGE_ERR_ARGUMENT, "null pointer or negative size");
+    if ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15) != 0) return fail(ctx, FRINGE_ERR_ARGUMENT, "pointers must be 16-byte aligned");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_CMUL][0], st));
+    CU(fringe::launch_cmul((const float2*)a, (const float2*)b, (float2*)out, (long)n, st));
+    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_CMUL][1], st));
+    ctx->ev_valid[FRINGE_KERNEL_CMUL] = true;
+    ctx->launches += (n > 0) ? 1 : 0;
+    return FRINGE_OK;
+}
+
+// Host variant: pieces of ~128 MB per operand flow through upload -> multiply -> download.
+int fringe_cmul(fringe_ctx* ctx, const float* a, const float* b, int64_t n, float* out) {
+    if (!ctx) return FRINGE_ERR_ARGUMENT;
+    if (n < 0 || (n > 0 && (!a || !b || !out))) return fail(ctx, FRINGE_ERR_ARGUMENT, "null pointer or negative size");
+    if (n == 0) return FRINGE_OK;
+    CU(cudaSetDevice(ctx->device));
+    const size_t piece = (size_t)16 << 20;                       // pixels per piece (even)
+    const size_t nbuf = (std::min((size_t)n, 2 * piece) + 1) & ~(size_t)1;    // even: keeps the b half 16-byte aligned
+    CU(ctx->in_slc.ensure(2 * nbuf * sizeof(float2)));            // a | b, double buffered halves
+    CU(ctx->o_out.ensure(nbuf * sizeof(float2)));
+    cudaStream_t st = ctx->stream;
+    size_t ev = 0;
+    int slot = 0;
+    std::vector<cudaEvent_t> freed(2, nullptr);
+    for (size_t off = 0; off < (size_t)n; off += piece, slot ^= 1) {
+        const size_t cnt = std::min(piece, (size_t)n - off);
+        float2* da = (float2*)ctx->in_slc.p + (size_t)slot * piece;
+        float2* db = (float2*)ctx->in_slc.p + nbuf + (size_t)slot * piece;
+        float2* dout = (float2*)ctx->o_out.p + (size_t)slot * piece;
+        if (freed[slot]) CU(cudaStreamWaitEvent(ctx->s_in, freed[slot], 0));     // slot's previous download done
+        CU(cudaMemcpyAsync(da, (const float2*)a + off, cnt * sizeof(float2), cudaMemcpyHostToDevice, ctx->s_in));
+        CU(cudaMemcpyAsync(db, (const float2*)b + off, cnt * sizeof(float2), cudaMemcpyHostToDevice, ctx->s_in));
+        cudaEvent_t e_in = ctx->pool_event(ev++), e_done = ctx->pool_event(ev++), e_out = ctx->pool_event(ev++);
+        CU(cudaEventRecord(e_in, ctx->s_in));
+        CU(cudaStreamWaitEvent(st, e_in, 0));
+        int rc = fringe_cmul_device(ctx, (const float*)da, (const float*)db, (int64_t)cnt, (float*)dout, st);
+        if (rc) return rc;
+        CU(cudaEventRecord(e_done, st));
+        CU(cudaStreamWaitEvent(ctx->s_out, e_done, 0));
+        CU(cudaMemcpyAsync((float2*)out + off, dout, cnt * sizeof(float2), cudaMemcpyDeviceToHost, ctx->s_out));
+        CU(cudaEventRecord(e_out, ctx->s_out));
+        freed[slot] = e_out;
+    }
+    CU(cudaStreamSynchronize(ctx->s_out));
+    CU(cudaStreamSynchronize(st));
+    return FRINGE_OK;
+}
+
 int fringe_last_kernel_ms(fringe_ctx* ctx, int kernel, float* ms) {
     if (!ctx || !ms || kernel < 0 || kernel >= FRINGE_KERNEL_COUNT) return FRINGE_ERR_ARGUMENT;
     if (!ctx->ev_valid[kernel]) return fail(ctx, FRINGE_ERR_ARGUMENT, "kernel has not been launched on this context");

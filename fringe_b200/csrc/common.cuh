@@ -79,6 +79,9 @@ cudaError_t launch_transpose_mma(const float2* slc, long npix, long first, long 
                                  cudaStream_t st);
 cudaError_t launch_evd_mma(const EvdArgs& a, cudaStream_t st);
 
+// out[i] = a[i] * b[i] (complex64, double arithmetic inside), n pixels; 16-byte aligned pointers
+cudaError_t launch_cmul(const float2* a, const float2* b, float2* out, long n, cudaStream_t st);
+
 // ---- microbench.cu --------------------------------------------------------------------
 cudaError_t measure_fp32_peak(cudaStream_t st, double* tflops);
 // register-resident 6x6 complex block update (144 FMAs per step, 3 CTAs/SM like the evd kernel):

@@ -163,8 +163,6 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
     const long beg = (long)blockIdx.x * chunk;
     const long end = min(total_pairs, beg + chunk);
     unsigned long long st_pix = 0, st_it = 0, st_cap = 0;
-    float2 xwarm = make_float2(0.f, 0.f);       // last converged eigenvector of this warp (warm start)
-    bool have_warm = false;
     PHASE_DECL
 
 #pragma unroll 1
@@ -308,13 +306,13 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
                     for (int j = 0; j < NPAD; ++j)
                         if (abs(j - lane) > BW) c[j] = make_float2(0.f, 0.f);
                 }
-                // start vector: the eigenvector of the previous pixel this warp solved (its window
-                // overlaps this one almost completely), else column k0 of C
+                // start vector: column k0 of C (warm-starting from the previous pixel's eigenvector was
+                // measured at -3 % but makes results depend on the block schedule at the 1e-7 level)
                 float2 x;
                 {
                     const float2 v = s_mat[g * Cfg::MAT + k0 * NPAD + r];
                     const float keep = (isstbas && abs(k0 - lane) > BW) ? 0.f : live;
-                    x = have_warm ? xwarm : make_float2(v.x * keep, -v.y * keep);
+                    x = make_float2(v.x * keep, -v.y * keep);
                     {   // unit-modulus start: the dominant eigenvector of a coherence matrix has nearly uniform magnitudes
                         const float m2 = x.x * x.x + x.y * x.y;
                         const float rs = (m2 > 0.f) ? fast_rsqrt(m2) : 0.f;
@@ -404,7 +402,6 @@ __global__ void __launch_bounds__(128, 3) k_evd_fast(const EvdArgs a) {
                 PHASE_MARK(4)
                 st_it += it;
                 st_cap += conv ? 0 : 1;
-                xwarm = x; have_warm = false && conv;   // warm start disabled: it makes results depend on the block schedule at the 1e-7 level
                 if (lam < 1.0e-6f) tc = -7.f;             // evd.cpp:723-727
                 else {
                     // ---------------- phase reference (evd.cpp:738-749) -----------------

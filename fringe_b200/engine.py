@@ -100,7 +100,7 @@ class Context:
         self._check(lib.fringe_evd_stats(self._h, arr))
         return {"pixels": arr[0], "power_iterations": arr[1], "fp64_pixels": arr[2], "capped": arr[3]}
 
-    KERNELS = {"amp_sort": 0, "nmap": 1, "transpose": 2, "evd": 3}
+    KERNELS = {"amp_sort": 0, "nmap": 1, "transpose": 2, "evd": 3, "cmul": 4}
 
     def last_kernel_ms(self, kernel: str) -> float:
         ms = C.c_float(0)
@@ -181,6 +181,25 @@ class Context:
             int(min_neighbors), count.ctypes.data if want_mask else None,
             wts.ctypes.data if want_mask else None, out.ctypes.data, tcorr.ctypes.data, comp.ctypes.data))
         return count, wts, out, tcorr, comp
+
+    def cmul(self, a, b):
+        """Datum adjustment product a * b of two complex64 rasters (``fringe_cmul``)."""
+        a = np.ascontiguousarray(a, np.complex64)
+        b = np.ascontiguousarray(b, np.complex64)
+        if a.shape != b.shape:
+            raise ValueError("shape mismatch")
+        out = np.empty_like(a)
+        self._check(lib.fringe_cmul(self._h, a.ctypes.data, b.ctypes.data, a.size, out.ctypes.data))
+        return out
+
+    def cmul_device(self, a, b, out=None):
+        import torch
+        assert a.is_cuda and b.is_cuda and a.dtype == torch.complex64 and b.dtype == torch.complex64
+        assert a.is_contiguous() and b.is_contiguous() and a.shape == b.shape
+        if out is None:
+            out = torch.empty_like(a)
+        self._check(lib.fringe_cmul_device(self._h, a.data_ptr(), b.data_ptr(), a.numel(), out.data_ptr(), self._stream()))
+        return out
 
     # ---- device tensors (torch) ------------------------------------------------------------
     @staticmethod

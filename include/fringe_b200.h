@@ -140,6 +140,17 @@ int fringe_nmap_evd_block(fringe_ctx* ctx, const float* slc, const uint8_t* mask
                           int mini_stack_count, int variant, int min_neighbors, int32_t* count,
                           uint32_t* wts, float* out, float* tcorr, float* comp);
 
+/* ---- datum adjustment of the sequential estimator ----------------------------------------
+ * out[i] = a[i] * b[i] on n complex64 pixels: the wrapped time series
+ * adjusted(date) = ministack phasor(date) * datum phasor(ministack), which
+ * python/adjustMiniStacks.py:180-199 delegates to GDAL's "mul" VRT pixel function (complex product
+ * evaluated in double, stored as CFloat32 -- the arithmetic reproduced here).  `a`, `b`, `out` may
+ * alias.  Host variant: host pointers (pinned preferred), returns when `out` is filled.  Device
+ * variant: 16-byte aligned device pointers, work queued on `stream`. */
+int fringe_cmul(fringe_ctx* ctx, const float* a, const float* b, int64_t n, float* out);
+int fringe_cmul_device(fringe_ctx* ctx, const float* a, const float* b, int64_t n, float* out,
+                       void* stream);
+
 /* Largest `bands` the evd kernels accept for the given method. */
 int fringe_evd_max_bands(int method, int variant);
 
@@ -151,7 +162,8 @@ enum {
     FRINGE_KERNEL_NMAP = 1,       /* window pair tests */
     FRINGE_KERNEL_TRANSPOSE = 2,  /* band-major -> pixel-major re-layout */
     FRINGE_KERNEL_EVD = 3,        /* covariance + eigen + post-processing */
-    FRINGE_KERNEL_COUNT = 4
+    FRINGE_KERNEL_CMUL = 4,       /* datum adjustment product */
+    FRINGE_KERNEL_COUNT = 5
 };
 int fringe_last_kernel_ms(fringe_ctx* ctx, int kernel, float* ms);
 /* FP32 FMA throughput of the device measured with a register-resident FMA loop; the roofline

@@ -72,6 +72,8 @@ class Oracle:
         lib.oracle_pd_inverse.argtypes = [dp, C.c_int]
         lib.oracle_nmap_block.argtypes = [fp, u8, dp] + [C.c_int] * 6 + [C.c_double, i32, u32, fp]
         lib.oracle_evd_block.argtypes = [fp, u32] + [C.c_int] * 12 + [fp, fp, fp, i32]
+        lib.oracle_cmul.argtypes = [fp, fp, C.c_long, fp]
+        lib.oracle_cmul.restype = None
         self.kind = lib.oracle_kind().decode()
 
     # -- helpers -------------------------------------------------------------------
@@ -172,6 +174,15 @@ class Oracle:
         if rc != 0:
             raise RuntimeError(f"oracle_evd_block rc={rc}")
         return (out, tcorr, comp, npix) if want_npix else (out, tcorr, comp)
+
+    def cmul(self, a, b):
+        """Datum adjustment product a * b (complex64 in, double arithmetic, complex64 out)."""
+        a = np.ascontiguousarray(a, np.complex64)
+        b = np.ascontiguousarray(b, np.complex64)
+        out = np.empty_like(a)
+        self.lib.oracle_cmul(self._p(a.view(np.float32), C.c_float), self._p(b.view(np.float32), C.c_float),
+                             a.size, self._p(out.view(np.float32), C.c_float))
+        return out
 
 
 _CACHE: dict[str, Oracle] = {}

@@ -100,4 +100,20 @@ int oracle_evd_block(const float* slc, const uint32_t* wts, int cols, int lines,
                                    reinterpret_cast<oracle::cfloat*>(comp), npix);
 }
 
+// Datum adjustment product (python/adjustMiniStacks.py:180-199): the reference writes a VRT whose
+// "mul" pixel function multiplies the two complex sources; GDAL (third party, version unpinned by the
+// reference) evaluates that in double -- starting from 1+0j, times source 1, times source 2 -- and
+// stores CFloat32.  Restated with the operations spelled out (no complex operator*, no contraction);
+// parity at this boundary is unpinned: GDAL is not available in this image.
+void oracle_cmul(const float* a, const float* b, long n, float* out) {
+    for (long i = 0; i < n; ++i) {
+        volatile double ar = (double)a[2 * i], ai = (double)a[2 * i + 1];       // 1+0j times source 1: exact
+        volatile double br = (double)b[2 * i], bi = (double)b[2 * i + 1];
+        volatile double p0 = ar * br, p1 = ai * bi, p2 = ar * bi, p3 = ai * br;
+        volatile double re = p0 - p1, im = p2 + p3;
+        out[2 * i] = (float)re;
+        out[2 * i + 1] = (float)im;
+    }
+}
+
 }  // extern "C"

@@ -41,3 +41,13 @@ run("C1", 20, 512, 512, 5, 2, "KS2", [dict(method="EVD"), dict(method="MLE")])
 run("C3", 100, 32, 2048, 5, 2, "KS2", [dict(method="MLE", variant=1, min_neighbors=5)])
 run("C5", 30, 256, 2048, 10, 10, "AD2", [dict(method="EVD")])
 run("C2'", 30, 128, 4096, 11, 5, "KS2", [dict(method="EVD")])
+
+# datum adjustment product: HBM-bound, 24 bytes per pixel
+a = torch.randn(1500 * 20000, dtype=torch.complex64, device=dev)
+b = torch.randn(1500 * 20000, dtype=torch.complex64, device=dev)
+o = torch.empty_like(a)
+for _ in range(3):
+    ctx.cmul_device(a, b, out=o)
+    torch.cuda.synchronize()
+t = ctx.last_kernel_ms("cmul")
+print(f"cmul: 30 M pixels {t:.3f} ms = {a.numel() * 24 / t / 1e6:.0f} GB/s (algorithmic 24 B/pixel)", flush=True)
