@@ -761,6 +761,65 @@ int fringe_cmul(fringe_ctx* ctx, const float* a, const float* b, int64_t n, floa
     return FRINGE_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// despeck (src/despeck/despeck.cpp:321-361, 387-432)
+// ---------------------------------------------------------------------------------------
+static int check_despeck(fringe_ctx* ctx, const void* z1, const void* wts, const void* out, int cols, int lines,
+                         int Nx, int Ny, int first_line, int n_lines) {
+    if (!ctx) return FRINGE_ERR_ARGUMENT;
+    if (!z1 || !wts || !out) return fail(ctx, FRINGE_ERR_ARGUMENT, "null pointer");
+    if (cols <= 0 || lines <= 0 || Nx < 0 || Ny < 0) return fail(ctx, FRINGE_ERR_ARGUMENT, "non-positive size");
+    if (first_line < 0 || n_lines < 0 || first_line + n_lines > lines)
+        return fail(ctx, FRINGE_ERR_ARGUMENT, "line range outside block");
+    return FRINGE_OK;
+}
+
+int fringe_despeck_block_device(fringe_ctx* ctx, const float* z1, const float* z2, const uint32_t* wts, int cols,
+                                int lines, int Nx, int Ny, int first_line, int n_lines, int compute_coherence,
+                                float* out, void* stream) {
+    int rc = check_despeck(ctx, z1, wts, out, cols, lines, Nx, Ny, first_line, n_lines);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    const size_t npix = (size_t)cols * lines;
+    const int mode = z2 ? (compute_coherence ? 2 : 1) : (compute_coherence ? 3 : 0);
+    CU(ctx->scratch.ensure(2 * npix * sizeof(float2)));
+    float2* d1 = (float2*)ctx->scratch.p;
+    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_DESPECK][0], st));
+    CU(fringe::launch_despeck((const float2*)z1, (const float2*)z2, wts, cols, lines, Nx, Ny, first_line, n_lines, mode,
+                              d1, d1 + npix, (float2*)out, st));
+    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_DESPECK][1], st));
+    ctx->ev_valid[FRINGE_KERNEL_DESPECK] = true;
+    ctx->launches += (n_lines > 0) ? 2 : 0;
+    return FRINGE_OK;
+}
+
+int fringe_despeck_block(fringe_ctx* ctx, const float* z1, const float* z2, const uint32_t* wts, int cols, int lines,
+                         int Nx, int Ny, int first_line, int n_lines, int compute_coherence, float* out) {
+    int rc = check_despeck(ctx, z1, wts, out, cols, lines, Nx, Ny, first_line, n_lines);
+    if (rc) return rc;
+    if (n_lines == 0) return FRINGE_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t npix = (size_t)cols * lines;
+    const int nu = fringe_nulong(Nx, Ny);
+    CU(ctx->in_slc.ensure(2 * npix * sizeof(float2)));
+    CU(ctx->in_wts.ensure(npix * nu * sizeof(uint32_t)));
+    CU(ctx->o_out.ensure(npix * sizeof(float2)));
+    float2* dz1 = (float2*)ctx->in_slc.p;
+    float2* dz2 = z2 ? dz1 + npix : nullptr;
+    CU(cudaMemcpyAsync(dz1, z1, npix * sizeof(float2), cudaMemcpyHostToDevice, st));
+    if (z2) CU(cudaMemcpyAsync(dz2, z2, npix * sizeof(float2), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->in_wts.p, wts, npix * nu * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    rc = fringe_despeck_block_device(ctx, (const float*)dz1, (const float*)dz2, (const uint32_t*)ctx->in_wts.p, cols, lines,
+                                     Nx, Ny, first_line, n_lines, compute_coherence, (float*)ctx->o_out.p, st);
+    if (rc) return rc;
+    const size_t off = (size_t)first_line * cols, cnt = (size_t)n_lines * cols;
+    CU(cudaMemcpyAsync((float2*)out + off, (float2*)ctx->o_out.p + off, cnt * sizeof(float2), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return FRINGE_OK;
+}
+
 int fringe_last_kernel_ms(fringe_ctx* ctx, int kernel, float* ms) {
     if (!ctx || !ms || kernel < 0 || kernel >= FRINGE_KERNEL_COUNT) return FRINGE_ERR_ARGUMENT;
     if (!ctx->ev_valid[kernel]) return fail(ctx, FRINGE_ERR_ARGUMENT, "kernel has not been launched on this context");

@@ -45,4 +45,116 @@ cudaError_t launch_cmul(const float2* a, const float2* b, float2* out, long n, c
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------
+// despeck: SHP-weighted average of one band's amplitude or of an interferogram,
+// optionally normalised to a coherence.  src/despeck/despeck.cpp:321-361 (per-block preparation)
+// and :387-432 (pixel loop).  Two kernels: the preparation is elementwise, the average is a gather
+// of up to (2Nx+1)(2Ny+1) prepared samples per pixel (L1/L2-resident: neighbouring pixels share
+// almost all of them).  All sums are float additions in window raster order and every product /
+// quotient is a single correctly rounded float operation, as in the reference, so the result is
+// bit-identical to the CPU loop.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float hypotf_exact(float2 z) {          // glibc hypotf, see nmap_kernels.cu
+    if (isinf(z.x) || isinf(z.y)) return __int_as_float(0x7f800000);
+    return (float)__dsqrt_rn(__dadd_rn(__dmul_rn((double)z.x, (double)z.x), __dmul_rn((double)z.y, (double)z.y)));
+}
+
+// mode 0: one band, d1 = |z1| ; mode 1: d1 = z1 * conj(z2) ; mode 2: mode 1 plus d2 = (|z1|^2, |z2|^2)
+__global__ void __launch_bounds__(256) k_despeck_prep(const float2* __restrict__ z1, const float2* __restrict__ z2,
+                                                      long n, int mode, float2* __restrict__ d1,
+                                                      float2* __restrict__ d2) {
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float2 a = __ldg(z1 + i);
+        if (mode == 0) { d1[i] = make_float2(hypotf_exact(a), 0.f); continue; }
+        const float2 b = __ldg(z2 + i);
+        // complex<float> a *= conj(b): four float products, one float add / subtract each (libgcc __mulsc3)
+        const float re = __fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
+        const float im = __fsub_rn(__fmul_rn(a.y, b.x), __fmul_rn(a.x, b.y));
+        d1[i] = make_float2(re, im);
+        if (mode == 2) {
+            const float p = hypotf_exact(a), q = hypotf_exact(b);
+            d2[i] = make_float2(__fmul_rn(p, p), __fmul_rn(q, q));
+        }
+    }
+}
+
+struct DespeckArgs {
+    const float2* d1;
+    const float2* d2;
+    const uint32_t* wts;
+    int cols, lines, Nx, Ny, nulong, first_line, n_lines, mode;
+    float2* out;
+};
+
+__global__ void __launch_bounds__(256) k_despeck(const DespeckArgs a) {
+    const long total = (long)a.n_lines * a.cols;
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long pp = (long)a.first_line * a.cols + i;
+    const int ci = (int)(pp / a.cols), cj = (int)(pp - (long)ci * a.cols);
+    const uint32_t* cen = a.wts + pp * a.nulong;
+    const int WX = 2 * a.Nx + 1, center = a.Ny * WX + a.Nx;
+    float2 res = make_float2(0.f, 0.f);
+    if ((__ldg(cen + (center >> 5)) >> (center & 31)) & 1u) {
+        const int xmin = max(cj - a.Nx, 0), xmax = min(a.cols - 1, cj + a.Nx);
+        const int ymin = max(ci - a.Ny, 0), ymax = min(a.lines - 1, ci + a.Ny);
+        float vr = 0.f, vi = 0.f, sr = 0.f, si = 0.f;
+        for (int ii = ymin; ii <= ymax; ++ii) {
+            int f = (ii - ci + a.Ny) * WX + (xmin - cj + a.Nx);
+            uint32_t word = __ldg(cen + (f >> 5));
+            for (int jj = xmin; jj <= xmax; ++jj, ++f) {
+                if ((f & 31) == 0) word = __ldg(cen + (f >> 5));
+                if ((word >> (f & 31)) & 1u) {
+                    const long q = (long)ii * a.cols + jj;
+                    const float2 v = __ldg(a.d1 + q);
+                    vr = __fadd_rn(vr, v.x); vi = __fadd_rn(vi, v.y);
+                    if (a.mode == 2) {
+                        const float2 w = __ldg(a.d2 + q);
+                        sr = __fadd_rn(sr, w.x); si = __fadd_rn(si, w.y);
+                    } else {
+                        sr = __fadd_rn(sr, 1.0f);                   // weights 1 + 0i
+                    }
+                }
+            }
+        }
+        if (sr > 0.f) {
+            if (a.mode == 2) {
+                if (si > 0.f) {
+                    const float den = __fmul_rn(__fsqrt_rn(sr), __fsqrt_rn(si));
+                    res = make_float2(__fdiv_rn(vr, den), __fdiv_rn(vi, den));
+                }
+            } else if (a.mode >= 0) {
+                res = make_float2(__fdiv_rn(vr, sr), __fdiv_rn(vi, sr));
+            }
+        }
+    }
+    a.out[pp] = res;
+}
+
+// mode: 0 one band, 1 interferogram, 2 interferogram coherence, 3 one band + coherence flag (the
+// reference then divides by sqrt(sum 1) * sqrt(0) only if the imaginary weight sum is positive: never)
+cudaError_t launch_despeck(const float2* z1, const float2* z2, const uint32_t* wts, int cols, int lines, int Nx,
+                           int Ny, int first_line, int n_lines, int mode, float2* d1, float2* d2, float2* out,
+                           cudaStream_t st) {
+    const long npix = (long)cols * lines;
+    if (npix <= 0 || n_lines <= 0) return cudaSuccess;
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    long blocks = (npix + 255) / 256;
+    if (blocks > (long)nsm * 32) blocks = (long)nsm * 32;
+    const int prep_mode = (mode == 3) ? 0 : mode;
+    k_despeck_prep<<<(unsigned)blocks, 256, 0, st>>>(z1, z2, npix, prep_mode, d1, d2);
+    DespeckArgs a;
+    a.d1 = d1; a.d2 = d2; a.wts = wts; a.cols = cols; a.lines = lines; a.Nx = Nx; a.Ny = Ny;
+    a.nulong = ((2 * Ny + 1) * (2 * Nx + 1) + 31) / 32;
+    a.first_line = first_line; a.n_lines = n_lines;
+    a.mode = (mode == 3) ? -1 : mode;                            // -1: numerator summed, result stays zero
+    a.out = out;
+    const long total = (long)n_lines * cols;
+    k_despeck<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
 }  // namespace fringe

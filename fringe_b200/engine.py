@@ -100,7 +100,7 @@ class Context:
         self._check(lib.fringe_evd_stats(self._h, arr))
         return {"pixels": arr[0], "power_iterations": arr[1], "fp64_pixels": arr[2], "capped": arr[3]}
 
-    KERNELS = {"amp_sort": 0, "nmap": 1, "transpose": 2, "evd": 3, "cmul": 4}
+    KERNELS = {"amp_sort": 0, "nmap": 1, "transpose": 2, "evd": 3, "cmul": 4, "despeck": 5}
 
     def last_kernel_ms(self, kernel: str) -> float:
         ms = C.c_float(0)
@@ -181,6 +181,36 @@ class Context:
             int(min_neighbors), count.ctypes.data if want_mask else None,
             wts.ctypes.data if want_mask else None, out.ctypes.data, tcorr.ctypes.data, comp.ctypes.data))
         return count, wts, out, tcorr, comp
+
+    def despeck_block(self, z1, wts, Nx, Ny, z2=None, coherence=False, first_line=0, n_lines=None):
+        """SHP-weighted average (``fringe_despeck_block``): z1 [, z2] (lines, cols) complex64 -> complex64."""
+        z1 = np.ascontiguousarray(z1, np.complex64)
+        lines, cols = z1.shape
+        if z2 is not None:
+            z2 = np.ascontiguousarray(z2, np.complex64)
+            if z2.shape != z1.shape:
+                raise ValueError("shape mismatch")
+        wts = np.ascontiguousarray(wts, np.uint32)
+        if n_lines is None:
+            n_lines = lines - first_line
+        out = np.zeros((lines, cols), np.complex64)
+        self._check(lib.fringe_despeck_block(self._h, z1.ctypes.data, None if z2 is None else z2.ctypes.data,
+                                             wts.ctypes.data, cols, lines, Nx, Ny, first_line, n_lines,
+                                             1 if coherence else 0, out.ctypes.data))
+        return out
+
+    def despeck_block_device(self, z1, wts, Nx, Ny, z2=None, coherence=False, first_line=0, n_lines=None, out=None):
+        import torch
+        assert z1.is_cuda and z1.dtype == torch.complex64 and z1.is_contiguous() and wts.is_cuda and wts.is_contiguous()
+        lines, cols = z1.shape
+        if n_lines is None:
+            n_lines = lines - first_line
+        if out is None:
+            out = torch.zeros_like(z1)
+        self._check(lib.fringe_despeck_block_device(
+            self._h, z1.data_ptr(), None if z2 is None else z2.data_ptr(), wts.data_ptr(), cols, lines, Nx, Ny,
+            first_line, n_lines, 1 if coherence else 0, out.data_ptr(), self._stream()))
+        return out
 
     def cmul(self, a, b):
         """Datum adjustment product a * b of two complex64 rasters (``fringe_cmul``)."""

@@ -151,6 +151,23 @@ int fringe_cmul(fringe_ctx* ctx, const float* a, const float* b, int64_t n, floa
 int fringe_cmul_device(fringe_ctx* ctx, const float* a, const float* b, int64_t n, float* out,
                        void* stream);
 
+/* ---- despeck: SHP-weighted average ----------------------------------------------------------
+ * One block of `lines` lines; replaces the preparation and pixel loops of
+ * src/despeck/despeck.cpp:321-361 and :387-432.  z1, z2: the two bands ([lines*cols] complex64) the
+ * reference reads with ibands[0] / ibands[1]; z2 == NULL = single band (its amplitude is averaged).
+ *   z2 != NULL, compute_coherence == 0   average of z1 * conj(z2) over the SHPs
+ *   z2 != NULL, compute_coherence != 0   that sum / (sqrt(sum |z1|^2) * sqrt(sum |z2|^2))
+ *   z2 == NULL, compute_coherence != 0   zeros, as the reference yields (its weight sum has no imaginary part)
+ * `out` [lines*cols] complex64 is written for lines [first_line, first_line + n_lines) only; pixels
+ * whose own mask bit is clear get 0.  Results are bit-identical to the CPU loop (float sums in window
+ * raster order). */
+int fringe_despeck_block(fringe_ctx* ctx, const float* z1, const float* z2, const uint32_t* wts, int cols,
+                         int lines, int Nx, int Ny, int first_line, int n_lines, int compute_coherence,
+                         float* out);
+int fringe_despeck_block_device(fringe_ctx* ctx, const float* z1, const float* z2, const uint32_t* wts,
+                                int cols, int lines, int Nx, int Ny, int first_line, int n_lines,
+                                int compute_coherence, float* out, void* stream);
+
 /* Largest `bands` the evd kernels accept for the given method. */
 int fringe_evd_max_bands(int method, int variant);
 
@@ -163,7 +180,8 @@ enum {
     FRINGE_KERNEL_TRANSPOSE = 2,  /* band-major -> pixel-major re-layout */
     FRINGE_KERNEL_EVD = 3,        /* covariance + eigen + post-processing */
     FRINGE_KERNEL_CMUL = 4,       /* datum adjustment product */
-    FRINGE_KERNEL_COUNT = 5
+    FRINGE_KERNEL_DESPECK = 5,    /* despeck preparation + SHP-weighted average */
+    FRINGE_KERNEL_COUNT = 6
 };
 int fringe_last_kernel_ms(fringe_ctx* ctx, int kernel, float* ms);
 /* FP32 FMA throughput of the device measured with a register-resident FMA loop; the roofline

@@ -72,6 +72,7 @@ class Oracle:
         lib.oracle_pd_inverse.argtypes = [dp, C.c_int]
         lib.oracle_nmap_block.argtypes = [fp, u8, dp] + [C.c_int] * 6 + [C.c_double, i32, u32, fp]
         lib.oracle_evd_block.argtypes = [fp, u32] + [C.c_int] * 12 + [fp, fp, fp, i32]
+        lib.oracle_despeck_block.argtypes = [fp, fp, u32] + [C.c_int] * 7 + [fp]
         lib.oracle_cmul.argtypes = [fp, fp, C.c_long, fp]
         lib.oracle_cmul.restype = None
         self.kind = lib.oracle_kind().decode()
@@ -174,6 +175,23 @@ class Oracle:
         if rc != 0:
             raise RuntimeError(f"oracle_evd_block rc={rc}")
         return (out, tcorr, comp, npix) if want_npix else (out, tcorr, comp)
+
+    def despeck_block(self, z1, wts, Nx, Ny, z2=None, coherence=False, first_line=0, n_lines=None):
+        """SHP-weighted average (src/despeck/despeck.cpp): z1 [, z2] (lines, cols) complex64 -> complex64."""
+        z1 = np.ascontiguousarray(z1, np.complex64)
+        lines, cols = z1.shape
+        if z2 is not None:
+            z2 = np.ascontiguousarray(z2, np.complex64)
+        wts = np.ascontiguousarray(wts, np.uint32)
+        if n_lines is None:
+            n_lines = lines - first_line
+        out = np.zeros((lines, cols), np.complex64)
+        rc = self.lib.oracle_despeck_block(self._p(z1.view(np.float32), C.c_float),
+                                           None if z2 is None else self._p(z2.view(np.float32), C.c_float),
+                                           self._p(wts, C.c_uint32), cols, lines, Nx, Ny, first_line, n_lines,
+                                           1 if coherence else 0, self._p(out.view(np.float32), C.c_float))
+        assert rc == 0
+        return out
 
     def cmul(self, a, b):
         """Datum adjustment product a * b (complex64 in, double arithmetic, complex64 out)."""

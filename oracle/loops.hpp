@@ -296,4 +296,63 @@ int evd_block(const cfloat* slc, const uint32_t* wts, int cols, int lines, int b
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------
+// despeck: SHP-weighted average of one band (amplitude) or of an interferogram, optionally
+// normalised to a coherence.  src/despeck/despeck.cpp:300-362 (per-block preparation) and :387-432
+// (the pixel loop); plain arrays instead of Armadillo columns, no GDAL.  z1 / z2: the two bands of
+// the block ([lines*cols] complex64), z2 == nullptr = single-band amplitude mode (ibands[1] = -1).
+// Sums are complex<float> accumulated in window raster order, exactly as the reference does.
+// ---------------------------------------------------------------------------------------
+template <class I>
+int despeck_block(const cfloat* z1, const cfloat* z2, const uint32_t* wts, int cols, int lines, int Nx, int Ny,
+                  int first_line, int n_lines, int compute_coherence, cfloat* out) {
+    const long npix_block = (long)cols * lines;
+    const int nulong = (int)std::ceil(((2 * Ny + 1) * (2 * Nx + 1)) / 32.0);
+    const typename I::Mask bitmask = {Ny, Nx};
+    std::vector<cfloat> d1(npix_block), d2(npix_block);
+    for (long jj = 0; jj < npix_block; ++jj) {                     // despeck.cpp:321-361
+        if (z2) {
+            cfloat a = z1[jj];
+            const cfloat b = z2[jj];
+            if (compute_coherence) {
+                const float amp1 = std::abs(a), amp2 = std::abs(b);
+                a *= std::conj(b);
+                d1[jj] = a;
+                d2[jj] = cfloat(amp1 * amp1, amp2 * amp2);
+            } else {
+                a *= std::conj(b);
+                d1[jj] = a;
+                d2[jj] = 1.0f;
+            }
+        } else {
+            d1[jj] = std::abs(z1[jj]);
+            d2[jj] = cfloat(1.0f, 0.0f);                           // arma ones(): 1 + 0i (despeck.cpp:360)
+        }
+    }
+    std::memset((void*)out, 0, sizeof(cfloat) * npix_block);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long pp = (long)first_line * cols; pp < (long)(first_line + n_lines) * cols; ++pp) {   // despeck.cpp:387-432
+        uint32_t* cen = const_cast<uint32_t*>(wts + pp * nulong);
+        if (bitmask.getbit(cen, 0, 0) == 0) continue;
+        const int ci = (int)(pp / cols), cj = (int)(pp % cols);
+        const int xmin = std::max(cj - Nx, 0), xmax = std::min(cols - 1, cj + Nx);
+        const int ymin = std::max(ci - Ny, 0), ymax = std::min(lines - 1, ci + Ny);
+        cfloat val = 0.0f, sumw = 0.0f;
+        for (int ii = ymin; ii <= ymax; ++ii)
+            for (int jj = xmin; jj <= xmax; ++jj)
+                if (bitmask.getbit(cen, ii - ci, jj - cj) != 0) {
+                    val += d1[(long)ii * cols + jj];
+                    sumw += d2[(long)ii * cols + jj];
+                }
+        if (sumw.real() > 0) {
+            if (compute_coherence) {
+                if (sumw.imag() > 0) out[pp] = val / (std::sqrt(sumw.real()) * std::sqrt(sumw.imag()));
+            } else {
+                out[pp] = val / sumw.real();
+            }
+        }
+    }
+    return 0;
+}
+
 }  // namespace oracle

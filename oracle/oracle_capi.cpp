@@ -100,6 +100,12 @@ int oracle_evd_block(const float* slc, const uint32_t* wts, int cols, int lines,
                                    reinterpret_cast<oracle::cfloat*>(comp), npix);
 }
 
+int oracle_despeck_block(const float* z1, const float* z2, const uint32_t* wts, int cols, int lines, int Nx, int Ny,
+                         int first_line, int n_lines, int compute_coherence, float* out) {
+    return oracle::despeck_block<Impl>((const oracle::cfloat*)z1, (const oracle::cfloat*)z2, wts, cols, lines, Nx, Ny,
+                                       first_line, n_lines, compute_coherence, (oracle::cfloat*)out);
+}
+
 // Datum adjustment product (python/adjustMiniStacks.py:180-199): the reference writes a VRT whose
 // "mul" pixel function multiplies the two complex sources; GDAL (third party, version unpinned by the
 // reference) evaluates that in double -- starting from 1+0j, times source 1, times source 2 -- and

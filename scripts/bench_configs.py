@@ -51,3 +51,17 @@ for _ in range(3):
     torch.cuda.synchronize()
 t = ctx.last_kernel_ms("cmul")
 print(f"cmul: 30 M pixels {t:.3f} ms = {a.numel() * 24 / t / 1e6:.0f} GB/s (algorithmic 24 B/pixel)", flush=True)
+
+# despeck: 30-date stack not needed, two bands of the 1500 x 20000 image, 11x5 window
+lines, cols = 1500, 20000
+slc = synth.make_stack_torch(30, lines, cols, seed=2, device=dev, row_range=(0, 300))
+count, wts = ctx.nmap_block_device(slc, 5, 2, "KS2", 0.05)
+z1, z2 = slc[0].contiguous(), slc[7].contiguous()
+for coh in (False, True):
+    for _ in range(3):
+        out = ctx.despeck_block_device(z1, wts, 5, 2, z2=z2, coherence=coh)
+        torch.cuda.synchronize()
+    t = ctx.last_kernel_ms("despeck")
+    npx = z1.numel()
+    print(f"despeck coherence={coh}: {npx / 1e6:.1f} M pixels {t:.3f} ms = {npx / t / 1e3:.0f} M px/s, "
+          f"{npx * (16 + 8 + 8) / t / 1e6:.0f} GB/s of the 32 algorithmic B/pixel (2 bands in, mask, 1 out)", flush=True)
