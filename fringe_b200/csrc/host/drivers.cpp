@@ -347,3 +347,98 @@ static int evd_driver(evdOptions* opts, int variant) {
 
 int evd_process(evdOptions* opts) { return evd_driver(opts, FRINGE_VARIANT_EVD); }
 int phase_link_process(evdOptions* opts) { return evd_driver(opts, FRINGE_VARIANT_PHASE_LINK); }
+
+// =====================================================================================================
+// despeck_process: src/despeck/despeck.cpp:14-500 -- same checks, error codes, block schedule and output
+// (ENVI, one band: Float32 for a single input band, CFloat32 for an interferogram / coherence).
+int despeck_process(despeckOptions* opts) {
+    opts->print();
+    const int Nx = opts->Nx, Ny = opts->Ny;
+    const int nulong = fringe_nulong(Nx, Ny);
+    std::cout << "Number of uint32 bytes for mask: " << nulong << "\n";
+    Raster in;
+    if (!in.open(opts->inputDS)) {
+        std::cout << "Cannot open stack file { " << opts->inputDS << " } for reading: " << in.error << "\nExiting with error code .... (102) \n";
+        return 102;
+    }
+    const int cols = in.cols, rows = in.rows, nbands = in.count();
+    std::cout << "Number of rows  = " << rows << "\nNumber of cols  = " << cols << "\nNumber of bands = " << nbands << "\n";
+    const int band1 = opts->ibands[0], band2 = opts->ibands[1];
+    if (band1 <= 0 || band1 > nbands) { std::cout << "Master band " << band1 << " outside the range of permissible bands\nExiting with error code ... (102) \n"; return 102; }
+    if (band2 > 0 && band2 > nbands) { std::cout << "Slave band " << band2 << "outside the range of permissible bands\nExiting with error code ... (102) \n"; return 102; }
+    Raster wts;
+    if (!wts.open(opts->wtsDS)) { std::cout << "Could not open weights dataset {" << opts->wtsDS << "}\nExiting with non-zero error code ... 105 \n"; return 105; }
+    {
+        int code = 0;
+        if (wts.cols != cols) { std::cout << "Width mismatch between input dataset and weight dataset\n"; code = 106; }
+        if (wts.rows != rows) { std::cout << "Length mismatch between input dataset and weight dataset \n"; code = 107; }
+        if (wts.count() != nulong) { std::cout << "Number of bands mismatch for weights and window size \n"; code = 108; }
+        auto geti = [&](const char* k) { auto it = wts.envi.fields.find(k); return it == wts.envi.fields.end() ? 0 : std::atoi(it->second.c_str()); };
+        const int inNx = geti("halfwindowx"), inNy = geti("halfwindowy");
+        if (inNx != Nx) { std::cout << "Half window size x of wts is different from input. \n"; code = 109; }
+        if (inNx == 0) { std::cout << "No non-zero metadata item called HALFWINDOWX \n"; code = 109; }
+        if (inNy != Ny) { std::cout << "Half window size y of wts is different from input. \n"; code = 110; }
+        if (inNy == 0) { std::cout << "No non-zero metadata item called HALFWINDOWY \n"; code = 110; }
+        if (code) { std::cout << "Exiting with error code ....(" << code << ")\n"; return code; }
+        if (!wts.interleaved || wts.envi.data_type != 13) { std::cout << "Weights dataset must be a UInt32 ENVI BIP raster\n"; return 105; }
+    }
+    const int ngpu = visible_gpus();
+    if (ngpu <= 0) { std::cout << "No CUDA device available and there is no CPU path.\n"; return 200 + FRINGE_ERR_NO_DEVICE; }
+
+    const int blockysize = block_height(opts->memsize, cols, opts->blocksize, 4 * (6 + nulong), rows, Ny);   // despeck.cpp:155
+    std::cout << "Block size = " << blockysize << " lines \n";
+    const std::vector<Block> sched = make_schedule(rows, blockysize, Ny);
+    std::cout << "Total number of blocks to process: " << sched.size() << "\n";
+
+    const bool cplx = band2 > 0;
+    EnviWriter wout;
+    if (!wout.create(opts->outputDS, cols, rows, 1, cplx ? 6 : 4)) {
+        std::cout << "Could not create despecked dataset {" << opts->outputDS << "} \nExiting with non-zero error code ... 104 \n";
+        return 104;
+    }
+    std::atomic<size_t> next(0);
+    std::atomic<int> rc(0);
+    std::mutex log_mu;
+    auto worker = [&](int dev) {
+        fringe_ctx* ctx = nullptr;
+        if (fringe_create(dev, &ctx) != FRINGE_OK) { rc = 200 + FRINGE_ERR_NO_DEVICE; return; }
+        const size_t bp = (size_t)cols * blockysize;
+        Pinned z1, z2, wbuf, out, real;
+        if (!z1.alloc(bp * 8) || !z2.alloc(bp * 8) || !wbuf.alloc(bp * nulong * 4) || !out.alloc(bp * 8) || !real.alloc(bp * 4)) {
+            rc = 200 + FRINGE_ERR_MEMORY; fringe_destroy(ctx); return;
+        }
+        for (size_t i = next++; i < sched.size() && rc == 0; i = next++) {
+            const Block& b = sched[i];
+            bool ok = in.read_band_lines(band1 - 1, b.yoff, b.inysize, (char*)z1.p, 8);
+            if (ok && cplx) ok = in.read_band_lines(band2 - 1, b.yoff, b.inysize, (char*)z2.p, 8);
+            if (ok) ok = wts.read_interleaved_lines(b.yoff, b.inysize, wbuf.p);
+            if (!ok) { std::lock_guard<std::mutex> g(log_mu); std::cout << "Error reading data at line " << b.yoff << "\nExiting with error code .... (108) \n"; rc = 108; break; }
+            const int stt = fringe_despeck_block(ctx, (const float*)z1.p, cplx ? (const float*)z2.p : nullptr, (const uint32_t*)wbuf.p,
+                                                 cols, b.inysize, Nx, Ny, b.first, b.nwrite, opts->computeCoherence ? 1 : 0, (float*)out.p);
+            if (stt != FRINGE_OK) {
+                std::lock_guard<std::mutex> g(log_mu);
+                std::cout << "Device error: " << fringe_last_error(ctx) << "\n";
+                rc = 200 + stt; break;
+            }
+            const size_t off = (size_t)b.first * cols, cnt = (size_t)b.nwrite * cols;
+            if (cplx) ok = wout.write_lines(b.yoff + b.first, b.nwrite, (const char*)out.p + off * 8);
+            else {                                   // Float32 output: real parts (GDAL converts the complex buffer)
+                const float* src = (const float*)out.p + 2 * off;
+                float* dst = (float*)real.p;
+                for (size_t k = 0; k < cnt; ++k) dst[k] = src[2 * k];
+                ok = wout.write_lines(b.yoff + b.first, b.nwrite, dst);
+            }
+            if (!ok) { std::lock_guard<std::mutex> g(log_mu); std::cout << "Error writing despeck data at line " << b.yoff << "\nExiting with error code .... (110) \n"; rc = 110; break; }
+        }
+        fringe_destroy(ctx);
+    };
+    {
+        std::vector<std::thread> th;
+        const int nw = (int)std::min<size_t>(ngpu, sched.size());
+        for (int d = 0; d < nw; ++d) th.emplace_back(worker, d);
+        for (auto& t : th) t.join();
+    }
+    if (rc != 0) return rc;
+    wout.close_file();
+    return 0;
+}

@@ -65,9 +65,33 @@ struct evdOptions {
     }
 };
 
+// src/despeck/despeck.hpp:19-56
+struct despeckOptions {
+    std::string inputDS;     // input VRT with SLCs as bands
+    std::string wtsDS;       // neighbourhood bit mask from nmap
+    std::string outputDS;    // despeckled amplitude / interferogram / coherence
+    int blocksize, memsize;
+    int ibands[2];           // 1-based bands: master, slave (-1 = single-band amplitude)
+    int Nx, Ny;
+    bool computeCoherence;
+
+    despeckOptions() : blocksize(64), memsize(512), Nx(5), Ny(5), computeCoherence(false) { ibands[0] = 1; ibands[1] = -1; }
+    void print() const {
+        std::cout << "Input Dataset: " << inputDS << std::endl;
+        std::cout << "Weights Dataset: " << wtsDS << std::endl;
+        std::cout << "Output Dataset: " << outputDS << std::endl;
+        std::cout << "Bands: " << ibands[0] << " " << ibands[1] << std::endl;
+        std::cout << "Window size: " << Nx << " " << Ny << std::endl;
+        std::cout << "Memsize: " << memsize << " Mb \n";
+        std::cout << "Blocksize: " << blocksize << " lines \n";
+        std::cout << "Coherence: " << computeCoherence << " \n";
+    }
+};
+
 // Block drivers (drivers.cpp).  Return 0 or the reference's error codes
 // (nmap: 1,102,104,105,106,108,111; evd: 101,102,105-110,112-121), plus 200+status when the
 // device library reports an error (there is no CPU fallback).
 int nmap_process(nmapOptions* opts);
 int evd_process(evdOptions* opts);            // src/evd/evd.cpp control flow
 int phase_link_process(evdOptions* opts);     // src/phase_link/phase_link.cpp control flow
+int despeck_process(despeckOptions* opts);    // src/despeck/despeck.cpp: 102, 104-110, 200+status

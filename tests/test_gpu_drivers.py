@@ -107,3 +107,31 @@ def test_sequential_chain(stack, oracle_lib):
     shutil.rmtree(os.path.join(out, "Datum_connection"))
     seq_cli.main(["-i", os.path.join(root, "SLC"), "-w", wts_path, "-o", out, "-x", "5", "-y", "2", "-s", "5", "-r", "2"])
     assert os.path.exists(os.path.join(dc, "tcorr.bin"))
+
+
+def test_despeck_cli_multi_block(stack, oracle_lib):
+    """despeck.py -> despecklib -> despeck_process (block schedule of despeck.cpp) -> fringe_despeck_block,
+    against the oracle on the whole image: amplitude (Float32 out), interferogram and coherence (CFloat32)."""
+    from fringe_b200.cli import despeck as despeck_cli
+    root, slc, vrt = stack
+    wts_path = os.path.join(root, "KS2d", "nmap")
+    cnt_path = os.path.join(root, "KS2d", "count")
+    nmap_cli.main(["-i", vrt, "-o", wts_path, "-c", cnt_path, "-x", "4", "-y", "3"])
+    wts = stackio.read_envi(wts_path)
+    # -r 1 -l 32: several overlapping blocks for 150 lines
+    out = os.path.join(root, "despeck", "amp")
+    despeck_cli.main(["-i", vrt, "-w", wts_path, "-o", out, "-x", "4", "-y", "3", "-b", "3", "-r", "1", "-l", "32"])
+    amp = stackio.read_envi(out)
+    assert amp.dtype == np.float32 and amp.shape == (150, 96)
+    want = oracle_lib.despeck_block(slc[2], wts, 4, 3)
+    assert np.array_equal(amp.view(np.uint32), want.real.astype(np.float32).view(np.uint32))
+    for name, coh in (("ifg", False), ("coh", True)):
+        out = os.path.join(root, "despeck", name)
+        despeck_cli.main(["-i", vrt, "-w", wts_path, "-o", out, "-x", "4", "-y", "3", "-b", "2", "9", "-r", "1", "-l", "32"]
+                         + (["-c"] if coh else []))
+        got = stackio.read_envi(out)
+        assert got.dtype == np.complex64
+        want = oracle_lib.despeck_block(slc[1], wts, 4, 3, z2=slc[8], coherence=coh)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    with pytest.raises(Exception, match="coherence"):
+        despeck_cli.main(["-i", vrt, "-w", wts_path, "-o", out + "x", "-b", "1", "-c"])

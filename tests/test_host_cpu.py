@@ -108,3 +108,37 @@ def test_block_schedule_matches_reference_rules():
             assert lo - ny >= yoff or lo == 0
             assert hi + ny <= yoff + n or hi == rows
         assert np.all(written == 1)
+
+
+def test_despeck_binding_and_error_codes(tmp_path):
+    """despecklib.Despeck (src/despeck/despecklib.pyx surface) and the checks of despeck.cpp:40-150 that
+    run before any device work."""
+    import despecklib
+    d = despecklib.Despeck()
+    assert (d.band1, d.band2, d.coherenceFlag, d.blocksize, d.memsize, d.halfWindowX, d.halfWindowY) == (1, -1, False, 64, 512, 5, 5)
+    slc = synth.make_stack(4, 10, 12, seed=2, region=4)
+    vrt = stackio.make_stack_on_disk(str(tmp_path), slc)
+    d.inputDS, d.weightsDS, d.outputDS = str(tmp_path / "nope.vrt"), str(tmp_path / "w"), str(tmp_path / "out")
+    with pytest.raises(RuntimeError, match="102"):               # despeck.cpp:43-50
+        d.run()
+    d.inputDS = vrt
+    d.band1 = 9
+    with pytest.raises(RuntimeError, match="102"):               # despeck.cpp:61-67
+        d.run()
+    d.band1, d.band2 = 1, 7
+    with pytest.raises(RuntimeError, match="102"):               # despeck.cpp:70-76
+        d.run()
+    d.band2 = 2
+    with pytest.raises(RuntimeError, match="105"):               # despeck.cpp:82-88
+        d.run()
+    stackio.write_envi(str(tmp_path / "w"), np.zeros((10, 12, 1), np.uint32), {"HALFWINDOWX": 2, "HALFWINDOWY": 2})
+    with pytest.raises(RuntimeError, match="110"):               # 11 x 11 window: 108, 109 and 110 all trip, the last one wins
+        d.run()
+    d.halfWindowX, d.halfWindowY = 3, 2
+    with pytest.raises(RuntimeError, match="109"):               # despeck.cpp:117-121 (after the band-count check 108)
+        d.run()
+    d.halfWindowX = 2
+    if engine.device_count() == 0:
+        with pytest.raises(RuntimeError, match="204"):           # no CPU path
+            d.run()
+        assert not os.path.exists(str(tmp_path / "out"))
