@@ -64,6 +64,8 @@ def _load() -> C.CDLL:
     lib.fringe_evd_block.argtypes = evd_args
     lib.fringe_evd_block_device.argtypes = evd_args + [vp]
     lib.fringe_nmap_evd_block.argtypes = [vp, vp, vp, vp] + [i] * 6 + [d] + [i] * 7 + [vp] * 5
+    lib.fringe_ampdispersion_block.argtypes = [vp, vp, vp, i, i, i, vp, vp]
+    lib.fringe_ampdispersion_block_device.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp]
     lib.fringe_despeck_block.argtypes = [vp, vp, vp, vp] + [i] * 7 + [vp]
     lib.fringe_despeck_block_device.argtypes = [vp, vp, vp, vp] + [i] * 7 + [vp, vp]
     lib.fringe_cmul.argtypes = [vp, vp, vp, C.c_int64, vp]

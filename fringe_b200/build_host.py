@@ -1,5 +1,5 @@
 """Builds the C++ host side: libfringe_host.so (block drivers + raster I/O over the C ABI) and the
-Python extension modules nmaplib / evdlib / phase_linklib / despecklib (pybind11), all in-tree."""
+Python extension modules nmaplib / evdlib / phase_linklib / despecklib / ampdispersionlib (pybind11), all in-tree."""
 from __future__ import annotations
 
 import os
@@ -27,7 +27,8 @@ def build(force: bool = False) -> None:
     link = ["-L" + LIBDIR, "-lfringe_host", "-lfringe_b200", "-Wl,-rpath,$ORIGIN/../lib"]
     for mod, src, defs in (("nmaplib", "nmaplib.cpp", []), ("evdlib", "evdlib.cpp", []),
                            ("phase_linklib", "evdlib.cpp", ["-DFRINGE_PHASE_LINK"]),
-                           ("despecklib", "despecklib.cpp", [])):
+                           ("despecklib", "despecklib.cpp", []),
+                           ("ampdispersionlib", "ampdispersionlib.cpp", [])):
         out = os.path.join(BINDINGS, mod + ext)
         if force or _newer(out, [os.path.join(HOST, src), HOST_LIB, __file__] + hdrs):
             _run([HOST_CXX] + common + ["-fvisibility=hidden", "-shared"] + defs + inc +

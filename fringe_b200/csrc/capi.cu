@@ -820,6 +820,50 @@ int fringe_despeck_block(fringe_ctx* ctx, const float* z1, const float* z2, cons
     return FRINGE_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// ampdispersion (src/ampdispersion/ampdispersion.cpp:207-247)
+// ---------------------------------------------------------------------------------------
+int fringe_ampdispersion_block_device(fringe_ctx* ctx, const float* slc, const double* alpha, int cols, int lines,
+                                      int bands, float* da, float* meanamp, void* stream) {
+    if (!ctx) return FRINGE_ERR_ARGUMENT;
+    if (!slc || !da || !meanamp) return fail(ctx, FRINGE_ERR_ARGUMENT, "null pointer");
+    if (cols <= 0 || lines <= 0 || bands <= 0) return fail(ctx, FRINGE_ERR_ARGUMENT, "non-positive size");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_AMPDISP][0], st));
+    CU(fringe::launch_ampdispersion((const float2*)slc, alpha, (long)cols * lines, bands, da, meanamp, st));
+    CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_AMPDISP][1], st));
+    ctx->ev_valid[FRINGE_KERNEL_AMPDISP] = true;
+    ctx->launches += 1;
+    return FRINGE_OK;
+}
+
+int fringe_ampdispersion_block(fringe_ctx* ctx, const float* slc, const double* alpha, int cols, int lines, int bands,
+                               float* da, float* meanamp) {
+    if (!ctx) return FRINGE_ERR_ARGUMENT;
+    if (!slc || !da || !meanamp) return fail(ctx, FRINGE_ERR_ARGUMENT, "null pointer");
+    if (cols <= 0 || lines <= 0 || bands <= 0) return fail(ctx, FRINGE_ERR_ARGUMENT, "non-positive size");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t npix = (size_t)cols * lines;
+    CU(ctx->in_slc.ensure(npix * bands * sizeof(float2)));
+    CU(ctx->o_tcorr.ensure(2 * npix * sizeof(float)));
+    const double* dalpha = nullptr;
+    if (alpha) {
+        CU(ctx->alpha.ensure(bands * sizeof(double)));
+        CU(cudaMemcpyAsync(ctx->alpha.p, alpha, bands * sizeof(double), cudaMemcpyHostToDevice, st));
+        dalpha = (const double*)ctx->alpha.p;
+    }
+    CU(cudaMemcpyAsync(ctx->in_slc.p, slc, npix * bands * sizeof(float2), cudaMemcpyHostToDevice, st));
+    float* dda = (float*)ctx->o_tcorr.p;
+    int rc = fringe_ampdispersion_block_device(ctx, (const float*)ctx->in_slc.p, dalpha, cols, lines, bands, dda, dda + npix, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(da, dda, npix * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(meanamp, dda + npix, npix * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return FRINGE_OK;
+}
+
 int fringe_last_kernel_ms(fringe_ctx* ctx, int kernel, float* ms) {
     if (!ctx || !ms || kernel < 0 || kernel >= FRINGE_KERNEL_COUNT) return FRINGE_ERR_ARGUMENT;
     if (!ctx->ev_valid[kernel]) return fail(ctx, FRINGE_ERR_ARGUMENT, "kernel has not been launched on this context");

@@ -81,6 +81,9 @@ cudaError_t launch_evd_mma(const EvdArgs& a, cudaStream_t st);
 
 // out[i] = a[i] * b[i] (complex64, double arithmetic inside), n pixels; 16-byte aligned pointers
 cudaError_t launch_cmul(const float2* a, const float2* b, float2* out, long n, cudaStream_t st);
+// ampdispersion: slc [bands][npix], alpha [bands] device doubles or nullptr; da, meanamp [npix]
+cudaError_t launch_ampdispersion(const float2* slc, const double* alpha, long npix, int bands, float* da, float* meanamp,
+                                 cudaStream_t st);
 // despeck: mode 0 one band, 1 interferogram, 2 interferogram coherence, 3 one band with the coherence flag;
 // d1, d2: npix float2 of scratch each (d2 only read in mode 2); out written for lines [first_line, +n_lines)
 cudaError_t launch_despeck(const float2* z1, const float2* z2, const uint32_t* wts, int cols, int lines, int Nx,

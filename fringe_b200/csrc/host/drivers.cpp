@@ -442,3 +442,95 @@ int despeck_process(despeckOptions* opts) {
     wout.close_file();
     return 0;
 }
+
+// =====================================================================================================
+// ampdispersion_process: src/ampdispersion/ampdispersion.cpp:14-330 -- calibration constants from the
+// band metadata normalised by the reference band, non-overlapping blocks of lines, two Float32 ENVI
+// rasters annotated with N = number of bands.
+int ampdispersion_process(ampdispersionOptions* opts) {
+    opts->print();
+    Raster in;
+    if (!in.open(opts->inputDS)) {
+        std::cout << "Cannot open stack file { " << opts->inputDS << " } for reading: " << in.error << "\nExiting with error code .... (102) \n";
+        return 102;
+    }
+    const int cols = in.cols, rows = in.rows, nbands = in.count();
+    std::cout << "Number of rows  = " << rows << "\nNumber of cols  = " << cols << "\nNumber of bands = " << nbands << "\n";
+    // block height: the reference keeps one band of a block in memory at a time (ampdispersion.cpp:56), this
+    // driver all of them (pinned, 8 bytes per band and pixel + the two outputs); blocks do not overlap, so
+    // the height has no influence on the result
+    int blockysize = int((opts->memsize * 1.0e6) / cols) / (opts->blocksize * (8 * nbands + 8)) * opts->blocksize;
+    if (blockysize < opts->blocksize) blockysize = opts->blocksize;
+    if (blockysize > rows) blockysize = rows;
+    std::cout << "Block size = " << blockysize << " lines \n";
+    std::cout << "Total number of blocks to process: " << (rows + blockysize - 1) / blockysize << "\n";
+
+    std::vector<double> alpha(nbands, 1.0);
+    for (int b = 0; b < nbands; ++b) {
+        double c = 0.0;
+        if (!in.bands.empty()) {
+            auto it = in.bands[b].md_slc.find("amplitudeConstant");
+            if (it != in.bands[b].md_slc.end()) c = std::atof(it->second.c_str());
+        }
+        if (c <= 0.0) { c = 1.0; std::cout << "No calibration constant found for band " << b + 1 << ". Setting to 1.0. \n"; }
+        alpha[b] = c;
+    }
+    if (opts->refband < 1 || opts->refband > nbands) {
+        std::cout << "Reference band number: " << opts->refband << " is invalid \nExiting with non-zero error code .... (102) \n";
+        return 102;
+    }
+    {
+        const double norm = alpha[opts->refband - 1];
+        for (auto& a : alpha) a /= norm;
+        alpha[opts->refband - 1] = 1.0;
+    }
+    for (int b = 0; b < nbands; ++b) std::cout << "Band " << b + 1 << ": " << alpha[b] << "\n";
+    const int ngpu = visible_gpus();
+    if (ngpu <= 0) { std::cout << "No CUDA device available and there is no CPU path.\n"; return 200 + FRINGE_ERR_NO_DEVICE; }
+
+    EnviWriter wda, wmean;
+    if (!wda.create(opts->daDS, cols, rows, 1, 4)) { std::cout << "Could not create ampdisp dataset {" << opts->daDS << "} \nExiting with non-zero error code ... 103 \n"; return 103; }
+    if (!wmean.create(opts->meanampDS, cols, rows, 1, 4)) { std::cout << "Could not create meanamp dataset {" << opts->meanampDS << "} \nExiting with non-zero error code ... 104 \n"; return 104; }
+    wda.set_metadata("N", std::to_string(nbands));
+    wmean.set_metadata("N", std::to_string(nbands));
+
+    std::vector<Block> sched;
+    for (int yoff = 0; yoff < rows; yoff += blockysize) sched.push_back({yoff, std::min(blockysize, rows - yoff), 0, std::min(blockysize, rows - yoff)});
+    std::atomic<size_t> next(0);
+    std::atomic<int> rc(0);
+    std::mutex log_mu;
+    auto worker = [&](int dev) {
+        fringe_ctx* ctx = nullptr;
+        if (fringe_create(dev, &ctx) != FRINGE_OK) { rc = 200 + FRINGE_ERR_NO_DEVICE; return; }
+        const size_t bp = (size_t)cols * blockysize;
+        Pinned slc, da, mean;
+        if (!slc.alloc(bp * nbands * 8) || !da.alloc(bp * 4) || !mean.alloc(bp * 4)) { rc = 200 + FRINGE_ERR_MEMORY; fringe_destroy(ctx); return; }
+        for (size_t i = next++; i < sched.size() && rc == 0; i = next++) {
+            const Block& b = sched[i];
+            const size_t np = (size_t)cols * b.inysize;
+            bool ok = true;
+            for (int band = 0; band < nbands && ok; ++band)
+                ok = in.read_band_lines(band, b.yoff, b.inysize, (char*)slc.p + (size_t)band * np * 8, 8);
+            if (!ok) { std::lock_guard<std::mutex> g(log_mu); std::cout << "Error reading data at line " << b.yoff << "\nExiting with error code .... (108) \n"; rc = 108; break; }
+            const int stt = fringe_ampdispersion_block(ctx, (const float*)slc.p, alpha.data(), cols, b.inysize, nbands, (float*)da.p, (float*)mean.p);
+            if (stt != FRINGE_OK) {
+                std::lock_guard<std::mutex> g(log_mu);
+                std::cout << "Device error: " << fringe_last_error(ctx) << "\n";
+                rc = 200 + stt; break;
+            }
+            if (!wda.write_lines(b.yoff, b.inysize, da.p)) { rc = 109; break; }
+            if (!wmean.write_lines(b.yoff, b.inysize, mean.p)) { rc = 110; break; }
+        }
+        fringe_destroy(ctx);
+    };
+    {
+        std::vector<std::thread> th;
+        const int nw = (int)std::min<size_t>(ngpu, sched.size());
+        for (int d = 0; d < nw; ++d) th.emplace_back(worker, d);
+        for (auto& t : th) t.join();
+    }
+    if (rc != 0) return rc;
+    wda.close_file();
+    wmean.close_file();
+    return 0;
+}

@@ -88,6 +88,25 @@ struct despeckOptions {
     }
 };
 
+// src/ampdispersion/ampdispersion.hpp:19-46
+struct ampdispersionOptions {
+    std::string inputDS;     // input VRT with SLCs as bands
+    std::string meanampDS;   // output mean normalised amplitude
+    std::string daDS;        // output amplitude dispersion
+    int blocksize, memsize;
+    int refband;             // 1-based reference band of the calibration constants
+
+    ampdispersionOptions() : blocksize(64), memsize(256), refband(1) {}
+    void print() const {
+        std::cout << "Input Dataset: " << inputDS << std::endl;
+        std::cout << "Dispersion Dataset: " << daDS << std::endl;
+        std::cout << "Mean amplitude Dataset: " << meanampDS << std::endl;
+        std::cout << "Memsize: " << memsize << " Mb \n";
+        std::cout << "Blocksize: " << blocksize << " lines \n";
+        std::cout << "Reference band: " << refband << " \n";
+    }
+};
+
 // Block drivers (drivers.cpp).  Return 0 or the reference's error codes
 // (nmap: 1,102,104,105,106,108,111; evd: 101,102,105-110,112-121), plus 200+status when the
 // device library reports an error (there is no CPU fallback).
@@ -95,3 +114,4 @@ int nmap_process(nmapOptions* opts);
 int evd_process(evdOptions* opts);            // src/evd/evd.cpp control flow
 int phase_link_process(evdOptions* opts);     // src/phase_link/phase_link.cpp control flow
 int despeck_process(despeckOptions* opts);    // src/despeck/despeck.cpp: 102, 104-110, 200+status
+int ampdispersion_process(ampdispersionOptions* opts);   // src/ampdispersion/ampdispersion.cpp: 102-104, 108-110

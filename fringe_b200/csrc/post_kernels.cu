@@ -157,4 +157,42 @@ cudaError_t launch_despeck(const float2* z1, const float2* z2, const uint32_t* w
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------
+// ampdispersion: mean calibrated amplitude and amplitude dispersion of every
+// pixel over the stack, src/ampdispersion/ampdispersion.cpp:207-247.  One thread per pixel streams
+// the band-major planes (coalesced 8-byte loads), sums in double in band order with the reference's
+// operation sequence, no contraction: HBM-bound, 8 N bytes in, 8 bytes out per pixel.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ampdispersion(const float2* __restrict__ slc, const double* __restrict__ alpha,
+                                                       long npix, int bands, float* __restrict__ da,
+                                                       float* __restrict__ meanamp) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    double mean = 0.0, meansq = 0.0, norms = 0.0;
+    for (int b = 0; b < bands; ++b) {
+        double absval = (double)hypotf_exact(__ldg(slc + (long)b * npix + i));
+        const int valid = (absval != 0.0);
+        absval = __dmul_rn(absval, __ddiv_rn((double)valid, alpha ? alpha[b] : 1.0));
+        mean = __dadd_rn(mean, absval);
+        meansq = __dadd_rn(meansq, __dmul_rn(absval, absval));
+        norms += (double)valid;
+    }
+    float m = 0.f, d = -1.f;
+    if (norms > 1.0) {
+        const double avg = __ddiv_rn(mean, norms), avg2 = __ddiv_rn(meansq, norms);
+        const double sdev = __dsqrt_rn(__dsub_rn(avg2, __dmul_rn(avg, avg)));
+        m = (float)avg;
+        d = (float)((!isnan(sdev) && sdev > 0.0) ? __ddiv_rn(sdev, avg) : -1.0);
+    }
+    meanamp[i] = m;
+    da[i] = d;
+}
+
+cudaError_t launch_ampdispersion(const float2* slc, const double* alpha, long npix, int bands, float* da, float* meanamp,
+                                 cudaStream_t st) {
+    if (npix <= 0) return cudaSuccess;
+    k_ampdispersion<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(slc, alpha, npix, bands, da, meanamp);
+    return cudaGetLastError();
+}
+
 }  // namespace fringe

@@ -100,7 +100,7 @@ class Context:
         self._check(lib.fringe_evd_stats(self._h, arr))
         return {"pixels": arr[0], "power_iterations": arr[1], "fp64_pixels": arr[2], "capped": arr[3]}
 
-    KERNELS = {"amp_sort": 0, "nmap": 1, "transpose": 2, "evd": 3, "cmul": 4, "despeck": 5}
+    KERNELS = {"amp_sort": 0, "nmap": 1, "transpose": 2, "evd": 3, "cmul": 4, "despeck": 5, "ampdispersion": 6}
 
     def last_kernel_ms(self, kernel: str) -> float:
         ms = C.c_float(0)
@@ -181,6 +181,31 @@ class Context:
             int(min_neighbors), count.ctypes.data if want_mask else None,
             wts.ctypes.data if want_mask else None, out.ctypes.data, tcorr.ctypes.data, comp.ctypes.data))
         return count, wts, out, tcorr, comp
+
+    def ampdispersion_block(self, slc, alpha=None):
+        """slc (bands, lines, cols) complex64 -> amplitude dispersion, mean amplitude (float32 each)."""
+        slc = np.ascontiguousarray(slc, np.complex64)
+        bands, lines, cols = slc.shape
+        alpha_p = None
+        if alpha is not None:
+            alpha = np.ascontiguousarray(alpha, np.float64)
+            alpha_p = alpha.ctypes.data
+        da = np.empty((lines, cols), np.float32)
+        mean = np.empty((lines, cols), np.float32)
+        self._check(lib.fringe_ampdispersion_block(self._h, slc.ctypes.data, alpha_p, cols, lines, bands,
+                                                   da.ctypes.data, mean.ctypes.data))
+        return da, mean
+
+    def ampdispersion_block_device(self, slc, alpha=None):
+        import torch
+        assert slc.is_cuda and slc.dtype == torch.complex64 and slc.is_contiguous()
+        bands, lines, cols = slc.shape
+        da = torch.empty((lines, cols), dtype=torch.float32, device=slc.device)
+        mean = torch.empty_like(da)
+        self._check(lib.fringe_ampdispersion_block_device(
+            self._h, slc.data_ptr(), None if alpha is None else alpha.data_ptr(), cols, lines, bands,
+            da.data_ptr(), mean.data_ptr(), self._stream()))
+        return da, mean
 
     def despeck_block(self, z1, wts, Nx, Ny, z2=None, coherence=False, first_line=0, n_lines=None):
         """SHP-weighted average (``fringe_despeck_block``): z1 [, z2] (lines, cols) complex64 -> complex64."""

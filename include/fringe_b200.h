@@ -151,6 +151,17 @@ int fringe_cmul(fringe_ctx* ctx, const float* a, const float* b, int64_t n, floa
 int fringe_cmul_device(fringe_ctx* ctx, const float* a, const float* b, int64_t n, float* out,
                        void* stream);
 
+/* ---- amplitude dispersion -----------------------------------------------------------------
+ * Mean calibrated amplitude and amplitude dispersion (sigma / mean over the dates with non-zero
+ * amplitude; -1 where fewer than two dates are valid or sigma is not positive) of every pixel of
+ * a block; replaces the loops src/ampdispersion/ampdispersion.cpp:207-247.  alpha: [bands]
+ * calibration constants already normalised by the reference band (:119-127), NULL = all 1.
+ * da, meanamp: float32 [lines*cols], the values the reference writes to its two Float32 rasters. */
+int fringe_ampdispersion_block(fringe_ctx* ctx, const float* slc, const double* alpha, int cols, int lines,
+                               int bands, float* da, float* meanamp);
+int fringe_ampdispersion_block_device(fringe_ctx* ctx, const float* slc, const double* alpha, int cols,
+                                      int lines, int bands, float* da, float* meanamp, void* stream);
+
 /* ---- despeck: SHP-weighted average ----------------------------------------------------------
  * One block of `lines` lines; replaces the preparation and pixel loops of
  * src/despeck/despeck.cpp:321-361 and :387-432.  z1, z2: the two bands ([lines*cols] complex64) the
@@ -181,7 +192,8 @@ enum {
     FRINGE_KERNEL_EVD = 3,        /* covariance + eigen + post-processing */
     FRINGE_KERNEL_CMUL = 4,       /* datum adjustment product */
     FRINGE_KERNEL_DESPECK = 5,    /* despeck preparation + SHP-weighted average */
-    FRINGE_KERNEL_COUNT = 6
+    FRINGE_KERNEL_AMPDISP = 6,    /* amplitude dispersion */
+    FRINGE_KERNEL_COUNT = 7
 };
 int fringe_last_kernel_ms(fringe_ctx* ctx, int kernel, float* ms);
 /* FP32 FMA throughput of the device measured with a register-resident FMA loop; the roofline

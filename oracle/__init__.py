@@ -72,6 +72,7 @@ class Oracle:
         lib.oracle_pd_inverse.argtypes = [dp, C.c_int]
         lib.oracle_nmap_block.argtypes = [fp, u8, dp] + [C.c_int] * 6 + [C.c_double, i32, u32, fp]
         lib.oracle_evd_block.argtypes = [fp, u32] + [C.c_int] * 12 + [fp, fp, fp, i32]
+        lib.oracle_ampdispersion_block.argtypes = [fp, dp, C.c_int, C.c_int, C.c_int, fp, fp]
         lib.oracle_despeck_block.argtypes = [fp, fp, u32] + [C.c_int] * 7 + [fp]
         lib.oracle_cmul.argtypes = [fp, fp, C.c_long, fp]
         lib.oracle_cmul.restype = None
@@ -175,6 +176,19 @@ class Oracle:
         if rc != 0:
             raise RuntimeError(f"oracle_evd_block rc={rc}")
         return (out, tcorr, comp, npix) if want_npix else (out, tcorr, comp)
+
+    def ampdispersion_block(self, slc, alpha=None):
+        """slc (bands, lines, cols) complex64 -> amplitude dispersion, mean amplitude (float32 each)."""
+        slc = np.ascontiguousarray(slc, np.complex64)
+        bands, lines, cols = slc.shape
+        if alpha is not None:
+            alpha = np.ascontiguousarray(alpha, np.float64)
+        da = np.empty((lines, cols), np.float32)
+        mean = np.empty((lines, cols), np.float32)
+        rc = self.lib.oracle_ampdispersion_block(self._p(slc.view(np.float32), C.c_float), self._p(alpha, C.c_double),
+                                                 cols, lines, bands, self._p(da, C.c_float), self._p(mean, C.c_float))
+        assert rc == 0
+        return da, mean
 
     def despeck_block(self, z1, wts, Nx, Ny, z2=None, coherence=False, first_line=0, n_lines=None):
         """SHP-weighted average (src/despeck/despeck.cpp): z1 [, z2] (lines, cols) complex64 -> complex64."""

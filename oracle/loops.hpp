@@ -355,4 +355,42 @@ int despeck_block(const cfloat* z1, const cfloat* z2, const uint32_t* wts, int c
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------
+// ampdispersion: per-pixel mean calibrated amplitude and amplitude dispersion over the stack.
+// src/ampdispersion/ampdispersion.cpp:207-247 (sums band by band in double, then the statistics);
+// alpha = calibration constants already normalised by the reference band (:119-127).  Outputs are
+// the doubles the reference hands to GDAL for its Float32 rasters, converted here.
+// ---------------------------------------------------------------------------------------
+inline int ampdispersion_block(const cfloat* slc, const double* alpha, int cols, int lines, int bands, float* da,
+                               float* meanamp) {
+    const long n = (long)cols * lines;
+    std::vector<double> mean(n, 0.0), meansq(n, 0.0), norms(n, 0.0);
+    for (int bb = 0; bb < bands; ++bb) {
+        const double al = alpha ? alpha[bb] : 1.0;
+        for (long ii = 0; ii < n; ++ii) {
+            volatile double absval = std::abs(slc[(long)bb * n + ii]);
+            const int valid = (absval != 0.0);
+            absval *= (valid / al);
+            volatile double sq = absval * absval;          // volatile: no contraction into the sums
+            mean[ii] += absval;
+            meansq[ii] += sq;
+            norms[ii] += valid;
+        }
+    }
+    for (long ii = 0; ii < n; ++ii) {
+        if (norms[ii] > 1) {
+            const double avg = mean[ii] / norms[ii];
+            const double avg2 = meansq[ii] / norms[ii];
+            volatile double a2 = avg * avg;
+            const double sdev = ::sqrt(avg2 - a2);
+            meanamp[ii] = (float)avg;
+            da[ii] = (float)(((!std::isnan(sdev)) && (sdev > 0)) ? (sdev / avg) : -1);
+        } else {
+            meanamp[ii] = 0.0f;
+            da[ii] = -1.0f;
+        }
+    }
+    return 0;
+}
+
 }  // namespace oracle

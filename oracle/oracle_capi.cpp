@@ -100,6 +100,11 @@ int oracle_evd_block(const float* slc, const uint32_t* wts, int cols, int lines,
                                    reinterpret_cast<oracle::cfloat*>(comp), npix);
 }
 
+int oracle_ampdispersion_block(const float* slc, const double* alpha, int cols, int lines, int bands, float* da,
+                               float* meanamp) {
+    return oracle::ampdispersion_block((const oracle::cfloat*)slc, alpha, cols, lines, bands, da, meanamp);
+}
+
 int oracle_despeck_block(const float* z1, const float* z2, const uint32_t* wts, int cols, int lines, int Nx, int Ny,
                          int first_line, int n_lines, int compute_coherence, float* out) {
     return oracle::despeck_block<Impl>((const oracle::cfloat*)z1, (const oracle::cfloat*)z2, wts, cols, lines, Nx, Ny,

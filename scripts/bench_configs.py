@@ -65,3 +65,12 @@ for coh in (False, True):
     npx = z1.numel()
     print(f"despeck coherence={coh}: {npx / 1e6:.1f} M pixels {t:.3f} ms = {npx / t / 1e3:.0f} M px/s, "
           f"{npx * (16 + 8 + 8) / t / 1e6:.0f} GB/s of the 32 algorithmic B/pixel (2 bands in, mask, 1 out)", flush=True)
+
+# ampdispersion: one streaming pass, 8 N + 8 bytes per pixel
+for _ in range(3):
+    da, mean = ctx.ampdispersion_block_device(slc)
+    torch.cuda.synchronize()
+t = ctx.last_kernel_ms("ampdispersion")
+npx = slc.shape[1] * slc.shape[2]
+print(f"ampdispersion: 30 dates {npx / 1e6:.1f} M pixels {t:.3f} ms = {npx / t / 1e3:.0f} M px/s, "
+      f"{npx * (8 * 30 + 8) / t / 1e6:.0f} GB/s (algorithmic 248 B/pixel)", flush=True)
