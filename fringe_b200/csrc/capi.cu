@@ -374,6 +374,30 @@ int chunk_rows(int cols, int bands, int total_rows) {
     return r;
 }
 
+// Row boundaries of the pipeline stages over [begin, end): full stages of `step` rows in the middle,
+// a ramp of quarter and half stages at both ends, so that the first upload and the last download -- the
+// two transfers nothing overlaps with -- are short.
+std::vector<int> chunk_plan(int begin, int end, int step) {
+    std::vector<int> cuts{begin};
+    const int total = end - begin;
+    if (total <= 0) return cuts;
+    const int q = std::max(1, step / 4), h = std::max(1, step / 2);
+    if (total < 3 * step) {                                  // too short for a ramp: plain stages
+        for (int r = begin + step; r < end; r += step) cuts.push_back(r);
+        cuts.push_back(end);
+        return cuts;
+    }
+    int r = begin;
+    r += q; cuts.push_back(r);
+    r += h; cuts.push_back(r);
+    const int tail = q + h;
+    while (end - r - tail > step) { r += step; cuts.push_back(r); }
+    if (end - r > tail) { r = end - tail; cuts.push_back(r); }
+    r = end - q; cuts.push_back(r);
+    cuts.push_back(end);
+    return cuts;
+}
+
 }  // namespace
 
 int fringe_nmap_block_device(fringe_ctx* ctx, const float* slc, const uint8_t* mask, const double* alpha,
@@ -660,12 +684,12 @@ int fringe_nmap_evd_block(fringe_ctx* ctx, const float* slc, const uint8_t* mask
         dalpha = (const double*)ctx->alpha.p;
     }
     CU(cudaMemsetAsync(ctx->o_wts.p, 0, npix * nu * sizeof(uint32_t), st));
-    const int step = chunk_rows(cols, bands, lines);
+    const std::vector<int> cuts = chunk_plan(0, lines, chunk_rows(cols, bands, lines));
     const int last = first_line + n_lines;
     int uploaded = 0;
     size_t ev = 0;
-    for (int r0 = 0; r0 < lines; r0 += step) {
-        const int r1 = std::min(lines, r0 + step);
+    for (size_t ci = 0; ci + 1 < cuts.size(); ++ci) {
+        const int r0 = cuts[ci], r1 = cuts[ci + 1];
         const int need = std::min(lines, r1 + Ny);
         const int s0 = uploaded, sn = need - uploaded;
         if (sn > 0) {
