@@ -1,40 +1,30 @@
 #!/usr/bin/env python3
-"""ampdispersion.py -- same command line as src/ampdispersion/ampdispersion.py:6-30 (defaults included)."""
-import argparse
-import os
+"""Amplitude dispersion from the command line: options of src/ampdispersion/ampdispersion.py:6-30, work done
+by ampdispersionlib.Ampdispersion."""
+from ._common import BLOCK_LINES, REQUIRED, build_parser, configure, ensure_parent, ram, use_bindings
 
-from ._common import use_bindings
+OPTIONS = [
+    ('-i', '--input', 'inputDS', str, REQUIRED, 'stack VRT, one band per acquisition'),
+    ('-o', '--output', 'outputDS', str, REQUIRED, 'amplitude dispersion raster to write'),
+    ('-m', '--mean', 'meanampDS', str, '', 'mean amplitude raster to write'),
+    BLOCK_LINES, ram(256),
+    ('-b', '--band', 'refBand', int, 1, 'band whose calibration constant the others are divided by'),
+]
+WIRING = {'inputDS': 'inputDS', 'outputDS': 'outputDS', 'meanampDS': 'meanampDS', 'blocksize': 'linesPerBlock',
+          'memsize': 'memorySize', 'refband': 'refBand'}
 
 
 def cmdLineParser(argv=None):
-    parser = argparse.ArgumentParser(description='Compute amplitude dispersion and mean amplitude of a stack of coregistered SLCs',
-                                     formatter_class=argparse.ArgumentDefaultsHelpFormatter)
-    parser.add_argument('-i', '--input', type=str, dest='inputDS', required=True, help='Input GDAL SLC stack VRT')
-    parser.add_argument('-o', '--output', type=str, dest='outputDS', required=True, help='Output amplitude dispersion dataset')
-    parser.add_argument('-m', '--mean', type=str, dest='meanampDS', default='', help='Output mean amplitude')
-    parser.add_argument('-l', '--linesperblock', type=int, dest='linesPerBlock', default=64, help='Quantum for block of lines')
-    parser.add_argument('-r', '--ram', type=int, dest='memorySize', default=256, help='Memory in Mb to use')
-    parser.add_argument('-b', '--band', type=int, dest='refBand', default=1, help='Reference band to use for relative normalization')
-    return parser.parse_args(argv)
-
-
-def runAmpdispersion(inps):
-    use_bindings()
-    import ampdispersionlib
-    aa = ampdispersionlib.Ampdispersion()
-    aa.inputDS = inps.inputDS
-    aa.outputDS = inps.outputDS
-    aa.meanampDS = inps.meanampDS
-    aa.blocksize = inps.linesPerBlock
-    aa.memsize = inps.memorySize
-    aa.refband = inps.refBand
-    aa.run()
+    return build_parser('Mean calibrated amplitude and amplitude dispersion of every pixel of an SLC stack',
+                        OPTIONS).parse_args(argv)
 
 
 def main(argv=None):
     inps = cmdLineParser(argv)
-    os.makedirs(os.path.abspath(os.path.dirname(inps.outputDS)), exist_ok=True)
-    runAmpdispersion(inps)
+    ensure_parent(inps.outputDS)
+    use_bindings()
+    import ampdispersionlib
+    configure(ampdispersionlib.Ampdispersion(), inps, WIRING).run()
 
 
 if __name__ == '__main__':

@@ -1,56 +1,41 @@
 #!/usr/bin/env python3
-"""despeck.py -- same command line as src/despeck/despeck.py:6-33 (defaults included)."""
-import argparse
-import os
+"""SHP-weighted multilooking from the command line: options of src/despeck/despeck.py:6-33, work done by
+despecklib.Despeck."""
+from ._common import BLOCK_LINES, REQUIRED, WINDOW_X, WINDOW_Y, build_parser, configure, ensure_parent, ram, use_bindings
 
-from ._common import use_bindings
+OPTIONS = [
+    ('-i', '--input', 'inputDS', str, REQUIRED, 'stack VRT, one band per acquisition'),
+    ('-o', '--output', 'outputDS', str, REQUIRED, 'filtered raster to write'),
+    ('-w', '--wts', 'wtsDS', str, REQUIRED, 'neighbourhood bit mask written by nmap'),
+    BLOCK_LINES, ram(512), WINDOW_X, WINDOW_Y,
+    ('-b', '--band', 'bands', 'ints', (), 'one band (its amplitude) or two (their interferogram), counted from 1'),
+    ('-c', '--corr', 'cohFlag', 'flag', None, 'normalise the interferogram to a coherence'),
+]
+WIRING = {'inputDS': 'inputDS', 'weightsDS': 'wtsDS', 'outputDS': 'outputDS', 'blocksize': 'linesPerBlock',
+          'memsize': 'memorySize', 'halfWindowX': 'halfWindowX', 'halfWindowY': 'halfWindowY'}
 
 
 def cmdLineParser(argv=None):
-    parser = argparse.ArgumentParser(description='Despeckle an amplitude or interferogram using a neighbourhood mask',
-                                     formatter_class=argparse.ArgumentDefaultsHelpFormatter)
-    parser.add_argument('-i', '--input', type=str, dest='inputDS', required=True, help='Input GDAL SLC stack VRT')
-    parser.add_argument('-o', '--output', type=str, dest='outputDS', required=True, help='Output despeckled dataset')
-    parser.add_argument('-w', '--wts', type=str, dest='wtsDS', required=True, help='Input neighborhood weights mask')
-    parser.add_argument('-l', '--linesperblock', type=int, dest='linesPerBlock', default=64, help='Quantum for block of lines')
-    parser.add_argument('-r', '--ram', type=int, dest='memorySize', default=512, help='Memory in Mb to use')
-    parser.add_argument('-x', '--xhalf', type=int, dest='halfWindowX', default=5, help='Half window size (range)')
-    parser.add_argument('-y', '--yhalf', type=int, dest='halfWindowY', default=5, help='Half window size (azimuth)')
-    parser.add_argument('-b', '--band', type=int, dest='bands', nargs='*', default=[],
-                        help='One band (amplitude) or two bands (interferogram), 1-based')
-    parser.add_argument('-c', '--corr', action='store_true', dest='cohFlag', default=False, help='Compute coherence as well')
-    return parser.parse_args(argv)
-
-
-def runDespeck(inps):
-    use_bindings()
-    import despecklib
-    aa = despecklib.Despeck()
-    aa.inputDS = inps.inputDS
-    aa.weightsDS = inps.wtsDS
-    aa.outputDS = inps.outputDS
-    aa.blocksize = inps.linesPerBlock
-    aa.memsize = inps.memorySize
-    aa.halfWindowX = inps.halfWindowX
-    aa.halfWindowY = inps.halfWindowY
-    if len(inps.bands) == 1:
-        aa.band1 = inps.bands[0]
-        if inps.cohFlag:
-            raise Exception('User requested coherence when requesting despeckling of SLC magnitude')
-    elif len(inps.bands) == 2:
-        aa.band1 = inps.bands[0]
-        aa.band2 = inps.bands[1]
-        aa.coherenceFlag = inps.cohFlag
-    elif len(inps.bands) != 0:
-        raise Exception('Despeck can handle one or two bands. More than two bands provided')
-    aa.run()
+    return build_parser('Average an amplitude or an interferogram over each pixel\'s homogeneous neighbours',
+                        OPTIONS).parse_args(argv)
 
 
 def main(argv=None):
     inps = cmdLineParser(argv)
-    outDir = os.path.abspath(os.path.dirname(inps.outputDS))
-    os.makedirs(outDir, exist_ok=True)
-    runDespeck(inps)
+    if len(inps.bands) > 2:
+        raise Exception('Despeck can handle one or two bands. More than two bands provided')
+    if len(inps.bands) == 1 and inps.cohFlag:
+        raise Exception('User requested coherence when requesting despeckling of SLC magnitude')
+    ensure_parent(inps.outputDS)
+    use_bindings()
+    import despecklib
+    job = configure(despecklib.Despeck(), inps, WIRING)
+    if inps.bands:
+        job.band1 = inps.bands[0]
+    if len(inps.bands) == 2:
+        job.band2 = inps.bands[1]
+        job.coherenceFlag = inps.cohFlag
+    job.run()
 
 
 if __name__ == '__main__':

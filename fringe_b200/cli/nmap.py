@@ -1,53 +1,35 @@
 #!/usr/bin/env python3
-"""nmap.py -- same command line as src/nmap/nmap.py:6-36 (defaults included)."""
-import argparse
-import os
+"""SHP selection from the command line: options of src/nmap/nmap.py:6-36, work done by nmaplib.Nmap."""
+from ._common import BLOCK_LINES, REQUIRED, WINDOW_X, WINDOW_Y, build_parser, configure, ensure_parent, ram, use_bindings
 
-from ._common import use_bindings
+OPTIONS = [
+    ('-i', '--input', 'inputDS', str, REQUIRED, 'stack VRT, one band per acquisition'),
+    ('-o', '--output', 'outputDS', str, REQUIRED, 'neighbourhood bit mask to write (UInt32 BIP)'),
+    ('-c', '--count', 'countDS', str, REQUIRED, 'neighbour count raster to write'),
+    ('-m', '--mask', 'maskDS', str, '', 'byte raster; pixels that are 0 there are skipped'),
+    BLOCK_LINES, ram(256), WINDOW_X, WINDOW_Y,
+    ('-p', '--prob', 'pValue', float, 0.05, 'two pixels are neighbours when the test p-value is at least this'),
+    ('-s', '--stat', 'method', str, 'KS2', 'two-sample test: KS2 or AD2'),
+    (None, '--nogpu', 'noGPU', 'flag', None, 'kept for compatibility; there is no CPU path'),
+]
+WIRING = {'inputDS': 'inputDS', 'weightsDS': 'outputDS', 'countDS': 'countDS', 'blocksize': 'linesPerBlock',
+          'memsize': 'memorySize', 'halfWindowX': 'halfWindowX', 'halfWindowY': 'halfWindowY',
+          'minimumProbability': 'pValue', 'method': lambda a: a.method.upper(), 'noGPU': 'noGPU'}
 
 
 def cmdLineParser(argv=None):
-    parser = argparse.ArgumentParser(description='Create neighborhood mask and count map using KS statistics for stack of coregistered SLCs',
-                                     formatter_class=argparse.ArgumentDefaultsHelpFormatter)
-    parser.add_argument('-i', '--input', type=str, dest='inputDS', required=True, help='Input GDAL SLC stack VRT')
-    parser.add_argument('-o', '--output', type=str, dest='outputDS', required=True, help='Output neighborhood weights mask')
-    parser.add_argument('-c', '--count', type=str, dest='countDS', required=True, help='Output count dataset')
-    parser.add_argument('-m', '--mask', type=str, dest='maskDS', default='', help='Optional mask layer to speed up computation')
-    parser.add_argument('-l', '--linesperblock', type=int, dest='linesPerBlock', default=64, help='Quantum for block of lines')
-    parser.add_argument('-r', '--ram', type=int, dest='memorySize', default=256, help='Memory in Mb to use')
-    parser.add_argument('-x', '--xhalf', type=int, dest='halfWindowX', default=5, help='Half window size (range)')
-    parser.add_argument('-y', '--yhalf', type=int, dest='halfWindowY', default=5, help='Half window size (azimuth)')
-    parser.add_argument('-p', '--prob', type=float, dest='pValue', default=0.05, help='Minimum p-value for labeling neighbors.')
-    parser.add_argument('-s', '--stat', type=str, dest='method', default='KS2', help='Statistical test to use - KS2 or AD2')
-    parser.add_argument('--nogpu', dest='noGPU', action='store_true', default=False,
-                        help='Accepted for compatibility; this implementation has no CPU path')
-    return parser.parse_args(argv)
-
-
-def runNmap(inps):
-    use_bindings()
-    import nmaplib
-    aa = nmaplib.Nmap()
-    aa.inputDS = inps.inputDS
-    aa.weightsDS = inps.outputDS
-    aa.countDS = inps.countDS
-    if inps.maskDS:
-        aa.maskDS = inps.maskDS
-    aa.blocksize = inps.linesPerBlock
-    aa.memsize = inps.memorySize
-    aa.halfWindowX = inps.halfWindowX
-    aa.halfWindowY = inps.halfWindowY
-    aa.minimumProbability = inps.pValue
-    aa.method = inps.method.upper()
-    aa.noGPU = inps.noGPU
-    aa.run()
+    return build_parser('Neighbourhood mask and neighbour count of a coregistered SLC stack', OPTIONS).parse_args(argv)
 
 
 def main(argv=None):
     inps = cmdLineParser(argv)
-    outDir = os.path.abspath(os.path.dirname(inps.outputDS))
-    os.makedirs(outDir, exist_ok=True)
-    runNmap(inps)
+    ensure_parent(inps.outputDS)
+    use_bindings()
+    import nmaplib
+    job = configure(nmaplib.Nmap(), inps, WIRING)
+    if inps.maskDS:
+        job.maskDS = inps.maskDS
+    job.run()
 
 
 if __name__ == '__main__':

@@ -1,184 +1,144 @@
 #!/usr/bin/env python3
-"""sequential.py -- the ministack estimator of src/sequential/sequential.py:144-254 with the Stack /
-MiniStack helpers of src/sequential/Stack.py, minus GDAL: sizes come from the .vrt / .hdr files and
-the compressed-SLC VRTs are written directly instead of shelling out to gdal_translate.
+"""Sequential (ministack) estimator from the command line.
 
-Layout produced (identical): <out>/fullStack/, <out>/miniStacks/<start>_<end>/EVD/{<Date>.slc,tcorr.bin},
-<out>/compressedSlc/<lastdate>/<lastdate>.slc(+.vrt), <out>/Datum_connection/EVD/.
+Behaviour and on-disk layout of src/sequential/sequential.py:144-254 with the stack bookkeeping of
+src/sequential/Stack.py, minus GDAL (sizes come from the .vrt / .hdr files, the compressed-SLC VRTs are
+written directly):
+
+    <out>/fullStack/{slcs,stack}/                    VRTs of the input SLCs
+    <out>/miniStacks/<first>_<last>/{slcs,stack,EVD}/ one folder per ministack; EVD/<date>.slc, tcorr.bin
+    <out>/compressedSlc/<last>/<last>.slc(+.vrt)     compressed SLC of each ministack
+    <out>/Datum_connection/{slcs,stack,EVD}/         EVD over all compressed SLCs
+
+Ministack k links (k-1) compressed SLCs followed by its own acquisitions with miniStackCount = k and the
+binding's default method (MLE); the datum connection runs with miniStackCount = 1.
 """
-import argparse
 import glob
 import os
+import shutil
 
-from ._common import use_bindings
+from ._common import BLOCK_LINES, REQUIRED, build_parser, ram, use_bindings
 from .. import stackio
+
+OPTIONS = [
+    ('-i', '--inDir', 'inputDir', str, REQUIRED, 'folder with one sub-folder per acquisition date holding <date>.slc'),
+    ('-w', '--weight_dataset', 'weightDS', str, REQUIRED, 'neighbourhood bit mask written by nmap'),
+    ('-o', '--outDir', 'outputDir', str, REQUIRED, 'folder for everything this run produces'),
+    BLOCK_LINES, ram(2048),
+    ('-x', '--xhalf', 'halfWindowX', int, 29, 'half width of the SHP window in range pixels'),
+    ('-y', '--yhalf', 'halfWindowY', int, 9, 'half height of the SHP window in azimuth lines'),
+    ('-m', '--minneigh', 'minNeighbors', int, 5, 'pixels with fewer neighbours are left empty'),
+    ('-s', '--mini_stack_size', 'miniStackSize', int, 10, 'acquisitions per ministack'),
+    ('-f', '--force', 'forceprocessing', 'flag', None, 'redo ministacks whose folder already exists'),
+]
 
 
 def cmdLineParser(argv=None):
-    parser = argparse.ArgumentParser(description='Perform MLE-based phase-linking on a stack of coregistered SLCs',
-                                     formatter_class=argparse.ArgumentDefaultsHelpFormatter)
-    parser.add_argument('-i', '--inDir', type=str, dest='inputDir', required=True, help='Input folder which contains folders for each SLC')
-    parser.add_argument('-w', '--weight_dataset', type=str, dest='weightDS', required=True, help='Input weights dataset')
-    parser.add_argument('-o', '--outDir', type=str, dest='outputDir', required=True, help='Output folder')
-    parser.add_argument('-l', '--linesperblock', type=int, dest='linesPerBlock', default=64, help='Quantum for block of lines')
-    parser.add_argument('-r', '--ram', type=int, dest='memorySize', default=2048, help='Memory in Mb to use')
-    parser.add_argument('-x', '--xhalf', type=int, dest='halfWindowX', default=29, help='Half window size (range)')
-    parser.add_argument('-y', '--yhalf', type=int, dest='halfWindowY', default=9, help='Half window size (azimuth)')
-    parser.add_argument('-m', '--minneigh', type=int, dest='minNeighbors', default=5, help='Minimum number of neighbors for computation')
+    parser = build_parser('Phase linking of a long SLC stack in ministacks with compressed-SLC hand-off', OPTIONS)
     parser.add_argument('-b', '--bbox', dest='bbox', nargs='+', type=str, default=None,
-                        help='bounding box : minLine maxLine minPixel maxPixel')
-    parser.add_argument('-s', '--mini_stack_size', type=int, dest='miniStackSize', default=10, help='mini stack size')
-    parser.add_argument('-f', '--force', dest='forceprocessing', action='store_true', default=False, help='Force reprocessing')
+                        help='crop: first line, last line, first pixel, last pixel')
     return parser.parse_args(argv)
 
 
-class Stack(object):
-    """src/sequential/Stack.py:36-175"""
-
-    def __init__(self, slcDir=None):
-        self.slcDir = slcDir
-        self.bbox = None
-
-    def configure(self, outDir):
-        self.outSlcVrtDir = os.path.join(outDir, "slcs")
-        self.outStackVrtDir = os.path.join(outDir, "stack")
-        os.makedirs(self.outSlcVrtDir, exist_ok=True)
-        os.makedirs(self.outStackVrtDir, exist_ok=True)
-
-    def gatherSLCs(self):
-        self.slcList = glob.glob(os.path.join(self.slcDir, '*/*.slc'))
-        if len(self.slcList) == 0:
-            self.slcList = glob.glob(os.path.join(self.slcDir, '*/*.slc.full'))
-        print('Number of SLCs discovered: ', len(self.slcList))
-        self.slcList.sort()
-        self.size = len(self.slcList)
-        self.applyBbox = [True] * self.size
-
-    def getSize(self):
-        self.size = len(self.slcList)
-
-    def getDates(self):
-        self.dateList = [os.path.basename(os.path.dirname(slc)) for slc in self.slcList]
-
-    @staticmethod
-    def _size(slc):
-        return stackio.raster_size(slc + '.vrt') if os.path.exists(slc + '.vrt') else stackio.raster_size(slc)
-
-    def get_x_y_offsets(self, ind):
-        width, height = self._size(self.slcList[ind])
-        ymin, ymax, xmin, xmax = 0, height, 0, width
-        if self.bbox and self.applyBbox[ind]:
-            ymin, ymax, xmin, xmax = self.bbox
-        return width, height, xmin, ymin, xmax - xmin, ymax - ymin
-
-    def writeStackVRT(self):
-        dates = []
-        for slc in self.slcList:
-            width, height = self._size(slc)
-            outname = os.path.basename(os.path.dirname(slc))
-            stackio.write_raw_vrt(os.path.join(self.outSlcVrtDir, outname + '.vrt'), slc, width, height)
-            dates.append(outname)
-        self.stackVRT = os.path.join(self.outStackVrtDir, 'stack.vrt')
-        print("writing ", self.stackVRT)
-        with open(self.stackVRT, 'w') as fid:
-            _, _, _, _, xsize, ysize = self.get_x_y_offsets(-1)
-            fid.write('<VRTDataset rasterXSize="{0}" rasterYSize="{1}">\n'.format(xsize, ysize))
-            for ind, date in enumerate(dates):
-                width, height, xmin, ymin, xs, ys = self.get_x_y_offsets(ind)
-                fid.write(stackio.STACK_BAND.format(width=width, height=height, xmin=xmin, ymin=ymin, xsize=xs,
-                                                    ysize=ys, date=date, acq=date, wvl=0.03, index=ind + 1, extra="",
-                                                    path=os.path.abspath(os.path.join(self.outSlcVrtDir, date + '.vrt'))))
-            fid.write('</VRTDataset>')
+def find_slcs(folder):
+    """Sorted <folder>/<date>/<date>.slc (or .slc.full) files; the date is the sub-folder's name."""
+    found = glob.glob(os.path.join(folder, '*/*.slc')) or glob.glob(os.path.join(folder, '*/*.slc.full'))
+    print('Number of SLCs discovered: ', len(found))
+    return sorted(found)
 
 
-class MiniStack(Stack):
-    """src/sequential/Stack.py:177-190; the compressed-SLC list is sorted here (the reference's glob is
-    not, Stack.py:184 -- the result is order-invariant)."""
-
-    def updateMiniStack(self, compressedSlcDir):
-        compSlcList = sorted(glob.glob(os.path.join(compressedSlcDir, '*/*.slc')))
-        self.slcList = compSlcList + self.slcList
-        self.applyBbox = [False] * len(compSlcList) + self.applyBbox
+def date_of(slc):
+    return os.path.basename(os.path.dirname(slc))
 
 
-def runEvd(inps, inputDataset, weightDS, outDir, miniStackCount, compressedSlcDir=None, compressedSlcName=None):
+def _size(slc):
+    return stackio.raster_size(slc + '.vrt') if os.path.exists(slc + '.vrt') else stackio.raster_size(slc)
+
+
+def write_stack(out_dir, slcs, crop, bbox):
+    """Per-date raw VRTs under <out_dir>/slcs and the band-per-date <out_dir>/stack/stack.vrt.
+    crop[i] says whether `bbox` (y0, y1, x0, x1) applies to slcs[i]: compressed SLCs are already cropped."""
+    slc_dir, stack_dir = os.path.join(out_dir, 'slcs'), os.path.join(out_dir, 'stack')
+    os.makedirs(slc_dir, exist_ok=True)
+    os.makedirs(stack_dir, exist_ok=True)
+
+    def window(i):
+        width, height = _size(slcs[i])
+        y0, y1, x0, x1 = bbox if (bbox and crop[i]) else (0, height, 0, width)
+        return width, height, x0, y0, x1 - x0, y1 - y0
+
+    for slc in slcs:
+        width, height = _size(slc)
+        stackio.write_raw_vrt(os.path.join(slc_dir, date_of(slc) + '.vrt'), slc, width, height)
+    stack_vrt = os.path.join(stack_dir, 'stack.vrt')
+    print('writing ', stack_vrt)
+    with open(stack_vrt, 'w') as fid:
+        *_, xsize, ysize = window(len(slcs) - 1)
+        fid.write('<VRTDataset rasterXSize="{0}" rasterYSize="{1}">\n'.format(xsize, ysize))
+        for i, slc in enumerate(slcs):
+            width, height, x0, y0, xs, ys = window(i)
+            date = date_of(slc)
+            fid.write(stackio.STACK_BAND.format(width=width, height=height, xmin=x0, ymin=y0, xsize=xs, ysize=ys,
+                                                date=date, acq=date, wvl=0.03, index=i + 1, extra='',
+                                                path=os.path.abspath(os.path.join(slc_dir, date + '.vrt'))))
+        fid.write('</VRTDataset>')
+    return stack_vrt
+
+
+def link(inps, stack_vrt, out_dir, first_real_band, comp_dir=None, comp_name=None):
+    """One evd run; the estimator stays at the binding's default (MLE), as in the reference."""
     use_bindings()
     import evdlib
-    aa = evdlib.Evd()                      # method stays at the struct default "MLE" (evd.hpp:66)
-    aa.inputDS = inputDataset
-    aa.weightsDS = weightDS
-    aa.outputFolder = outDir
-    aa.miniStackCount = miniStackCount
-    aa.blocksize = inps.linesPerBlock
-    aa.memsize = inps.memorySize
-    aa.halfWindowX = inps.halfWindowX
-    aa.halfWindowY = inps.halfWindowY
-    aa.minimumNeighbors = inps.minNeighbors
-    aa.outputCompressedSlcFolder = compressedSlcDir if compressedSlcDir else aa.outputFolder
-    aa.compSlc = compressedSlcName if compressedSlcName else "compslc.bin"
-    aa.run()
+    job = evdlib.Evd()
+    job.inputDS, job.weightsDS, job.outputFolder = stack_vrt, inps.weightDS, out_dir
+    job.miniStackCount = first_real_band
+    job.blocksize, job.memsize = inps.linesPerBlock, inps.memorySize
+    job.halfWindowX, job.halfWindowY = inps.halfWindowX, inps.halfWindowY
+    job.minimumNeighbors = inps.minNeighbors
+    job.outputCompressedSlcFolder = comp_dir or out_dir
+    job.compSlc = comp_name or 'compslc.bin'
+    job.run()
 
 
 def main(argv=None):
     inps = cmdLineParser(argv)
-    weightDS = inps.weightDS
-    inps.outputDir = os.path.abspath(inps.outputDir)
-    outDir = os.path.join(inps.outputDir, "fullStack")
-    compressedSlcDir = os.path.join(inps.outputDir, "compressedSlc")
-    os.makedirs(compressedSlcDir, exist_ok=True)
+    root = inps.outputDir = os.path.abspath(inps.outputDir)
+    bbox = tuple(int(v) for v in inps.bbox) if inps.bbox is not None else None
+    if bbox:
+        print('input bounding box in (y0, y1, x0, x1): {}'.format(bbox))
+    comp_root = os.path.join(root, 'compressedSlc')
+    os.makedirs(comp_root, exist_ok=True)
 
-    stack = Stack(inps.inputDir)
-    if inps.bbox is not None:
-        inps.bbox = tuple(int(i) for i in inps.bbox)
-        print('input bounding box in (y0, y1, x0, x1): {}'.format(inps.bbox))
-    stack.bbox = inps.bbox
-    stack.gatherSLCs()
-    stack.getDates()
-    stack.configure(outDir)
-    stack.writeStackVRT()
+    slcs = find_slcs(inps.inputDir)
+    write_stack(os.path.join(root, 'fullStack'), slcs, [True] * len(slcs), bbox)
 
-    miniStackCount = 0
-    indStart = 0
-    while indStart < stack.size:
-        miniStackCount += 1
-        indEnd = min(indStart + inps.miniStackSize, stack.size)
-        startDate, endDate = stack.dateList[indStart], stack.dateList[indEnd - 1]
-        outDir = os.path.join(inps.outputDir, "miniStacks/" + startDate + "_" + endDate)
-        if os.path.isdir(outDir) and (not inps.forceprocessing):
-            print('{0} looks like it has already been processed. Skipping ... '.format(outDir))
-        else:
-            print('Processing {0}'.format(outDir))
-            miniStack = MiniStack()
-            miniStack.slcList = stack.slcList[indStart:indEnd]
-            miniStack.getSize()
-            miniStack.applyBbox = [True] * miniStack.size
-            miniStack.updateMiniStack(compressedSlcDir)
-            miniStack.bbox = inps.bbox
-            miniStack.getDates()
-            miniStack.configure(outDir)
-            miniStack.writeStackVRT()
-            evdDir = os.path.join(outDir, "EVD")
-            if inps.forceprocessing and os.path.isdir(evdDir):
-                import shutil
-                shutil.rmtree(evdDir)
-            compressedSlcName = miniStack.dateList[-1] + ".slc"
-            compSlcDir = os.path.join(compressedSlcDir, miniStack.dateList[-1])
-            os.makedirs(compSlcDir, exist_ok=True)
-            runEvd(inps, miniStack.stackVRT, weightDS, evdDir, miniStackCount, compSlcDir, compressedSlcName)
-            comp = os.path.join(compSlcDir, compressedSlcName)
-            w, h = stackio.raster_size(comp)
-            stackio.write_raw_vrt(comp + ".vrt", comp, w, h)
-        indStart += inps.miniStackSize
+    for k, start in enumerate(range(0, len(slcs), inps.miniStackSize), start=1):
+        own = slcs[start:start + inps.miniStackSize]
+        folder = os.path.join(root, 'miniStacks', date_of(own[0]) + '_' + date_of(own[-1]))
+        if os.path.isdir(folder) and not inps.forceprocessing:
+            print('{0} looks like it has already been processed. Skipping ... '.format(folder))
+            continue
+        print('Processing {0}'.format(folder))
+        # compressed SLCs of the earlier ministacks first (sorted; the reference's glob order is arbitrary
+        # and the result does not depend on it), uncropped because they already are
+        earlier = sorted(glob.glob(os.path.join(comp_root, '*/*.slc')))
+        members = earlier + own
+        stack_vrt = write_stack(folder, members, [False] * len(earlier) + [True] * len(own), bbox)
+        evd_dir = os.path.join(folder, 'EVD')
+        if inps.forceprocessing and os.path.isdir(evd_dir):
+            shutil.rmtree(evd_dir)
+        last = date_of(own[-1])
+        comp_dir = os.path.join(comp_root, last)
+        os.makedirs(comp_dir, exist_ok=True)
+        link(inps, stack_vrt, evd_dir, k, comp_dir, last + '.slc')
+        comp = os.path.join(comp_dir, last + '.slc')
+        width, height = stackio.raster_size(comp)
+        stackio.write_raw_vrt(comp + '.vrt', comp, width, height)
 
-    outDir = os.path.join(inps.outputDir, "Datum_connection")
-    compSlcStack = Stack(compressedSlcDir)
-    compSlcStack.gatherSLCs()
-    compSlcStack.bbox = None
-    compSlcStack.applyBbox = [False] * compSlcStack.size
-    compSlcStack.getDates()
-    compSlcStack.configure(outDir)
-    compSlcStack.writeStackVRT()
-    runEvd(inps, compSlcStack.stackVRT, weightDS, outDir + "/EVD", 1)
+    datum = os.path.join(root, 'Datum_connection')
+    comps = find_slcs(comp_root)
+    stack_vrt = write_stack(datum, comps, [False] * len(comps), None)
+    link(inps, stack_vrt, os.path.join(datum, 'EVD'), 1)
 
 
 if __name__ == '__main__':
