@@ -7,19 +7,28 @@
 //   layout      k_transpose_mma splits every sample into a TF32 "hi" part and a TF32 "lo"
 //               remainder (x = hi + lo to ~2^-22) and stores a pixel's 32 (zero padded) bands as
 //               128 floats: for g = 0..7 two quads (re, re', im, im') of bands (g, g+8) and
-//               (g+16, g+24) -- each quad is an A fragment as loaded -- then lo in the same order.  Lane (g, t) of a warp therefore fetches everything it needs of
-//               one SHP with four 16-byte loads, and the eight lanes that share t read the SHP's
-//               512 bytes contiguously.
+//               (g+16, g+24) -- each quad is an A fragment as loaded -- then lo in the same order.
+//               Lane (g, t) of a warp therefore fetches everything it needs of one SHP with four
+//               16-byte loads, and the eight lanes that share t read the SHP's 512 bytes
+//               contiguously.
 //   covariance  One warp per pixel.  Four SHPs form one k-chunk of m16n8k8: k = 0..3 are the real
 //               parts of the four samples, k = 4..7 their imaginary parts, so
 //                   Re C = [Zr|Zi] [Zr|Zi]^T          Im C = [Zr|Zi] [-Zi|Zr]^T
 //               and the B fragments of the second product are the first one's with the two
 //               registers swapped and one sign flipped.  Only the 6 of 8 16x8 tiles that touch the
 //               upper triangle are computed: 12 accumulator tiles (48 registers) x 3 products
-//               (hi*hi + hi*lo + lo*hi) = 36 mma.sync per 4 SHPs.
-//   hand-off    accumulator fragments -> coherence -> one full Hermitian matrix in shared memory.
-//   eigen, epilogue: as in evd_fast.cu (lane = row, vector broadcast from shared memory,
-//               heavy-ball momentum, phase reference / compressed SLC / temporal coherence).
+//               (hi*hi + hi*lo + lo*hi) = 36 mma.sync per 4 SHPs, issued product-major so that no
+//               instruction waits for the one before it.
+//   hand-off    accumulator fragments -> coherence -> planar (re | im) Hermitian matrix in shared
+//               memory.
+//   eigen       lane = row; the row lives in registers as pairs of consecutive columns and the
+//               matrix-vector product runs on fma.rn.f32x2; heavy-ball momentum switched on from the
+//               first observed residual decay; Rayleigh quotient and residual are single-round warp
+//               reductions in consecutive iterations, scheduled where convergence is predicted.
+//   epilogue    phase reference / compressed SLC / temporal coherence from the register-resident row.
+//   schedule    one 16-warp CTA per SM; a CTA owns a band of 4 rows x a column segment and its warps
+//               draw pixels from a shared counter in column-major order, so the union of their
+//               windows stays in L1.
 #include <math_constants.h>
 
 #include <cstdlib>
