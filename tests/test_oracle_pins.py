@@ -131,6 +131,12 @@ def test_port_equals_reference_bit_for_bit():
                dict(method=oracle.MLE, variant=oracle.VARIANT_PHASE_LINK, min_neighbors=4)):
         for x, y in zip(port.evd_block(slc, wp, 4, 2, **kw), ref.evd_block(slc, wp, 4, 2, **kw)):
             assert np.array_equal(x, y)
+    # the SURVEY 8f rows: despeck reads the mask through the reference's own Ulongmask in the reference build
+    for kw in (dict(), dict(z2=slc[5]), dict(z2=slc[5], coherence=True)):
+        a, b = port.despeck_block(slc[2], wp, 4, 2, **kw), ref.despeck_block(slc[2], wp, 4, 2, **kw)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    for x, y in zip(port.ampdispersion_block(slc), ref.ampdispersion_block(slc)):
+        assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
 
 
 def test_block_results_independent_of_block_schedule(lib):
