@@ -49,7 +49,21 @@ def main():
         o, t, c = ref.evd_block(slc, wts_ks, 5, 2, **kw)
         out[name + "_out"], out[name + "_tcorr"], out[name + "_comp"] = o, t, c
     np.savez_compressed(os.path.join(HERE, "block_12x24x40.npz"), **out)
+    make_post(ref, slc, wts_ks)
     print("wrote", os.listdir(HERE))
+
+
+def make_post(ref, slc, wts_ks):
+    """SURVEY 8f rows on the same block: despeck (three modes), ampdispersion with calibration
+    constants, datum-adjustment product.  Separate file so the older fixtures stay byte-identical."""
+    alpha = np.linspace(1.0, 1.33, slc.shape[0])
+    da, mean = ref.ampdispersion_block(slc, alpha)
+    post = {"alpha": alpha, "ampdisp_da": da, "ampdisp_mean": mean,
+            "despeck_amp": ref.despeck_block(slc[2], wts_ks, 5, 2),
+            "despeck_ifg": ref.despeck_block(slc[2], wts_ks, 5, 2, z2=slc[9]),
+            "despeck_coh": ref.despeck_block(slc[2], wts_ks, 5, 2, z2=slc[9], coherence=True),
+            "cmul": ref.cmul(slc[4], slc[7])}
+    np.savez_compressed(os.path.join(HERE, "post_12x24x40.npz"), **post)
 
 
 if __name__ == "__main__":

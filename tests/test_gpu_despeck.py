@@ -52,3 +52,18 @@ def test_despeck_argument_errors(ctx):
     w = np.zeros((4, 4, 1), np.uint32)
     with pytest.raises(Exception):
         ctx.despeck_block(z, w, 1, 1, first_line=3, n_lines=4)
+
+
+def test_post_rows_against_golden_fixtures(ctx):
+    """GPU results of the three SURVEY 8f rows against the committed fixtures, bit for bit."""
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(gold, "block_12x24x40.npz"))
+    p = np.load(os.path.join(gold, "post_12x24x40.npz"))
+    slc, wts = g["slc"], g["wts_ks"]
+    da, mean = ctx.ampdispersion_block(slc, p["alpha"])
+    assert _same(da, p["ampdisp_da"]) and _same(mean, p["ampdisp_mean"])
+    assert _same(ctx.despeck_block(slc[2], wts, 5, 2), p["despeck_amp"])
+    assert _same(ctx.despeck_block(slc[2], wts, 5, 2, z2=slc[9]), p["despeck_ifg"])
+    assert _same(ctx.despeck_block(slc[2], wts, 5, 2, z2=slc[9], coherence=True), p["despeck_coh"])
+    assert _same(ctx.cmul(slc[4], slc[7]), p["cmul"])

@@ -104,6 +104,20 @@ def test_golden_blocks(lib):
         assert np.allclose(cp[ok], g[name + "_comp"][ok], atol=1e-4), name
 
 
+def test_golden_post_rows(lib):
+    """SURVEY 8f rows against the committed fixtures (tests/golden/make_golden.py: make_post)."""
+    g = np.load(os.path.join(GOLD, "block_12x24x40.npz"))
+    p = np.load(os.path.join(GOLD, "post_12x24x40.npz"))
+    slc, wts = g["slc"], g["wts_ks"]
+    same = lambda a, b: np.array_equal(np.asarray(a).view(np.uint32), np.asarray(b).view(np.uint32))
+    da, mean = lib.ampdispersion_block(slc, p["alpha"])
+    assert same(da, p["ampdisp_da"]) and same(mean, p["ampdisp_mean"])
+    assert same(lib.despeck_block(slc[2], wts, 5, 2), p["despeck_amp"])
+    assert same(lib.despeck_block(slc[2], wts, 5, 2, z2=slc[9]), p["despeck_ifg"])
+    assert same(lib.despeck_block(slc[2], wts, 5, 2, z2=slc[9], coherence=True), p["despeck_coh"])
+    assert same(lib.cmul(slc[4], slc[7]), p["cmul"])
+
+
 @pytest.mark.skipif(not oracle.available("reference"), reason="reference-header build not present")
 def test_port_equals_reference_bit_for_bit():
     port, ref = oracle.load("port"), oracle.load("reference")
