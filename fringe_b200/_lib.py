@@ -10,7 +10,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libfringe_b200.so")
+LIB_PATH = os.environ.get("FRINGE_B200_LIB") or os.path.join(_HERE, "lib", "libfringe_b200.so")   # override: development builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "fringe_b200.h")
 
 OK, ERR_METHOD, ERR_ARGUMENT, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_CUDA, ERR_MEMORY = range(7)

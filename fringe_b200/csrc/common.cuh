@@ -78,6 +78,10 @@ int evd_mma_order(int bands);
 cudaError_t launch_transpose_mma(const float2* slc, long npix, long first, long count, int bands, float2* zpix,
                                  cudaStream_t st);
 cudaError_t launch_evd_mma(const EvdArgs& a, cudaStream_t st);
+// FP64 MLE / phase_link kernel with one Hermitian row per lane in registers (mle_kernels.cu): bands <= 32;
+// same pixel-major layout as the generic kernel (zblock = 0).  evd_mle_order = 0: not covered.
+int evd_mle_order(int bands);
+cudaError_t launch_evd_mle(const EvdArgs& a, cudaStream_t st);
 
 // out[i] = a[i] * b[i] (complex64, double arithmetic inside), n pixels; 16-byte aligned pointers
 cudaError_t launch_cmul(const float2* a, const float2* b, float2* out, long n, cudaStream_t st);

@@ -1016,6 +1016,7 @@ cudaError_t launch_evd(const EvdArgs& a, cudaStream_t st, int* n_launches) {
     const bool dp = (a.method == 1) || (a.variant == 1);
     if (n_launches) *n_launches = 1;
     if (!(a.force_generic & 1) && evd_fast_supported(a)) return launch_evd_fast(a, st);
+    if (!(a.force_generic & 1) && dp && a.zblock == 0 && evd_mle_order(a.bands) > 0) return launch_evd_mle(a, st);
     return dp ? launch_evd_dp<true>(a, st) : launch_evd_dp<false>(a, st);
 }
 
