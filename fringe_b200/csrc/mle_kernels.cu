@@ -68,144 +68,199 @@ __device__ __forceinline__ float wsumf(float v) {
 
 template <int NT>
 struct MleCfg {
-    static constexpr int WARPS = 4;
-#ifdef FRINGE_MLE_MIN_CTAS
-    static constexpr int MIN_CTAS = FRINGE_MLE_MIN_CTAS;
+    // one CTA per SM; warps limited by registers (65536 / threads) and shared memory (227 kB)
+#ifdef FRINGE_MLE_WARPS
+    static constexpr int WARPS = FRINGE_MLE_WARPS;
 #else
-    static constexpr int MIN_CTAS = NT <= 16 ? 4 : (NT <= 24 ? 3 : 2);   // register budget 128 / 168 / 255 per thread
+    static constexpr int WARPS = NT <= 16 ? 16 : (NT <= 24 ? 12 : (NT <= 28 ? 8 : 7));
 #endif
+    static constexpr int MIN_CTAS = 1;
+    static constexpr int MAX_WORK = 1024;                    // pixels per CTA (band rows x segment columns)
     static constexpr int BAND = 4;                            // rows of a CTA's pixel band
     static constexpr int NPAIR = NT * (NT - 1) / 2;
     static constexpr int NSLOT = (NPAIR + 31) / 32;           // covariance pairs per lane
     static constexpr int NPACK = NT * (NT + 1) / 2;           // packed lower triangle
     // per warp: Mp, F complex double packed | Lr real packed | rsv, dv NT doubles | Cf float2 packed |
     //           zs 2 x NT float2 | list 64 ints
-    static constexpr int SMEM_PER_WARP = 16 * NPACK + 16 * NPACK + 8 * NPACK + 16 * NT + 8 * NPACK + 16 * NT + 256;
+    static constexpr int SMEM_PER_WARP = 16 * NPACK + 16 * NPACK + 8 * NPACK + 16 * NT + 8 * NPACK + 16 * NT + 256 + 64 * NT;   // + pan [NT][4] complex
 };
 
-// Packed column-major lower triangle of an N x N matrix: column j starts at coff(j), element (i, j),
-// i >= j, sits at coff(j) + i - j.  Lanes that walk down a column read consecutive addresses.
-__device__ __forceinline__ int coff(int j, int N) { return (j * (2 * N - j + 1)) >> 1; }
+// Packed column-major lower triangle with the static pitch NT (the instantiation's order; rows and
+// columns >= N are padding): column j starts at coff(j), element (i, j), i >= j, sits at coff(j) + i - j.
+// Lanes that walk down a column read consecutive addresses, and for an unrolled j the offset is an
+// immediate.
+template <int NT>
+__device__ __forceinline__ int coff(int j) { return (j * (2 * NT - j + 1)) >> 1; }
+
+// one predicated shared-memory store (the compiler turns `if (p) *q = v` in these loops into a branch)
+__device__ __forceinline__ void sts_pred(double2* q, double2 v, bool pred) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(q);
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.shared.v2.f64 [%0], {%1, %2};\n\t}"
+                 :: "r"(addr), "d"(v.x), "d"(v.y), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void sts_pred(double* q, double v, bool pred) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(q);
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.shared.f64 [%0], %1;\n\t}"
+                 :: "r"(addr), "d"(v), "r"((int)pred) : "memory");
+}
 
 // ---------------------------------------------------------------------------------------
 // Complex Cholesky F = L L^H in shared memory, in place, lane = row; rsv[k] = 1 / L(k,k).
-// Returns false (warp-uniform) on a non-positive pivot, the failure LAPACK zpotrf reports.
+// Panels of 4 columns: a lane takes its row's 4 panel entries into registers, the panel is factored
+// there (pivots and the L(j,k) of the other panel columns arrive by shuffles: no shared-memory
+// traffic, no barriers), written back, and a row-major copy `pan` feeds the broadcast operands of the
+// rank-4 trailing update.  Returns false (warp-uniform) on a non-positive pivot, the failure LAPACK
+// zpotrf reports.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ bool chol_c_smem(double2* F, double* rsv, int N, int lane) {
+template <int NT>
+__device__ __noinline__ bool chol_c_smem(double2* F, double2* pan, double* rsv, int N, int lane) {
     const int row = min(lane, N - 1);
+    const bool live = lane < N;
 #pragma unroll 1
     for (int kb = 0; kb < N; kb += 4) {
         const int kend = min(kb + 4, N);
-#pragma unroll 1
-        for (int k = kb; k < kend; ++k) {
-            const int ck = coff(k, N);
-            const double d = F[ck].x;
-            if (!__all_sync(FULLM, d > 0.0)) return false;
-            const double rs = rsqrt(d);
-            const bool act = lane > k && lane < N;
-            double2 l = F[ck + max(row, k) - k];
-            l.x = act ? l.x * rs : 0.0; l.y = act ? l.y * rs : 0.0;
-            if (act) F[ck + row - k] = l;
-            if (lane == k) { F[ck] = make_double2(d * rs, 0.0); rsv[k] = rs; }
-            __syncwarp();
-#pragma unroll 1
-            for (int j = k + 1; j < kend; ++j) {             // rest of the panel
-                const double2 v = F[ck + j - k];               // L(j,k), broadcast
-                const int idx = coff(j, N) + max(row, j) - j;
-                double2 a = F[idx];
-                a.x = fma(-l.x, v.x, a.x); a.x = fma(-l.y, v.y, a.x);       // a(i,j) -= l(i,k) conj(l(j,k))
-                a.y = fma(-l.y, v.x, a.y); a.y = fma(l.x, v.y, a.y);
-                if (lane >= j && lane < N) F[idx] = a;
+        double2 p[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int k = min(kb + t, N - 1);
+            p[t] = F[coff<NT>(k) + max(row, k) - k];
+        }
+        bool ok = true;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int k = kb + t;
+            if (k < N) {
+                const double d = __shfl_sync(FULLM, p[t].x, k);
+                ok = ok && __all_sync(FULLM, d > 0.0);
+                const double rs = rsqrt(d);
+                if (lane == k) rsv[k] = rs;
+                const bool act = lane > k && live;
+                p[t].x = act ? p[t].x * rs : (lane == k ? d * rs : 0.0);
+                p[t].y = act ? p[t].y * rs : 0.0;
+#pragma unroll
+                for (int u = t + 1; u < 4; ++u) {
+                    if (kb + u < N) {                          // a(i,j) -= l(i,k) conj(l(j,k)), j = kb + u
+                        const double vr = __shfl_sync(FULLM, p[t].x, kb + u), vi = __shfl_sync(FULLM, p[t].y, kb + u);
+                        const bool on = lane >= kb + u;
+                        const double lr = on ? p[t].x : 0.0, li = on ? p[t].y : 0.0;
+                        p[u].x = fma(-lr, vr, p[u].x); p[u].x = fma(-li, vi, p[u].x);
+                        p[u].y = fma(-li, vr, p[u].y); p[u].y = fma(lr, vi, p[u].y);
+                    }
+                }
             }
-            __syncwarp();
+        }
+        if (!ok) return false;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int k = min(kb + t, N - 1);
+            sts_pred(&F[coff<NT>(k) + max(row, k) - k], p[t], kb + t < N && lane >= kb + t && live);
         }
         if (kend < N) {                                       // trailing update by the finished panel (always 4 wide here)
+            const bool own = lane >= kend && live;
             double2 lp[4];
-            const bool own = lane >= kend && lane < N;
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                const double2 v = F[coff(kb + t, N) + max(row, kend) - (kb + t)];
-                lp[t] = own ? v : make_double2(0.0, 0.0);
+                sts_pred(&pan[row * 4 + t], p[t], own);
+                lp[t] = own ? p[t] : make_double2(0.0, 0.0);
             }
+            __syncwarp();
+            int cjm = coff<NT>(kend) - kend;                  // coff(j) - j, advanced with j
 #pragma unroll 1
             for (int j = kend; j < N; ++j) {
-                const int idx = coff(j, N) + max(row, j) - j;
-                double2 a = F[idx];
+                double2* q = F + cjm + max(row, j);
+                double2 a = *q;
+                const double2* pj = pan + j * 4;               // L(j, kb .. kb+3), broadcast
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
-                    const double2 v = F[coff(kb + t, N) + j - (kb + t)];   // L(j, kb+t), broadcast
+                    const double2 v = pj[t];
                     a.x = fma(-lp[t].x, v.x, a.x); a.x = fma(-lp[t].y, v.y, a.x);
                     a.y = fma(-lp[t].y, v.x, a.y); a.y = fma(lp[t].x, v.y, a.y);
                 }
-                if (lane >= j && lane < N) F[idx] = a;
+                sts_pred(q, a, lane >= j && live);
+                cjm += NT - j - 1;
             }
-            __syncwarp();
         }
+        __syncwarp();
     }
     return true;
 }
 
-// the same for a real symmetric matrix; dv[k] = 1 / L(k,k)
-__device__ __forceinline__ bool chol_r_smem(double* A, double* dv, int N, int lane) {
+// the same for a real symmetric matrix; dv[k] = 1 / L(k,k); pan is used as [N][4] doubles
+template <int NT>
+__device__ __noinline__ bool chol_r_smem(double* A, double* pan, double* dv, int N, int lane) {
     const int row = min(lane, N - 1);
+    const bool live = lane < N;
 #pragma unroll 1
     for (int kb = 0; kb < N; kb += 4) {
         const int kend = min(kb + 4, N);
-#pragma unroll 1
-        for (int k = kb; k < kend; ++k) {
-            const int ck = coff(k, N);
-            const double d = A[ck];
-            if (!__all_sync(FULLM, d > 0.0)) return false;
-            const double rs = rsqrt(d);
-            const bool act = lane > k && lane < N;
-            double l = A[ck + max(row, k) - k];
-            l = act ? l * rs : 0.0;
-            if (act) A[ck + row - k] = l;
-            if (lane == k) { A[ck] = d * rs; dv[k] = rs; }
-            __syncwarp();
-#pragma unroll 1
-            for (int j = k + 1; j < kend; ++j) {
-                const double v = A[ck + j - k];
-                const int idx = coff(j, N) + max(row, j) - j;
-                const double a = fma(-l, v, A[idx]);
-                if (lane >= j && lane < N) A[idx] = a;
+        double p[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int k = min(kb + t, N - 1);
+            p[t] = A[coff<NT>(k) + max(row, k) - k];
+        }
+        bool ok = true;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int k = kb + t;
+            if (k < N) {
+                const double d = __shfl_sync(FULLM, p[t], k);
+                ok = ok && __all_sync(FULLM, d > 0.0);
+                const double rs = rsqrt(d);
+                if (lane == k) dv[k] = rs;
+                p[t] = (lane > k && live) ? p[t] * rs : (lane == k ? d * rs : 0.0);
+#pragma unroll
+                for (int u = t + 1; u < 4; ++u) {
+                    if (kb + u < N) {
+                        const double v = __shfl_sync(FULLM, p[t], kb + u);
+                        p[u] = fma(-((lane >= kb + u) ? p[t] : 0.0), v, p[u]);
+                    }
+                }
             }
-            __syncwarp();
+        }
+        if (!ok) return false;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int k = min(kb + t, N - 1);
+            sts_pred(&A[coff<NT>(k) + max(row, k) - k], p[t], kb + t < N && lane >= kb + t && live);
         }
         if (kend < N) {
+            const bool own = lane >= kend && live;
             double lp[4];
-            const bool own = lane >= kend && lane < N;
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                const double v = A[coff(kb + t, N) + max(row, kend) - (kb + t)];
-                lp[t] = own ? v : 0.0;
-            }
-#pragma unroll 1
-            for (int j = kend; j < N; ++j) {
-                const int idx = coff(j, N) + max(row, j) - j;
-                double a = A[idx];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) a = fma(-lp[t], A[coff(kb + t, N) + j - (kb + t)], a);
-                if (lane >= j && lane < N) A[idx] = a;
+                sts_pred(&pan[row * 4 + t], p[t], own);
+                lp[t] = own ? p[t] : 0.0;
             }
             __syncwarp();
+            int cjm = coff<NT>(kend) - kend;
+#pragma unroll 1
+            for (int j = kend; j < N; ++j) {
+                double* q = A + cjm + max(row, j);
+                double a = *q;
+                const double* pj = pan + j * 4;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) a = fma(-lp[t], pj[t], a);
+                sts_pred(q, a, lane >= j && live);
+                cjm += NT - j - 1;
+            }
         }
+        __syncwarp();
     }
     return true;
 }
 
 // Row `row` of the Hermitian matrix whose lower triangle is packed in P: element j into fr[j] + i fi[j]
-// (the diagonal entry is read as stored).  Every array element is written (columns >= N get zeros).
+// (the diagonal entry is read as stored; columns >= N deliver padding nobody uses).
 template <int NT>
-__device__ __forceinline__ void load_row(const double2* __restrict__ P, int row, int N, double (&fr)[NT], double (&fi)[NT]) {
-    const int crow = coff(row, N);
+__device__ __forceinline__ void load_row(const double2* __restrict__ P, int row, double (&fr)[NT], double (&fi)[NT]) {
+    const double2* up = P + coff<NT>(row) - row;           // P(j, row), j > row, at up[j]
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
-        const int jj = min(j, N - 1);
-        const bool low = (jj <= row);
-        const double2 v = P[low ? coff(jj, N) + row - jj : crow + jj - row];
-        fr[j] = (j < N) ? v.x : 0.0;
-        fi[j] = (j < N) ? (low ? v.y : -v.y) : 0.0;
+        const bool low = (j <= row);
+        const double2 v = low ? P[coff<NT>(j) - j + row] : up[j];
+        fr[j] = v.x;
+        fi[j] = low ? v.y : -v.y;
     }
 }
 
@@ -258,8 +313,9 @@ __global__ void __launch_bounds__(MleCfg<NT>::WARPS * 32, MleCfg<NT>::MIN_CTAS) 
         s_off[f] = (f < W) ? make_short2((short)(fy - a.Ny), (short)(f - fy * WX - a.Nx))
                            : make_short2((short)-30000, (short)-30000);
     }
-    __shared__ int s_next;
-    if (threadIdx.x == 0) s_next = 0;
+    __shared__ int s_nwork;
+    __shared__ unsigned short s_work[MleCfg<NT>::MAX_WORK];       // pixels of this CTA that reach the solver
+    if (threadIdx.x == 0) s_nwork = 0;
     __syncthreads();
     const int lut_bytes = ((a.nulong * 32 * (int)sizeof(short2)) + 15) & ~15;
 
@@ -272,6 +328,7 @@ __global__ void __launch_bounds__(MleCfg<NT>::WARPS * 32, MleCfg<NT>::MIN_CTAS) 
     float2* Cf = reinterpret_cast<float2*>(dv + NT);                       // packed lower C, FP32
     float2* zs = Cf + Cfg::NPACK;                                          // [2][NT] staged samples
     int* s_list = reinterpret_cast<int*>(zs + 2 * NT);                     // [64]
+    double2* pan = reinterpret_cast<double2*>(s_list + 64);                // [NT][4] panel rows of the factorisation in progress
 
     const int k0 = a.mini_stack_count - 1;
     const bool isstbas = (a.method == 2), ismle = (a.method == 1);
@@ -282,9 +339,9 @@ __global__ void __launch_bounds__(MleCfg<NT>::WARPS * 32, MleCfg<NT>::MIN_CTAS) 
     const int need = pl ? a.min_neighbors : 2;                             // evd.cpp:566 / phase_link.cpp:524
     const int E = N * (N - 1) / 2;
     const int nslot = (E + 31) >> 5;
-    const int npack = N * (N + 1) / 2;
+    constexpr int npack = Cfg::NPACK;                                     // elementwise passes run over the padding too
     const int r = min(lane, N - 1);                                        // my row (lanes >= N shadow the last one)
-    const int cr_own = coff(r, N);
+    const int cr_own = coff<NT>(r);
     const bool live = lane < N;
 
     // covariance pairs of this lane: slot s <-> pair e = 32 s + lane of the strict upper triangle, row-major
@@ -310,23 +367,57 @@ __global__ void __launch_bounds__(MleCfg<NT>::WARPS * 32, MleCfg<NT>::MIN_CTAS) 
     unsigned int st_pix = 0, st_fact = 0, st_steps = 0, st_dp = 0, st_cap = 0;
     const uint32_t lt_mask = (1u << lane) - 1u;
 
+    // All warps of the CTA walk through the phases of a pixel together (__syncthreads between them): the
+    // instruction working set of the SM is then one phase at a time.  Measured on the version with
+    // independent warps: 64 % instruction-cache hit rate and the GPC-level instruction cache at 95 % of
+    // its request bandwidth -- the kernel was bound by instruction fetch, not by any arithmetic pipe.
+    const int nwarps = blockDim.x >> 5;
+
+    // ---- pass 0: which pixels reach the solver?  The others (mask centre off, too few SHPs, or fewer SHPs
+    // than bands under MLE: rank(C) <= npix < N, lambda_min = 0, sentinel -2 of evd.cpp:613-617) get their
+    // outputs here, so that no warp idles at the phase barriers below on their behalf.
 #pragma unroll 1
-    for (;;) {
-        int kdraw = 0;
-        if (lane == 0) kdraw = atomicAdd(&s_next, 1);
-        kdraw = __shfl_sync(FULLM, kdraw, 0);
-        if (!__all_sync(FULLM, kdraw < total)) break;
+    for (int k = warp; k < total; k += nwarps) {
+        const int row = row0 + k % rows, col = c0 + k / rows;
+        const long pg = (long)row * a.cols + col;
+        const uint32_t* mwords = a.wts + pg * a.nulong;
+        const bool center_on = __all_sync(FULLM, (__ldg(&mwords[center >> 5]) >> (center & 31)) & 1u);
+        int npix = 0;
+        if (center_on) {
+            for (int w = lane; w < a.nulong * 32; w += 32) {
+                const uint32_t word = __ldg(&mwords[w >> 5]);
+                const short2 d = s_off[w];
+                const int yy = row + d.x, xx = col + d.y;
+                const bool ok = ((word >> (w & 31)) & 1u) && yy >= 0 && yy < a.lines && xx >= 0 && xx < a.cols;
+                npix += __popc(__ballot_sync(FULLM, ok));
+            }
+        }
+        const bool rank_deficient = !pl && ismle && npix < N;
+        if (center_on && npix >= need && !rank_deficient) {
+            if (lane == 0) s_work[atomicAdd(&s_nwork, 1)] = (unsigned short)k;
+        } else {
+            if (live) a.out[(long)lane * npix_block + pg] = make_float2(0.f, 0.f);
+            if (lane == 0) { a.tcorr[pg] = (center_on && npix >= need) ? -2.f : 0.f; a.comp[pg] = make_float2(0.f, 0.f); }
+        }
+    }
+    __syncthreads();
+    const int nwork = s_nwork;
+
+#pragma unroll 1
+    for (int kbase = 0; kbase < nwork; kbase += nwarps) {
+        const bool mine = kbase + warp < nwork;
+        const int kdraw = s_work[min(kbase + warp, nwork - 1)];
         const int row = row0 + kdraw % rows;
         const int col = c0 + kdraw / rows;
         const long pg = (long)row * a.cols + col;
         const uint32_t* mwords = a.wts + pg * a.nulong;
-        const bool center_on = __all_sync(FULLM, (__ldg(&mwords[center >> 5]) >> (center & 31)) & 1u);
+        const bool go = mine;
 
         float tc = 0.f;
         bool have_vec = false;
         double vxr = 0.0, vxi = 0.0;                          // eigenvector component of this lane
 
-        // SHP list of mask words w0, w0 + 1 -> s_list (if store), returns its length
+        // SHP list of mask words w0, w0 + 1 -> s_list, returns its length
         auto build_list = [&](int w0, bool store) -> int {
             int n = 0;
 #pragma unroll
@@ -343,16 +434,32 @@ __global__ void __launch_bounds__(MleCfg<NT>::WARPS * 32, MleCfg<NT>::MIN_CTAS) 
             return n;
         };
 
-        int npix = 0;
-        if (center_on) {
-            for (int w0 = 0; w0 < a.nulong; w0 += 2) npix += build_list(w0, false);
-        }
-        bool go = center_on && npix >= need;
-        if (go && !pl && ismle && npix < N) { tc = -2.f; go = false; }     // rank(C) <= npix < N: lambda_min = 0 (evd.cpp:613-617)
+        bool failed = false, run_evd = false, c_in_mp = true, have_inv = false, okr = false;
+        double dmax = 0.0;
+        // F = scale * Mp + dadd I on the packed triangle
+        auto assemble = [&](double scale, double dadd) {
+            for (int e = lane; e < npack; e += 32) { const double2 v = Mp[e]; F[e] = make_double2(scale * v.x, scale * v.y); }
+            __syncwarp();
+            if (live) { const double2 v = F[cr_own]; F[cr_own] = make_double2(v.x + dadd, 0.0); }
+            __syncwarp();
+        };
+        auto fill_abs = [&](double shift) {
+            // |C| elementwise on the packed triangle; padding entries are forced finite (they meet zero
+            // multipliers in the unrolled substitutions of the inverse)
+            __syncwarp();
+            for (int e = lane; e < npack; e += 32) {
+                const double2 v = Mp[e];
+                const double m = sqrt(fma(v.x, v.x, v.y * v.y));
+                Lr[e] = (m <= 2.0) ? m : 0.0;
+            }
+            __syncwarp();
+            if (live) Lr[cr_own] = 1.0 - shift;
+            __syncwarp();
+        };
 
+        // ================= phase 1: covariance (evd.cpp:537-564) =================
         if (go) {
             ++st_pix;
-            // ---------------- covariance (evd.cpp:537-564) --------------------------------
             {
                 double ar[Cfg::NSLOT], ai[Cfg::NSLOT];
 #pragma unroll
@@ -402,7 +509,7 @@ __global__ void __launch_bounds__(MleCfg<NT>::WARPS * 32, MleCfg<NT>::MIN_CTAS) 
                         const int i = pij[s] & 0xff, j = pij[s] >> 8;
                         const double den = sqrt(dv[i] * dv[j]);
                         const double cx = ar[s] / den, cy = ai[s] / den;
-                        const int idx = coff(i, N) + j - i;
+                        const int idx = coff<NT>(i) + j - i;
                         Mp[idx] = make_double2(cx, -cy);
                         Cf[idx] = make_float2((float)cx, -(float)cy);
                     }
@@ -411,90 +518,86 @@ __global__ void __launch_bounds__(MleCfg<NT>::WARPS * 32, MleCfg<NT>::MIN_CTAS) 
                 __syncwarp();
             }
 
-            bool failed = false, run_evd = false, c_in_mp = true;
-            // F = scale * Mp + dadd I on the packed triangle
-            auto assemble = [&](double scale, double dadd) {
-                for (int e = lane; e < npack; e += 32) { const double2 v = Mp[e]; F[e] = make_double2(scale * v.x, scale * v.y); }
-                __syncwarp();
-                if (live) { const double2 v = F[cr_own]; F[cr_own] = make_double2(v.x + dadd, 0.0); }
-                __syncwarp();
-            };
-
-            // ---------------- gate 1: lambda_min(C) >= 1e-6 (evd.cpp:608-617) ---------------
+        }
+        __syncthreads();
+        // ================= phase 2: gate 1, lambda_min(C) >= 1e-6 (evd.cpp:608-617) =================
+        if (go && !pl) {
+            assemble(1.0, -1.0e-6);
+            ++st_fact;
+            if (!chol_c_smem<NT>(F, pan, rsv, N, lane)) { tc = -2.f; failed = true; }
+        }
+        // ================= phase 3: |C| and its factor (evd.cpp:619-653); same barrier interval (both are
+        // factorisation code) =================
+        if (go && !failed) {
+            ++st_dp;
+            fill_abs(0.0);
+            okr = chol_r_smem<NT>(Lr, reinterpret_cast<double*>(pan), dv, N, lane);
+            if (!okr) {                                       // |C| itself is not positive definite
+                if (pl) run_evd = true; else { tc = -4.f; failed = true; }
+            }
+        }
+        __syncthreads();
+        // ================= phase 4: inverse, gate 2, M = inv(|C|) o C =================
+        if (go && okr) {
+            double xv[NT];                                   // lane c: column c (= row c) of inv(|C|)
+#pragma unroll
+            for (int j = 0; j < NT; ++j) xv[j] = 0.0;
+            // lane c solves L L^T x = e_c privately: the factor is read at uniform addresses (broadcasts,
+            // immediate offsets), the vector stays in registers
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+                if (i < N) {
+                    double sacc = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+                    for (int m = 0; m < NT; ++m) { if (m < i) sacc = fma(-Lr[coff<NT>(m) + i - m], xv[m], sacc); }
+                    xv[i] = sacc * dv[i];
+                }
+            }
+#pragma unroll
+            for (int i = NT - 1; i >= 0; --i) {
+                if (i < N) {
+                    double sacc = xv[i];
+#pragma unroll
+                    for (int m = 0; m < NT; ++m) { if (m > i) sacc = fma(-Lr[coff<NT>(i) + m - i], xv[m], sacc); }   // xv[m >= N] = 0
+                    xv[i] = sacc * dv[i];
+                }
+            }
+            have_inv = true;
             if (!pl) {
-                assemble(1.0, -1.0e-6);
-                ++st_fact;
-                if (!chol_c_smem(F, rsv, N, lane)) { tc = -2.f; failed = true; }
+                // gate 2: lambda_min(|C|) = 1 / lambda_max(inv); max diagonal <= lambda_max <= max row sum;
+                // in between the two bounds a factorisation of |C| - 1e-6 I decides
+                double rowsum = 0.0, dg = 0.0;
+#pragma unroll
+                for (int j = 0; j < NT; ++j) { rowsum += fabs(xv[j]); dg = (j == lane) ? xv[j] : dg; }
+                if (!live) { rowsum = 0.0; dg = 0.0; }
+                const double mrow = wmax(rowsum), mdiag = wmax(dg);
+                if (!__all_sync(FULLM, mrow <= 0.999e6)) {
+                    if (__all_sync(FULLM, mdiag >= 1.001e6)) { tc = -4.f; failed = true; }
+                    else {
+                        fill_abs(1.0e-6);
+                        if (!chol_r_smem<NT>(Lr, reinterpret_cast<double*>(pan), dv, N, lane)) { tc = -4.f; failed = true; }
+                    }
+                }
             }
-            // ---------------- |C|, gate 2, inverse (evd.cpp:619-653) ------------------------
-            double dmax = 0.0;
+            // every lane rewrites the lower part of its own row of Mp in place (evd.cpp:655-657)
             if (!failed) {
-                ++st_dp;
-                double* X = reinterpret_cast<double*>(F);       // X[m * N + c] = inv(|C|)(m, c)
-                bool have_inv = false;
-                double shift = 0.0;
-#pragma unroll 1
-                for (int pass = 0; pass < 2; ++pass) {
-                    __syncwarp();
-                    for (int e = lane; e < npack; e += 32) { const double2 v = Mp[e]; Lr[e] = sqrt(fma(v.x, v.x, v.y * v.y)); }
-                    __syncwarp();
-                    if (live) Lr[cr_own] = 1.0 - shift;
-                    __syncwarp();
-                    const bool okr = chol_r_smem(Lr, dv, N, lane);
-                    if (pass == 1) { if (!okr) { tc = -4.f; failed = true; } break; }
-                    if (!okr) {                                   // |C| itself is not positive definite
-                        if (pl) run_evd = true; else { tc = -4.f; failed = true; }
-                        break;
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    if (j < N) {
+                        double2* q = Mp + coff<NT>(j) - j + max(r, j);
+                        const double2 v = *q;
+                        sts_pred(q, make_double2(xv[j] * v.x, (j == lane) ? 0.0 : xv[j] * v.y), j <= lane && live);
+                        dmax = (j == lane) ? xv[j] : dmax;
                     }
-                    // lane c: column c of inv(|C|) = (L L^T)^-1 e_c by private substitutions; the factor is read
-                    // at uniform addresses (broadcasts), the vector lives in X[. * N + c]
-                    const int c = r;
-#pragma unroll 1
-                    for (int i = 0; i < N; ++i) {
-                        double s = (i == c) ? 1.0 : 0.0;
-#pragma unroll 2
-                        for (int m = 0; m < i; ++m) s = fma(-Lr[coff(m, N) + i - m], X[m * N + c], s);
-                        X[i * N + c] = s * dv[i];
-                    }
-#pragma unroll 1
-                    for (int i = N - 1; i >= 0; --i) {
-                        double s = X[i * N + c];
-                        const int ci = coff(i, N) - i;
-#pragma unroll 2
-                        for (int m = i + 1; m < N; ++m) s = fma(-Lr[ci + m], X[m * N + c], s);
-                        X[i * N + c] = s * dv[i];
-                    }
-                    __syncwarp();
-                    have_inv = true;
-                    if (pl) break;
-                    // gate 2: lambda_min(|C|) = 1 / lambda_max(inv); max diagonal <= lambda_max <= max row sum
-                    double rowsum = 0.0;
-                    for (int j = 0; j < N; ++j) rowsum += fabs(X[j * N + c]);
-                    double dg = X[c * N + c];
-                    if (!live) { rowsum = 0.0; dg = 0.0; }
-                    const double mrow = wmax(rowsum), mdiag = wmax(dg);
-                    if (__all_sync(FULLM, mrow <= 0.999e6)) break;     // passes for certain
-                    if (__all_sync(FULLM, mdiag >= 1.001e6)) { tc = -4.f; failed = true; break; }
-                    shift = 1.0e-6;                               // in between: decide by factorising |C| - 1e-6 I
                 }
-                // ---------------- M = inv(|C|) o C (evd.cpp:655-657), in place in Mp ----------------
-                if (!failed && !run_evd && have_inv) {
-#pragma unroll 1
-                    for (int j = 0; j < N; ++j) {
-                        if (lane >= j && live) {
-                            const double w = X[j * N + lane];
-                            const int idx = coff(j, N) + lane - j;
-                            const double2 v = Mp[idx];
-                            Mp[idx] = make_double2(w * v.x, (j == lane) ? 0.0 : w * v.y);
-                            if (j == lane) dmax = w;
-                        }
-                    }
-                    c_in_mp = false;
-                    __syncwarp();
-                    dmax = wmax(live ? dmax : 0.0);
-                }
+                c_in_mp = false;
+                __syncwarp();
+                dmax = wmax(live ? dmax : 0.0);
             }
-
+        }
+        __syncthreads();
+        // ================= phase 5: eigen solves =================
+        if (go) {
             // ---------------- eigen solves ------------------------------------------------------
             // stage 0: smallest eigenpair of M (MLE).  stage 1 (phase_link only): dominant eigenvector of C
             // (phase_link.cpp:586-600) by FP64 power iteration with momentum, and if that stalls by the
@@ -508,7 +611,7 @@ __global__ void __launch_bounds__(MleCfg<NT>::WARPS * 32, MleCfg<NT>::MIN_CTAS) 
                     if (failed || run_evd) continue;
                     // start vector: phases of the middle column of C (the MLE phases are close to them)
                     const int km = N >> 1;
-                    const float2 cst = Cf[(r >= km) ? coff(km, N) + r - km : cr_own + km - r];
+                    const float2 cst = Cf[(r >= km) ? coff<NT>(km) + r - km : cr_own + km - r];
                     xr = cst.x; xi = (r >= km) ? cst.y : -cst.y;
                     const double m2 = xr * xr + xi * xi;
                     if (m2 > 0.0) { const double s = rsqrt(m2); xr *= s; xi *= s; } else { xr = 1.0; xi = 0.0; }
@@ -524,8 +627,8 @@ __global__ void __launch_bounds__(MleCfg<NT>::WARPS * 32, MleCfg<NT>::MIN_CTAS) 
                         __syncwarp();
                         c_in_mp = true;
                     }
-                    load_row<NT>(Mp, r, N, fr, fi);
-                    const double2 ck0 = Mp[(r >= k0) ? coff(k0, N) + r - k0 : cr_own + k0 - r];   // start: column k0 of C
+                    load_row<NT>(Mp, r, fr, fi);
+                    const double2 ck0 = Mp[(r >= k0) ? coff<NT>(k0) + r - k0 : cr_own + k0 - r];   // start: column k0 of C
                     xr = ck0.x; xi = (r >= k0) ? ck0.y : -ck0.y;
                     if (!live) { xr = 0.0; xi = 0.0; }
                     double xpr = 0.0, xpi = 0.0;
@@ -603,7 +706,7 @@ __global__ void __launch_bounds__(MleCfg<NT>::WARPS * 32, MleCfg<NT>::MIN_CTAS) 
                     if (stage == 0) assemble(1.0, -sig);
                     else assemble(-1.0, (double)N - sig);          // N I - C: diagonal N - 1
                     ++st_fact;
-                    const bool ok = chol_c_smem(F, rsv, N, lane);
+                    const bool ok = chol_c_smem<NT>(F, pan, rsv, N, lane);
                     if (!ok) {
                         if (pending == 0) { if (++attempts >= 6) gave_up = true; else { back *= 1.0e3; sig = -back; } continue; }
                         hi = fmin(hi, sig);
@@ -617,7 +720,7 @@ __global__ void __launch_bounds__(MleCfg<NT>::WARPS * 32, MleCfg<NT>::MIN_CTAS) 
                     }
                     sigma_ok = sig;
                     since = 0; res_prev = -1.0;
-                    load_row<NT>(F, r, N, fr, fi);
+                    load_row<NT>(F, r, fr, fi);
                     const double rs_own = rsv[r];
                     bool reshift = false;
 #pragma unroll 1
@@ -669,7 +772,8 @@ __global__ void __launch_bounds__(MleCfg<NT>::WARPS * 32, MleCfg<NT>::MIN_CTAS) 
             }
         }
 
-        // -------- phase reference, compression, temporal coherence (evd.cpp:738-786) --------
+        __syncthreads();
+        // ================= phase 6: phase reference, compression, temporal coherence (evd.cpp:738-786) =================
         float2 o = make_float2(0.f, 0.f);
         float2 cmp = make_float2(0.f, 0.f);
         if (have_vec) {
@@ -701,7 +805,7 @@ __global__ void __launch_bounds__(MleCfg<NT>::WARPS * 32, MleCfg<NT>::MIN_CTAS) 
             if (live) {
                 for (int i = 0; i < lane; ++i) {
                     if (isstbas && (lane - i) > BW) continue;
-                    const float2 c = Cf[coff(i, N) + lane - i];
+                    const float2 c = Cf[coff<NT>(i) + lane - i];
                     const float mm = sqrtf(c.x * c.x + c.y * c.y);
                     float ex = 1.f, ey = 0.f;
                     if (mm > 0.f) { ex = c.x / mm; ey = -c.y / mm; }
@@ -716,9 +820,9 @@ __global__ void __launch_bounds__(MleCfg<NT>::WARPS * 32, MleCfg<NT>::MIN_CTAS) 
             cnt = __reduce_add_sync(FULLM, cnt);
             tc = sqrtf(sr * sr + si * si) / (float)cnt;
         }
-        if (live) a.out[(long)lane * npix_block + pg] = o;
-        if (lane == 0) { a.tcorr[pg] = tc; a.comp[pg] = cmp; }
-        __syncwarp();
+        if (live && mine) a.out[(long)lane * npix_block + pg] = o;
+        if (lane == 0 && mine) { a.tcorr[pg] = tc; a.comp[pg] = cmp; }
+        __syncthreads();
     }
     if (a.stats && lane == 0) {
         atomicAdd(&a.stats[0], (unsigned long long)st_pix);
@@ -746,6 +850,7 @@ static cudaError_t launch_mle_t(const EvdArgs& a, cudaStream_t st) {
     if (nseg < 1) nseg = 1;
     int seglen = (a.cols + nseg - 1) / nseg;
     if (seglen < 16) seglen = 16;
+    if (seglen * Cfg::BAND > Cfg::MAX_WORK) seglen = Cfg::MAX_WORK / Cfg::BAND;
     nseg = (a.cols + seglen - 1) / seglen;
     EvdArgs b = a;
     b.tile_pairs = seglen;
