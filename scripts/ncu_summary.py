@@ -19,6 +19,9 @@ KEYS = [
     "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
     "smsp__sass_inst_executed_op_local_ld.sum", "smsp__sass_inst_executed_op_local_st.sum",
     "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "sm__icc_request_hit_rate.pct", "gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
 ]
 STALL = "smsp__average_warps_issue_stalled_"
 
