@@ -12,6 +12,8 @@ import re
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FRINGE_B200_LIB") or os.path.join(_HERE, "lib", "libfringe_b200.so")   # override: development builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "fringe_b200.h")
+PROF_HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "fringe_b200_prof.h")
+PROF_LIB_PATH = os.path.join(_HERE, "lib", "libfringe_b200_prof.so")
 
 OK, ERR_METHOD, ERR_ARGUMENT, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_CUDA, ERR_MEMORY = range(7)
 NMAP_KS2, NMAP_AD2 = 0, 1
@@ -25,9 +27,9 @@ class FringeError(RuntimeError):
         self.status = status
 
 
-def declared_symbols() -> list[str]:
-    """Every function name include/fringe_b200.h declares (used by the ABI export test)."""
-    text = open(HEADER_PATH).read()
+def declared_symbols(header: str | None = None) -> list[str]:
+    """Every function name a header declares (include/fringe_b200.h by default; used by the ABI export test)."""
+    text = open(header or HEADER_PATH).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(fringe_[a-z0-9_]+)\s*\(", text)))
 
@@ -70,15 +72,23 @@ def _load() -> C.CDLL:
     lib.fringe_despeck_block_device.argtypes = [vp, vp, vp, vp] + [i] * 7 + [vp, vp]
     lib.fringe_cmul.argtypes = [vp, vp, vp, C.c_int64, vp]
     lib.fringe_cmul_device.argtypes = [vp, vp, vp, C.c_int64, vp, vp]
+    # context-bound profiling hooks (include/fringe_b200_prof.h, group a)
     lib.fringe_evd_stats.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.fringe_evd_phase_cycles.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.fringe_last_kernel_ms.argtypes = [vp, i, C.POINTER(C.c_float)]
-    lib.fringe_fp32_peak.argtypes = [vp, C.POINTER(d)]
-    lib.fringe_block_fma_rate.argtypes = [vp, C.POINTER(d)]
-    lib.fringe_mma_tf32_rate.argtypes = [vp, C.POINTER(d)]
+    lib.fringe_prof_force_generic.argtypes = [vp, i]
     for name in declared_symbols():
         getattr(lib, name)          # AttributeError here = header / library mismatch
     return lib
 
 
 lib = _load()
+
+
+def prof_lib() -> C.CDLL:
+    """libfringe_b200_prof.so: the stand-alone microbenchmarks (bench.py, scripts/)."""
+    p = C.CDLL(PROF_LIB_PATH)
+    for name in ("fringe_prof_fp32_peak", "fringe_prof_mma_tf32_rate", "fringe_prof_fp64_peak"):
+        getattr(p, name).argtypes = [C.c_int, C.POINTER(C.c_double)]
+    p.fringe_prof_block_fma_rate.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    return p

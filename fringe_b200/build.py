@@ -23,8 +23,11 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--use_fast_math=false", "-Xcompiler", "-fPIC",
               "-ccbin", HOST_CXX] + ARCH
 
-CUDA_SOURCES = ["capi.cu", "nmap_kernels.cu", "evd_kernels.cu", "evd_fast.cu", "evd_mma.cu", "mle_kernels.cu", "post_kernels.cu", "microbench.cu"]
+CUDA_SOURCES = ["capi.cu", "nmap_kernels.cu", "evd_kernels.cu", "evd_mma.cu", "mle_kernels.cu", "post_kernels.cu"]
 CUDA_LIB = os.path.join(LIBDIR, "libfringe_b200.so")
+# profiling microbenchmarks: their own library (include/fringe_b200_prof.h), not part of the drop-in one
+PROF_SOURCES = ["microbench.cu"]
+PROF_LIB = os.path.join(LIBDIR, "libfringe_b200_prof.so")
 
 
 def _newer(target: str, deps: list[str]) -> bool:
@@ -42,10 +45,11 @@ def _run(cmd: list[str]) -> None:
 def build_cuda(force: bool = False, verbose_ptxas: bool = False, phase_clocks: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     srcs = [os.path.join(CSRC, s) for s in CUDA_SOURCES]
-    deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "fringe_b200.h"),
-                   os.path.abspath(__file__)]
+    psrcs = [os.path.join(CSRC, s) for s in PROF_SOURCES]
+    deps = srcs + psrcs + [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "fringe_b200.h"),
+                           os.path.join(ROOT, "include", "fringe_b200_prof.h"), os.path.abspath(__file__)]
     deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    if force or _newer(CUDA_LIB, deps):
+    if force or _newer(CUDA_LIB, deps) or _newer(PROF_LIB, deps):
         flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
         if verbose_ptxas:
             flags += ["-Xptxas", "-v"]
@@ -55,9 +59,10 @@ def build_cuda(force: bool = False, verbose_ptxas: bool = False, phase_clocks: b
         os.makedirs(objdir, exist_ok=True)
         procs = []
         objs = []
-        for s in srcs:                       # one nvcc per translation unit, in parallel
+        pobjs = []
+        for s in srcs + psrcs:               # one nvcc per translation unit, in parallel
             o = os.path.join(objdir, os.path.basename(s)[:-3] + ".o")
-            objs.append(o)
+            (pobjs if s in psrcs else objs).append(o)
             cmd = [NVCC] + flags + ["-c", "-o", o, s]
             print("+", " ".join(cmd), flush=True)
             procs.append((cmd, subprocess.Popen(cmd)))
@@ -65,6 +70,7 @@ def build_cuda(force: bool = False, verbose_ptxas: bool = False, phase_clocks: b
             if p.wait() != 0:
                 raise subprocess.CalledProcessError(p.returncode, cmd)
         _run([NVCC] + ARCH + ["-shared", "-o", CUDA_LIB] + objs)
+        _run([NVCC] + ARCH + ["-shared", "-o", PROF_LIB] + pobjs)
     return CUDA_LIB
 
 

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/fringe_b200.h"
+#include "../../include/fringe_b200_prof.h"
 #include "common.cuh"
 
 namespace {
@@ -36,6 +37,7 @@ struct fringe_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     int64_t launches = 0;
+    bool prof_generic = false;            // fringe_prof_force_generic: A/B comparisons only
     // workspaces reused across blocks
     DevBuf amp, valid, zpix, adtab, alpha, stats, scratch;
     DevBuf in_slc, in_mask, in_wts, o_count, o_wts, o_out, o_tcorr, o_comp;
@@ -171,7 +173,6 @@ int check_geometry(fringe_ctx* ctx, int cols, int lines, int bands, int Nx, int 
     if (!ctx) return FRINGE_ERR_ARGUMENT;
     if (cols <= 0 || lines <= 0 || bands <= 0 || Nx < 0 || Ny < 0)
         return fail(ctx, FRINGE_ERR_ARGUMENT, "non-positive geometry");
-    if ((long)fringe_nulong(Nx, Ny) > 32) return fail(ctx, FRINGE_ERR_UNSUPPORTED, "window larger than 1024 pixels");
     return FRINGE_OK;
 }
 
@@ -324,7 +325,7 @@ int nmap_prepare(fringe_ctx* ctx, int cols, int lines, int bands, int Nx, int Ny
     CU(cudaSetDevice(ctx->device));
     const size_t npix = (size_t)cols * lines;
     if (!fringe::nmap_plan(bands, Nx, Ny, method, &plan->g))
-        return fail(ctx, FRINGE_ERR_UNSUPPORTED, "bands x window too large for the shared-memory tile");
+        return fail(ctx, FRINGE_ERR_UNSUPPORTED, "no pair-test plan");      // not reached: the plan falls back to the global-memory kernel
     if (method == FRINGE_NMAP_KS2) {
         fringe_ks2_critical_count(bands, pvalue, &plan->kcrit, nullptr);
     } else {
@@ -366,7 +367,6 @@ int nmap_launch_rows(fringe_ctx* ctx, const NmapPlan& plan, const float* slc, co
 // rows per pipeline stage: ~384 MB of input per stage, at least 8 rows (20 / 40 / 80 / 160 rows of the
 // 30 x 20000 bench geometry measured 308 / 293 / 287 / 293 ms per end-to-end step)
 int chunk_rows(int cols, int bands, int total_rows) {
-    if (const char* e = getenv("FRINGE_CHUNK_ROWS")) { const int v = atoi(e); if (v > 0) return v; }
     const double row_bytes = (double)cols * bands * 8.0;
     int r = (int)(384.0e6 / row_bytes);
     if (r < 8) r = 8;
@@ -472,6 +472,65 @@ int fringe_nmap_block(fringe_ctx* ctx, const float* slc, const uint8_t* mask, co
     return FRINGE_OK;
 }
 
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// Link-time drop-in for the reference's one C-style kernel boundary (src/nmap/nmap_cuda.h:13-17, called
+// at src/nmap/nmap.cpp:475-485 under BUILD_NMAP_WITH_CUDA): same names, same C++ linkage, same argument
+// meaning -- amplitudes pixel-major [pixel][band] as computed by nmap.cpp:370-381, the validity mask,
+// host pointers in and out, synchronous, KS2 (the reference's device path ignores `method`,
+// nmap_cuda.cu:310).  lockGPU / unlockGPU create / destroy the context on device 0 like
+// nmap_cuda.cu:368-376.  Errors are reported on stderr and, as in cudaUtils.h:13-21, end the process.
+// ---------------------------------------------------------------------------------------
+namespace { fringe_ctx* g_shim_ctx = nullptr; }
+
+void lockGPU() {
+    if (g_shim_ctx) return;
+    const int rc = fringe_create(0, &g_shim_ctx);
+    if (rc != FRINGE_OK) { std::fprintf(stderr, "lockGPU: %s\n", fringe_status_string(rc)); std::exit(1); }
+}
+
+void unlockGPU() {
+    if (g_shim_ctx) fringe_destroy(g_shim_ctx);
+    g_shim_ctx = nullptr;
+}
+
+void nmapProcessBlock(float* amp, unsigned char* msk, int cols, int lines, int bands, int* cnt, unsigned int* wmask,
+                      int wtslen, double pval, int Nx, int Ny) {
+    if (!g_shim_ctx) lockGPU();
+    fringe_ctx* ctx = g_shim_ctx;
+    auto die = [&](const char* what, int rc) {
+        std::fprintf(stderr, "nmapProcessBlock: %s (%s: %s)\n", what, fringe_status_string(rc), fringe_last_error(ctx));
+        std::exit(1);
+    };
+    if (!amp || !msk || !cnt || !wmask || wtslen != fringe_nulong(Nx, Ny)) die("bad arguments", FRINGE_ERR_ARGUMENT);
+    cudaStream_t st = ctx->stream;
+    NmapPlan plan;
+    int rc = nmap_prepare(ctx, cols, lines, bands, Nx, Ny, FRINGE_NMAP_KS2, pval, st, &plan);
+    if (rc) die("prepare", rc);
+    const size_t npix = (size_t)cols * lines;
+    auto cu = [&](cudaError_t e, const char* what) { if (e != cudaSuccess) { cuda_fail(ctx, e, what); die(what, FRINGE_ERR_CUDA); } };
+    cu(ctx->in_slc.ensure(npix * bands * sizeof(float)), "alloc amp");
+    cu(ctx->in_mask.ensure(npix), "alloc mask");
+    cu(ctx->o_count.ensure(npix * sizeof(int32_t)), "alloc count");
+    cu(ctx->o_wts.ensure(npix * wtslen * sizeof(uint32_t)), "alloc wts");
+    cu(cudaMemcpyAsync(ctx->in_slc.p, amp, npix * bands * sizeof(float), cudaMemcpyHostToDevice, st), "upload amp");
+    cu(cudaMemcpyAsync(ctx->in_mask.p, msk, npix, cudaMemcpyHostToDevice, st), "upload mask");
+    cu(cudaMemsetAsync(ctx->o_wts.p, 0, npix * wtslen * sizeof(uint32_t), st), "clear wts");
+    cu(fringe::launch_amp_in_sort((const float*)ctx->in_slc.p, (const uint8_t*)ctx->in_mask.p, (long)npix, bands,
+                                  (float*)ctx->amp.p, (uint8_t*)ctx->valid.p, st), "sort");
+    cu(fringe::launch_nmap((const float*)ctx->amp.p, (const uint8_t*)ctx->valid.p, cols, lines, bands, Nx, Ny, FRINGE_NMAP_KS2,
+                           plan.kcrit, plan.scrit, (const double*)ctx->adtab.p, plan.g, (int32_t*)ctx->o_count.p,
+                           (uint32_t*)ctx->o_wts.p, 0, lines, st), "pair tests");
+    cu(fringe::launch_count((const uint32_t*)ctx->o_wts.p, cols, wtslen, 0, lines, (int32_t*)ctx->o_count.p, st), "count");
+    ctx->launches += 3;
+    cu(cudaMemcpyAsync(cnt, ctx->o_count.p, npix * sizeof(int32_t), cudaMemcpyDeviceToHost, st), "download count");
+    cu(cudaMemcpyAsync(wmask, ctx->o_wts.p, npix * wtslen * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "download wts");
+    cu(cudaStreamSynchronize(st), "synchronize");
+}
+
+extern "C" {
+
 // ---------------------------------------------------------------------------------------
 // evd / phase_link
 // ---------------------------------------------------------------------------------------
@@ -503,16 +562,8 @@ int evd_prepare(fringe_ctx* ctx, int cols, int lines, int bands, int method, int
     CU(cudaSetDevice(ctx->device));
     const size_t npix = (size_t)cols * lines;
     plan->NP = (bands + 1) & ~1;
-    plan->generic = getenv("FRINGE_EVD_GENERIC") != nullptr;      // debug switch
-    if (!plan->generic && variant == FRINGE_VARIANT_EVD && method != FRINGE_EVD_MLE &&
-        fringe::evd_fast_padded_bands(bands) > 0)
-    {
-        plan->NP = fringe::evd_fast_padded_bands(bands);
-        plan->zblock = fringe::evd_fast_block(bands);
-    }
-    if (!plan->generic && variant == FRINGE_VARIANT_EVD && method != FRINGE_EVD_MLE &&
-        fringe::evd_mma_order(bands) > 0 && getenv("FRINGE_EVD_FP32") == nullptr)   // debug switch: FP32-FMA covariance kernel
-    {
+    plan->generic = ctx->prof_generic;
+    if (!plan->generic && variant == FRINGE_VARIANT_EVD && method != FRINGE_EVD_MLE && fringe::evd_mma_order(bands) > 0) {
         plan->NP = 64;                        // 128 floats per pixel: TF32 hi and lo parts of 32 bands
         plan->zblock = -1;
     }
@@ -520,8 +571,8 @@ int evd_prepare(fringe_ctx* ctx, int cols, int lines, int bands, int method, int
     // exhausted / out-of-block SHP slots at it instead of branching
     CU(ctx->zpix.ensure((npix + 1) * plan->NP * sizeof(float2)));
     CU(cudaMemsetAsync((float2*)ctx->zpix.p + npix * plan->NP, 0, plan->NP * sizeof(float2), st));
-    CU(ctx->stats.ensure(12 * sizeof(unsigned long long)));      // 4 counters + 8 phase clocks
-    CU(cudaMemsetAsync(ctx->stats.p, 0, 12 * sizeof(unsigned long long), st));
+    CU(ctx->stats.ensure(16 * sizeof(unsigned long long)));      // 8 counters + 8 phase clocks
+    CU(cudaMemsetAsync(ctx->stats.p, 0, 16 * sizeof(unsigned long long), st));
     return FRINGE_OK;
 }
 
@@ -549,7 +600,7 @@ int evd_launch_rows(fringe_ctx* ctx, const EvdPlan& plan, const float* slc, cons
     a.out = (float2*)out; a.tcorr = tcorr; a.comp = (float2*)comp;
     a.stats = (unsigned long long*)ctx->stats.p;
     a.zblock = plan.zblock; a.tile_pairs = 0; a.scratch = nullptr;
-    if (!fringe::evd_fast_supported(a) || plan.generic) {
+    if (plan.zblock >= 0) {
         int gw; long gg; size_t gs; bool use_scratch;
         fringe::evd_generic_plan(a, &gw, &gg, &gs, &use_scratch);
         if (use_scratch) {
@@ -558,7 +609,7 @@ int evd_launch_rows(fringe_ctx* ctx, const EvdPlan& plan, const float* slc, cons
             a.scratch = (unsigned char*)ctx->scratch.p;
         }
     }
-    a.force_generic = (plan.generic ? 1 : 0) | (getenv("FRINGE_EVD_DEBUG_SHORT") ? (atoi(getenv("FRINGE_EVD_DEBUG_SHORT")) << 1) : 0);
+    a.force_generic = plan.generic ? 1 : 0;
     int nl = 0;
     CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_EVD][0], st));
     if (n_lines > 0) CU(fringe::launch_evd(a, st, &nl));
@@ -897,44 +948,29 @@ int fringe_last_kernel_ms(fringe_ctx* ctx, int kernel, float* ms) {
     return FRINGE_OK;
 }
 
-int fringe_fp32_peak(fringe_ctx* ctx, double* tflops) {
-    if (!ctx || !tflops) return FRINGE_ERR_ARGUMENT;
-    CU(cudaSetDevice(ctx->device));
-    CU(fringe::measure_fp32_peak(ctx->stream, tflops));
-    return FRINGE_OK;
-}
-
-int fringe_block_fma_rate(fringe_ctx* ctx, double tflops[3]) {
-    if (!ctx || !tflops) return FRINGE_ERR_ARGUMENT;
-    CU(cudaSetDevice(ctx->device));
-    CU(fringe::measure_block_fma(ctx->stream, tflops));
-    return FRINGE_OK;
-}
-
-int fringe_mma_tf32_rate(fringe_ctx* ctx, double* tflops) {
-    if (!ctx || !tflops) return FRINGE_ERR_ARGUMENT;
-    CU(cudaSetDevice(ctx->device));
-    CU(fringe::measure_mma_tf32(ctx->stream, tflops));
-    return FRINGE_OK;
-}
-
 int fringe_evd_phase_cycles(fringe_ctx* ctx, int64_t cycles[8]) {
     if (!ctx || !cycles) return FRINGE_ERR_ARGUMENT;
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
-    unsigned long long h[12] = {0};
+    unsigned long long h[16] = {0};
     if (ctx->stats.p) CU(cudaMemcpy(h, ctx->stats.p, sizeof(h), cudaMemcpyDeviceToHost));
-    for (int i = 0; i < 8; ++i) cycles[i] = (int64_t)h[4 + i];
+    for (int i = 0; i < 8; ++i) cycles[i] = (int64_t)h[8 + i];
     return FRINGE_OK;
 }
 
-int fringe_evd_stats(fringe_ctx* ctx, int64_t stats[4]) {
+int fringe_evd_stats(fringe_ctx* ctx, int64_t stats[8]) {
     if (!ctx || !stats) return FRINGE_ERR_ARGUMENT;
     CU(cudaSetDevice(ctx->device));
     CU(cudaDeviceSynchronize());
-    unsigned long long h[4] = {0, 0, 0, 0};
+    unsigned long long h[8] = {0};
     if (ctx->stats.p) CU(cudaMemcpy(h, ctx->stats.p, sizeof(h), cudaMemcpyDeviceToHost));
-    for (int i = 0; i < 4; ++i) stats[i] = (int64_t)h[i];
+    for (int i = 0; i < 8; ++i) stats[i] = (int64_t)h[i];
+    return FRINGE_OK;
+}
+
+int fringe_prof_force_generic(fringe_ctx* ctx, int on) {
+    if (!ctx) return FRINGE_ERR_ARGUMENT;
+    ctx->prof_generic = on != 0;
     return FRINGE_OK;
 }
 

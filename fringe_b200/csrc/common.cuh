@@ -14,13 +14,17 @@ cudaError_t launch_amp_sort(const float2* slc, const uint8_t* mask, const double
                             int lines, int bands, float* amp, uint8_t* valid, int row0, int nrows,
                             cudaStream_t st);
 
+// the same from amplitudes handed over pixel-major [pixel][band] with the reference's validity mask (nmapProcessBlock)
+cudaError_t launch_amp_in_sort(const float* amp_in, const uint8_t* msk, long npix, int bands, float* amp, uint8_t* valid,
+                               cudaStream_t st);
+
 struct NmapGeometry {
-    int tile_w, tile_h;      // output pixels per CTA
+    int tile_w, tile_h;      // output pixels per CTA (0 x 0: the global-memory kernel, no tile fits)
     size_t smem_bytes;
     bool table_in_smem;      // AD2 term table staged in shared memory
 };
-// Chooses the CTA tile so that tile+halo of all ranks fits in shared memory.
-// Returns false when even the smallest tile does not fit.
+// Chooses the CTA tile so that tile+halo of all ranks fits in shared memory; when even the smallest
+// tile does not fit, the plan selects the (slower) global-memory kernel.  Always returns true.
 bool nmap_plan(int bands, int Nx, int Ny, int method, NmapGeometry* g);
 
 cudaError_t launch_nmap(const float* amp, const uint8_t* valid, int cols, int lines, int bands,
@@ -52,10 +56,10 @@ struct EvdArgs {
     float* tcorr;            // [npix]
     float2* comp;            // [npix]
     unsigned long long* stats;   // [4] device counters
-    int force_generic;           // debug: bit 0 bypasses the register-blocked kernel, upper bits cap iterations
+    int force_generic;           // profiling (fringe_prof_force_generic): bit 0 bypasses the specialised kernels
     unsigned char* scratch;      // generic kernel, large bands: per-warp workspaces in global memory (else NULL)
-    int tile_pairs;              // set by the fast kernel's launcher: pixel pairs per CTA tile
-    int zblock;                  // 0: zpix is interleaved complex; B > 0: de-interleaved per block of B samples
+    int tile_pairs;              // set by the launchers of the specialised kernels: columns per CTA segment
+    int zblock;                  // 0: zpix is interleaved complex [pix][NP]; -1: the TF32 hi/lo layout of evd_mma.cu
 };
 int evd_max_bands(int method, int variant);
 // launch geometry of the generic kernel; *use_scratch = the per-warp workspace does not fit shared
@@ -64,14 +68,7 @@ void evd_generic_plan(const EvdArgs& a, int* warps, long* grid, size_t* smem, bo
 size_t evd_generic_workspace_bytes(int bands, bool dp);
 cudaError_t launch_evd(const EvdArgs& a, cudaStream_t st, int* n_launches);
 
-// ---- evd_fast.cu ----------------------------------------------------------------------
-// Register-blocked packed-FMA kernel (evd_fast2.cu) for EVD/STBAS with bands <= 30.  It needs the
-// pixel-major stack padded to evd_fast_padded_bands(bands) samples per pixel (0 = not eligible)
-// and de-interleaved per block of evd_fast_block(bands) samples.
-int evd_fast_padded_bands(int bands);
-int evd_fast_block(int bands);
-bool evd_fast_supported(const EvdArgs& a);
-cudaError_t launch_evd_fast(const EvdArgs& a, cudaStream_t st);
+// ---- evd_mma.cu -----------------------------------------------------------------------
 // tensor-pipe variant (evd_mma.cu): its own pixel-major layout (zblock = -1, NP = 64: 128 floats per
 // pixel, TF32 hi and lo parts) and eigen order evd_mma_order(bands) (0 = not eligible, bands <= 32)
 int evd_mma_order(int bands);
@@ -93,13 +90,5 @@ cudaError_t launch_ampdispersion(const float2* slc, const double* alpha, long np
 cudaError_t launch_despeck(const float2* z1, const float2* z2, const uint32_t* wts, int cols, int lines, int Nx,
                            int Ny, int first_line, int n_lines, int mode, float2* d1, float2* d2, float2* out,
                            cudaStream_t st);
-
-// ---- microbench.cu --------------------------------------------------------------------
-cudaError_t measure_fp32_peak(cudaStream_t st, double* tflops);
-// register-resident 6x6 complex block update (144 FMAs per step, 3 CTAs/SM like the evd kernel):
-// tflops[0..2] = interleaved / de-interleaved scalar FFMA, packed f32x2
-cudaError_t measure_block_fma(cudaStream_t st, double* tflops);
-// dense TFLOP/s of mma.sync.m16n8k8 TF32 (legacy warp-level tensor path), 12 accumulator tiles per warp
-cudaError_t measure_mma_tf32(cudaStream_t st, double* tflops);
 
 }  // namespace fringe

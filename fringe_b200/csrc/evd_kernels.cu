@@ -35,7 +35,7 @@ namespace fringe {
 #ifdef FRINGE_PHASE_CLOCKS
 #define GPH_DECL long long gph_t = clock64(); unsigned long long gph[6] = {0, 0, 0, 0, 0, 0};
 #define GPH_MARK(k) { const long long gph_n = clock64(); gph[k] += (unsigned long long)(gph_n - gph_t); gph_t = gph_n; }
-#define GPH_FLUSH if (a.stats && lane == 0) { for (int k = 0; k < 6; ++k) atomicAdd(&a.stats[4 + k], gph[k]); }
+#define GPH_FLUSH if (a.stats && lane == 0) { for (int k = 0; k < 6; ++k) atomicAdd(&a.stats[8 + k], gph[k]); }
 #else
 #define GPH_DECL
 #define GPH_MARK(k)
@@ -646,8 +646,9 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
     for (long i = beg + warp; i < end; i += WARPS) {
         const long p = (long)a.first_line * a.cols + i;
         const int ci = (int)(p / a.cols), cj = (int)(p - (long)ci * a.cols);
-        const uint32_t myword = (lane < a.nulong) ? __ldg(&a.wts[p * a.nulong + lane]) : 0u;
-        const uint32_t cword = __shfl_sync(FULL, myword, center >> 5);
+        // lane w keeps mask word (32 * round + w); windows of more than 1024 pixels take several rounds
+        uint32_t myword = (lane < a.nulong) ? __ldg(&a.wts[p * a.nulong + lane]) : 0u;
+        const uint32_t cword = __ldg(&a.wts[p * a.nulong + (center >> 5)]);
         float tc = 0.f;
         bool have_vec = false;
         float2 vf[HR];
@@ -683,7 +684,11 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
                 int cnt = 0;
                 int dy = -a.Ny, dx = -a.Nx;
                 for (int f = 0; f < W; ++f) {
-                    const uint32_t wd = __shfl_sync(FULL, myword, f >> 5);
+                    if ((f & 1023) == 0 && (f > 0 || chunk > 0)) {      // next (or, for a new entry chunk, first) round of 32 words
+                        const int w = (f >> 5) + lane;
+                        myword = (w < a.nulong) ? __ldg(&a.wts[p * a.nulong + w]) : 0u;
+                    }
+                    const uint32_t wd = __shfl_sync(FULL, myword, (f >> 5) & 31);
                     const int yy = ci + dy, xx = cj + dx;
                     if (((wd >> (f & 31)) & 1u) && yy >= 0 && yy < a.lines && xx >= 0 && xx < a.cols) {
                         ++cnt;
@@ -1015,7 +1020,7 @@ static cudaError_t launch_evd_dp(const EvdArgs& a, cudaStream_t st) {
 cudaError_t launch_evd(const EvdArgs& a, cudaStream_t st, int* n_launches) {
     const bool dp = (a.method == 1) || (a.variant == 1);
     if (n_launches) *n_launches = 1;
-    if (!(a.force_generic & 1) && evd_fast_supported(a)) return launch_evd_fast(a, st);
+    if (!(a.force_generic & 1) && a.zblock < 0) return launch_evd_mma(a, st);
     if (!(a.force_generic & 1) && dp && a.zblock == 0 && evd_mle_order(a.bands) > 0) return launch_evd_mle(a, st);
     return dp ? launch_evd_dp<true>(a, st) : launch_evd_dp<false>(a, st);
 }

@@ -1,6 +1,6 @@
 // Tensor-pipe covariance (3xTF32 mma.sync) + in-register power iteration (sm_100a), bands <= 32.
 //
-// Same arithmetic contract and the same eigen solve / epilogue as evd_fast.cu (EVD / STBAS,
+// Same arithmetic contract and the same eigen solve / epilogue as experimental/evd_fast_fp32_fma.cu (EVD / STBAS,
 // evd.cpp control flow); only the masked Gram product C = sum_k z_k z_k^H moves from FP32 FMAs
 // to the warp-level tensor path:
 //
@@ -42,7 +42,7 @@ namespace fringe {
 #ifdef FRINGE_PHASE_CLOCKS
 #define PHASE_DECL long long ph_t = clock64(); unsigned long long ph[6] = {0, 0, 0, 0, 0, 0};
 #define PHASE_MARK(k) { const long long ph_n = clock64(); ph[k] += (unsigned long long)(ph_n - ph_t); ph_t = ph_n; }
-#define PHASE_FLUSH if (a.stats && lane == 0) { for (int k = 0; k < 6; ++k) atomicAdd(&a.stats[4 + k], ph[k]); }
+#define PHASE_FLUSH if (a.stats && lane == 0) { for (int k = 0; k < 6; ++k) atomicAdd(&a.stats[8 + k], ph[k]); }
 #else
 #define PHASE_DECL
 #define PHASE_MARK(k)
@@ -422,12 +422,12 @@ __global__ void __launch_bounds__(512, 1) k_evd_mma(const EvdArgs a) {
                 x.x *= sc; x.y *= sc;
             }
             PHASE_MARK(3)
-            // Power iteration with heavy-ball momentum (see evd_fast.cu): x+ = C x / lambda - beta x-
+            // Power iteration with heavy-ball momentum (see experimental/evd_fast_fp32_fma.cu): x+ = C x / lambda - beta x-
             float lam = 1.f, inv_lam = 1.f, beta = 0.f, rho_prev = -1.f;
             float2 xp = make_float2(0.f, 0.f);
             int it = 0, buf = 0, next_chk = 3, gap = 2;
             bool conv = false;
-            const int kMaxIter = (a.force_generic >> 1) ? (a.force_generic >> 1) : 1000;   // upper bits: timing experiment only
+            const int kMaxIter = 1000;
             const float tol2 = 1.0e-12f;                 // relative residual 1e-6: 3x margin on the 1e-3 rad gate in the worst test pixel
 #pragma unroll 1
             for (; it < kMaxIter; ++it) {
@@ -628,8 +628,7 @@ static cudaError_t launch_mma_t(const EvdArgs& a, cudaStream_t st) {
     // bands of BAND rows x column segments; segments as long as possible (less halo re-reading at
     // their ends) while there are still >= mult CTAs per SM to even out the tail (one CTA per SM at a
     // time: 8 per SM lost 8 % to the last partial wave, 48 and 96 measured equal)
-    int mult = 48;
-    if (const char* ev = getenv("FRINGE_EVD_CHUNKS")) { const int v = atoi(ev); if (v > 0) mult = v; }
+    const int mult = 48;
     const int nbands = (a.n_lines + Cfg::BAND - 1) / Cfg::BAND;
     int nseg = (nsm * mult + nbands - 1) / nbands;
     if (nseg < 1) nseg = 1;

@@ -95,6 +95,10 @@ int nmap_process(nmapOptions* opts) {
         std::cout << "Cannot open stack file { " << opts->inputDS << " } for reading: " << in.error << "\nExiting with error code .... (102) \n";
         return 102;
     }
+    if (!in.is_cfloat32_stack()) {
+        std::cout << "Input stack { " << opts->inputDS << " } is not a VRT with one flat CFloat32 file per band\nExiting with error code .... (102) \n";
+        return 102;
+    }
     const int cols = in.cols, rows = in.rows, nbands = in.count();
     std::cout << "Number of rows  = " << rows << "\nNumber of cols  = " << cols << "\nNumber of bands = " << nbands << "\n";
     Raster msk;
@@ -116,7 +120,8 @@ int nmap_process(nmapOptions* opts) {
     if (ngpu <= 0) { std::cout << "No CUDA device available and there is no CPU path.\n"; return 200 + FRINGE_ERR_NO_DEVICE; }
     std::cout << "Executing on " << ngpu << " GPU(s)\n";
 
-    const int blockysize = block_height(opts->memsize, cols, opts->blocksize, 4 * (nbands + 2 + nulong), rows, Ny);
+    // every worker (one per GPU) holds its own pinned block: the memory budget is shared between them
+    const int blockysize = block_height(std::max(1, opts->memsize / ngpu), cols, opts->blocksize, 4 * (nbands + 2 + nulong), rows, Ny);
     std::cout << "Block size = " << blockysize << " lines \n";
     const std::vector<Block> sched = make_schedule(rows, blockysize, Ny);
     std::cout << "Total number of blocks to process: " << sched.size() << "\n";
@@ -157,6 +162,7 @@ int nmap_process(nmapOptions* opts) {
         const size_t bp = (size_t)cols * blockysize;
         Pinned slc, mask, count, wts;
         std::vector<int16_t> c16(bp);
+        std::vector<char> mask_scratch;
         if (!slc.alloc(bp * nbands * 8) || !mask.alloc(bp) || !count.alloc(bp * 4) || !wts.alloc(bp * nulong * 4)) {
             rc = 200 + FRINGE_ERR_MEMORY; fringe_destroy(ctx); return;
         }
@@ -166,10 +172,7 @@ int nmap_process(nmapOptions* opts) {
             bool ok = true;
             for (int band = 0; band < nbands && ok; ++band)
                 ok = in.read_band_lines(band, b.yoff, b.inysize, (char*)slc.p + (size_t)band * np * 8, 8);
-            if (ok && have_mask) {
-                ok = msk.interleaved ? msk.read_interleaved_lines(b.yoff, b.inysize, mask.p)
-                                     : msk.read_band_lines(0, b.yoff, b.inysize, mask.p, 1);
-            }
+            if (ok && have_mask) ok = msk.read_mask_lines(b.yoff, b.inysize, (uint8_t*)mask.p, mask_scratch);
             if (!ok) {
                 std::lock_guard<std::mutex> g(log_mu);
                 std::cout << "Error reading data at line " << b.yoff << "\nExiting with error code .... (108) \n";
@@ -226,6 +229,10 @@ static int evd_driver(evdOptions* opts, int variant) {
         std::cout << "Cannot open stack file { " << opts->inputDS << " } for reading: " << in.error << "\n";
         return 102;
     }
+    if (!in.is_cfloat32_stack()) {
+        std::cout << "Input stack { " << opts->inputDS << " } is not a VRT with one flat CFloat32 file per band\nExiting with error code .... (102) \n";
+        return 102;
+    }
     const int cols = in.cols, rows = in.rows, nbands = in.count();
     std::cout << "Number of rows  = " << rows << "\nNumber of cols  = " << cols << "\nNumber of bands = " << nbands << "\n";
     if (method == FRINGE_EVD_STBAS) {
@@ -256,7 +263,7 @@ static int evd_driver(evdOptions* opts, int variant) {
     const int ngpu = visible_gpus();
     if (ngpu <= 0) { std::cout << "No CUDA device available and there is no CPU path.\n"; return 200 + FRINGE_ERR_NO_DEVICE; }
 
-    const int blockysize = block_height(opts->memsize, cols, opts->blocksize, nbands * 20 + 4 + nulong, rows, Ny);
+    const int blockysize = block_height(std::max(1, opts->memsize / ngpu), cols, opts->blocksize, nbands * 20 + 4 + nulong, rows, Ny);
     std::cout << "Block size = " << blockysize << " lines \n";
     const std::vector<Block> sched = make_schedule(rows, blockysize, Ny);
     std::cout << "Total number of blocks to process: " << sched.size() << "\n";
@@ -361,6 +368,10 @@ int despeck_process(despeckOptions* opts) {
         std::cout << "Cannot open stack file { " << opts->inputDS << " } for reading: " << in.error << "\nExiting with error code .... (102) \n";
         return 102;
     }
+    if (!in.is_cfloat32_stack()) {
+        std::cout << "Input stack { " << opts->inputDS << " } is not a VRT with one flat CFloat32 file per band\nExiting with error code .... (102) \n";
+        return 102;
+    }
     const int cols = in.cols, rows = in.rows, nbands = in.count();
     std::cout << "Number of rows  = " << rows << "\nNumber of cols  = " << cols << "\nNumber of bands = " << nbands << "\n";
     const int band1 = opts->ibands[0], band2 = opts->ibands[1];
@@ -385,7 +396,7 @@ int despeck_process(despeckOptions* opts) {
     const int ngpu = visible_gpus();
     if (ngpu <= 0) { std::cout << "No CUDA device available and there is no CPU path.\n"; return 200 + FRINGE_ERR_NO_DEVICE; }
 
-    const int blockysize = block_height(opts->memsize, cols, opts->blocksize, 4 * (6 + nulong), rows, Ny);   // despeck.cpp:155
+    const int blockysize = block_height(std::max(1, opts->memsize / ngpu), cols, opts->blocksize, 4 * (6 + nulong), rows, Ny);   // despeck.cpp:155
     std::cout << "Block size = " << blockysize << " lines \n";
     const std::vector<Block> sched = make_schedule(rows, blockysize, Ny);
     std::cout << "Total number of blocks to process: " << sched.size() << "\n";
@@ -452,6 +463,10 @@ int ampdispersion_process(ampdispersionOptions* opts) {
     Raster in;
     if (!in.open(opts->inputDS)) {
         std::cout << "Cannot open stack file { " << opts->inputDS << " } for reading: " << in.error << "\nExiting with error code .... (102) \n";
+        return 102;
+    }
+    if (!in.is_cfloat32_stack()) {
+        std::cout << "Input stack { " << opts->inputDS << " } is not a VRT with one flat CFloat32 file per band\nExiting with error code .... (102) \n";
         return 102;
     }
     const int cols = in.cols, rows = in.rows, nbands = in.count();

@@ -9,6 +9,7 @@
 // A GDAL-backed implementation of the same three classes is the deployment alternative
 // (INTEGRATION.md); nothing here touches the device.
 #pragma once
+#include <errno.h>
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -47,6 +48,28 @@ inline bool slurp(const std::string& path, std::string& out) {
     std::ifstream f(path.c_str(), std::ios::binary);
     if (!f) return false;
     std::ostringstream ss; ss << f.rdbuf(); out = ss.str();
+    return true;
+}
+
+// pread / pwrite until every byte has moved: a single call may transfer less than asked (Linux caps one
+// call near 2 GiB; signals interrupt it), which is not an error
+inline bool pread_all(int fd, void* dst, size_t bytes, off_t off) {
+    char* p = static_cast<char*>(dst);
+    while (bytes > 0) {
+        const ssize_t k = ::pread(fd, p, bytes > ((size_t)1 << 30) ? ((size_t)1 << 30) : bytes, off);
+        if (k < 0) { if (errno == EINTR) continue; return false; }
+        if (k == 0) return false;                     // end of file before the block was complete
+        p += k; off += k; bytes -= (size_t)k;
+    }
+    return true;
+}
+inline bool pwrite_all(int fd, const void* src, size_t bytes, off_t off) {
+    const char* p = static_cast<const char*>(src);
+    while (bytes > 0) {
+        const ssize_t k = ::pwrite(fd, p, bytes > ((size_t)1 << 30) ? ((size_t)1 << 30) : bytes, off);
+        if (k < 0) { if (errno == EINTR) continue; return false; }
+        p += k; off += k; bytes -= (size_t)k;
+    }
     return true;
 }
 
@@ -283,6 +306,7 @@ struct Raster {
 
     // Read lines [yoff, yoff+n) of band b (0-based) as tightly packed samples.
     bool read_band_lines(int b, int yoff, int n, void* dst, int elem_bytes) {
+        if (b < 0 || b >= (int)bands.size()) { error = "band index outside the raster (not a band-per-file stack?)"; return false; }
         const RawBand& rb = bands[b];
         if (rb.elem_bytes != elem_bytes) { error = "unexpected sample type in " + rb.path; return false; }
         char* out = static_cast<char*>(dst);
@@ -291,11 +315,11 @@ struct Raster {
         for (int r = 0; r < n; ++r) {
             const long off = rb.image_offset + (long)(rb.y_off + yoff + r) * rb.line_offset + (long)rb.x_off * rb.pixel_offset;
             if (packed) {
-                const ssize_t want = (ssize_t)cols * elem_bytes;
-                if (::pread(rb.fd, out + (size_t)r * want, want, off) != want) { error = "short read from " + rb.path; return false; }
+                const size_t want = (size_t)cols * elem_bytes;
+                if (!pread_all(rb.fd, out + (size_t)r * want, want, off)) { error = "short read from " + rb.path; return false; }
             } else {
                 tmp.resize((size_t)cols * rb.pixel_offset);
-                if (::pread(rb.fd, tmp.data(), tmp.size(), off) != (ssize_t)tmp.size()) { error = "short read from " + rb.path; return false; }
+                if (!pread_all(rb.fd, tmp.data(), tmp.size(), off)) { error = "short read from " + rb.path; return false; }
                 for (int c = 0; c < cols; ++c) std::memcpy(out + ((size_t)r * cols + c) * elem_bytes, tmp.data() + (size_t)c * rb.pixel_offset, elem_bytes);
             }
         }
@@ -304,8 +328,34 @@ struct Raster {
     // Read lines of an interleaved (BIP) ENVI file: all bands, pixel-interleaved, packed.
     bool read_interleaved_lines(int yoff, int n, void* dst) {
         const size_t line_bytes = (size_t)cols * envi.bands * envi_type_bytes(envi.data_type);
-        const ssize_t want = (ssize_t)(line_bytes * n);
-        if (::pread(fd, dst, want, envi.header_offset + (long)yoff * line_bytes) != want) { error = "short read from " + path; return false; }
+        if (!pread_all(fd, dst, line_bytes * (size_t)n, (off_t)envi.header_offset + (off_t)yoff * (off_t)line_bytes)) { error = "short read from " + path; return false; }
+        return true;
+    }
+    // Lines of a single-band raster of any integer / float type as a byte mask (non-zero -> 1), the
+    // conversion GDAL's RasterIO(..., GDT_Byte) applies for nmap.cpp:323-343 in effect.
+    bool read_mask_lines(int yoff, int n, uint8_t* dst, std::vector<char>& scratch) {
+        int eb = 0; bool is_float = false;
+        if (interleaved) { eb = envi_type_bytes(envi.data_type); is_float = (envi.data_type == 4 || envi.data_type == 5); }
+        else if (!bands.empty()) { eb = bands[0].elem_bytes; is_float = lower(bands[0].dtype).find("float") != std::string::npos; }
+        const size_t npx = (size_t)cols * n;
+        if (eb == 1) return interleaved ? read_interleaved_lines(yoff, n, dst) : read_band_lines(0, yoff, n, dst, 1);
+        if (eb != 2 && eb != 4 && eb != 8) { error = "unsupported mask sample type in " + path; return false; }
+        scratch.resize(npx * eb);
+        if (!(interleaved ? read_interleaved_lines(yoff, n, scratch.data()) : read_band_lines(0, yoff, n, scratch.data(), eb))) return false;
+        for (size_t k = 0; k < npx; ++k) {
+            bool nz;
+            if (eb == 2) { uint16_t v; std::memcpy(&v, scratch.data() + 2 * k, 2); nz = v != 0; }
+            else if (eb == 4 && is_float) { float v; std::memcpy(&v, scratch.data() + 4 * k, 4); nz = v != 0.f; }
+            else if (eb == 4) { uint32_t v; std::memcpy(&v, scratch.data() + 4 * k, 4); nz = v != 0; }
+            else { double v; std::memcpy(&v, scratch.data() + 8 * k, 8); nz = v != 0.0; }
+            dst[k] = nz ? 1 : 0;
+        }
+        return true;
+    }
+    // true when every band is a flat CFloat32 file (what the drivers read as the SLC stack)
+    bool is_cfloat32_stack() const {
+        if (interleaved || bands.empty()) return false;
+        for (const auto& b : bands) if (lower(b.dtype) != "cfloat32" || b.elem_bytes != 8) return false;
         return true;
     }
 };
@@ -319,7 +369,7 @@ struct EnviWriter {
         path = p; cols = c; rows = r; bands = nb; data_type = envi_type;
         fd = ::open(p.c_str(), O_CREAT | O_TRUNC | O_WRONLY, 0666);
         if (fd < 0) return false;
-        const off_t total = (off_t)cols * rows * bands * envi_type_bytes(envi_type);
+        const off_t total = (off_t)cols * (off_t)rows * (off_t)bands * (off_t)envi_type_bytes(envi_type);
         if (::ftruncate(fd, total) != 0) return false;
         return write_header();
     }
@@ -335,8 +385,7 @@ struct EnviWriter {
     }
     bool write_lines(int y0, int n, const void* src) {
         const size_t line_bytes = (size_t)cols * bands * envi_type_bytes(data_type);
-        const ssize_t want = (ssize_t)(line_bytes * n);
-        return ::pwrite(fd, src, want, (off_t)y0 * line_bytes) == want;
+        return pwrite_all(fd, src, line_bytes * (size_t)n, (off_t)y0 * (off_t)line_bytes);
     }
     bool close_file() {
         bool ok = true;

@@ -1,10 +1,14 @@
+// libfringe_b200_prof.so -- stand-alone microbenchmarks (include/fringe_b200_prof.h, group b); not part of
+// the drop-in library.
 // FP32 FMA peak microbenchmark: the measured denominator of the covariance + eigen roofline.
 // Two register-resident variants are timed (scalar FFMA chains and packed fma.rn.f32x2, the
 // sm_100 two-wide FP32 FMA); the better one is reported.
 #include <cstdio>
 #include <cstdlib>
 
-#include "common.cuh"
+#include <cuda_runtime.h>
+
+#include "../../include/fringe_b200_prof.h"
 
 namespace fringe {
 
@@ -285,3 +289,66 @@ cudaError_t measure_mma_tf32(cudaStream_t st, double* tflops) {
 }
 
 }  // namespace fringe
+
+// ---------------------------------------------------------------------------------------------------
+// FP64 FMA peak (register-resident DFMA chains): denominator for the MLE / phase_link kernel.
+namespace fringe {
+__global__ void __launch_bounds__(256) k_dfma(double* out, int iters, double x, double y) {
+    double a[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a[c] = (double)(threadIdx.x + c) * 1e-6;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) a[c] = fma(a[c], x, y);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) s += a[c];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+cudaError_t measure_fp64_peak(cudaStream_t st, double* tflops) {
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = nsm * 8, threads = 256, iters = 1024;
+    double* out = nullptr;
+    cudaError_t e = cudaMalloc(&out, (size_t)blocks * threads * sizeof(double));
+    if (e != cudaSuccess) return e;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0, st);
+        k_dfma<<<blocks, threads, 0, st>>>(out, iters, 0.999, 1e-3);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = (ms > 0.f) ? 2.0 * blocks * threads * (double)iters * 64 / (ms * 1e-3) * 1e-12 : 0.0;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops = best;
+    return cudaGetLastError();
+}
+}  // namespace fringe
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+static int prof_run(int device, cudaError_t (*fn)(cudaStream_t, double*), double* out) {
+    if (!out) return FRINGE_ERR_ARGUMENT;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) { cudaGetLastError(); return FRINGE_ERR_NO_DEVICE; }
+    if (cudaSetDevice(device) != cudaSuccess) return FRINGE_ERR_CUDA;
+    return fn(nullptr, out) == cudaSuccess ? FRINGE_OK : FRINGE_ERR_CUDA;
+}
+int fringe_prof_fp32_peak(int device, double* tflops) { return prof_run(device, fringe::measure_fp32_peak, tflops); }
+int fringe_prof_block_fma_rate(int device, double tflops[3]) { return prof_run(device, fringe::measure_block_fma, tflops); }
+int fringe_prof_mma_tf32_rate(int device, double* tflops) { return prof_run(device, fringe::measure_mma_tf32, tflops); }
+int fringe_prof_fp64_peak(int device, double* tflops) { return prof_run(device, fringe::measure_fp64_peak, tflops); }
+}

@@ -92,6 +92,46 @@ cudaError_t launch_amp_sort(const float2* slc, const uint8_t* mask, const double
     return cudaGetLastError();
 }
 
+// Sort of amplitudes handed over pixel-major ([pixel][band], the reference's arma::fmat amp(N, cols * H)),
+// as nmapProcessBlock receives them (src/nmap/nmap_cuda.h:13-17, runSortAmp nmap_cuda.cu:243-255): same
+// shared-memory insertion sort, output rank-major like k_amp_sort.  msk is the reference's zeromask.
+__global__ void __launch_bounds__(128) k_amp_in_sort(const float* __restrict__ amp_in, const uint8_t* __restrict__ msk,
+                                                     long npix, int bands, float* __restrict__ amp,
+                                                     uint8_t* __restrict__ valid) {
+    extern __shared__ float s_col[];   // [bands][blockDim.x]
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const long p = (long)blockIdx.x * nt + tid;
+    if (p >= npix) return;
+    const bool ok = msk[p] != 0;
+    for (int b = 0; b < bands; ++b) s_col[b * nt + tid] = amp_in[p * bands + b];
+    if (ok) {
+        for (int i = 1; i < bands; ++i) {
+            const float key = s_col[i * nt + tid];
+            int j = i - 1;
+            while (j >= 0) {
+                const float c = s_col[j * nt + tid];
+                if (!(c > key)) break;
+                s_col[(j + 1) * nt + tid] = c;
+                --j;
+            }
+            s_col[(j + 1) * nt + tid] = key;
+        }
+    }
+    for (int b = 0; b < bands; ++b) amp[(long)b * npix + p] = ok ? s_col[b * nt + tid] : 0.f;
+    valid[p] = ok ? 1 : 0;
+}
+
+cudaError_t launch_amp_in_sort(const float* amp_in, const uint8_t* msk, long npix, int bands, float* amp, uint8_t* valid,
+                               cudaStream_t st) {
+    if (npix <= 0) return cudaSuccess;
+    int nt = 128;
+    while (nt > 32 && (size_t)nt * bands * sizeof(float) > 160 * 1024) nt >>= 1;
+    cudaError_t e = cudaFuncSetAttribute(k_amp_in_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    k_amp_in_sort<<<(unsigned)((npix + nt - 1) / nt), nt, (size_t)nt * bands * sizeof(float), st>>>(amp_in, msk, npix, bands, amp, valid);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------
 // pair tests
 // ---------------------------------------------------------------------------------------
@@ -237,6 +277,67 @@ __global__ void k_nmap(const NmapKernelArgs a) {
     atomicOr(&wp[(W - 1) >> 5], word);
 }
 
+// The same pair tests straight from global memory, for band counts x windows whose tile does not fit
+// shared memory (e.g. 200 dates with the 59 x 19 window of the sequential workflow): one thread per
+// pixel, keys read rank-major (coalesced across the threads of a warp, served by L1 / L2).  Slower than
+// the staged kernel, identical results.
+template <int METHOD>
+__global__ void __launch_bounds__(128) k_nmap_global(const NmapKernelArgs a) {
+    const int N = a.bands, Nx = a.Nx, Ny = a.Ny;
+    const long npix = (long)a.cols * a.lines;
+    const int gx = blockIdx.x * blockDim.x + threadIdx.x, gy = a.row0 + blockIdx.y;
+    if (gx >= a.cols || gy >= a.row1) return;
+    const long p = (long)gy * a.cols + gx;
+    if (!a.valid[p]) return;
+    const uint32_t* __restrict__ key = reinterpret_cast<const uint32_t*>(a.amp);
+    uint32_t* wp = a.wts + p * a.nulong;
+    const int WX = 2 * Nx + 1, W = WX * (2 * Ny + 1), center = Ny * WX + Nx;
+    uint32_t word = 1u << (center & 31);
+    const int kc = min(max(a.kcrit, 0), N);
+    int dy = 0, dx = 1;
+    for (int f = center + 1; f < W; ++f) {
+        if (dx > Nx) { dx = -Nx; ++dy; }
+        if ((f & 31) == 0) { atomicOr(&wp[(f - 1) >> 5], word); word = 0u; }
+        const int qy = gy + dy, qx = gx + dx;
+        if (qy < a.lines && qx >= 0 && qx < a.cols) {
+            const long q = (long)qy * a.cols + qx;
+            if (a.valid[q]) {
+                bool similar;
+                if (METHOD == 0) {
+                    bool bad = a.kcrit < 0;
+                    for (int i = kc; i < N && !bad; ++i) {
+                        const uint32_t a_hi = __ldg(&key[(long)i * npix + p]), a_lo = __ldg(&key[(long)(i - kc) * npix + p]);
+                        const uint32_t b_hi = __ldg(&key[(long)i * npix + q]), b_lo = __ldg(&key[(long)(i - kc) * npix + q]);
+                        bad = (b_lo > a_hi) | (a_lo > b_hi);
+                    }
+                    similar = !bad;
+                } else {
+                    // AD2unique.hpp:211-303 merge (ties: the element of B first), table sum in the reference's order
+                    int ia = 0, ib = 0, m2 = 0;
+                    uint32_t va = __ldg(&key[p]), vb = __ldg(&key[q]);
+                    double S = 0.0;
+                    const double* Tj = a.ad_table;
+                    for (int j = 0; j < 2 * N - 1; ++j) {
+                        const bool ta = (ib >= N) || (ia < N && va < vb);
+                        if (ta) { ++ia; ++m2; va = (ia < N) ? __ldg(&key[(long)ia * npix + p]) : 0xFFFFFFFFu; }
+                        else { ++ib; --m2; vb = (ib < N) ? __ldg(&key[(long)ib * npix + q]) : 0xFFFFFFFFu; }
+                        S = __dadd_rn(S, Tj[abs(m2)]);
+                        Tj += N + 1;
+                    }
+                    similar = S <= a.scrit;
+                }
+                if (similar) {
+                    word |= (1u << (f & 31));
+                    const int fm = W - 1 - f;
+                    atomicOr(&a.wts[q * a.nulong + (fm >> 5)], 1u << (fm & 31));
+                }
+            }
+        }
+        ++dx;
+    }
+    atomicOr(&wp[(W - 1) >> 5], word);
+}
+
 // neighbour count = number of set bits (count(pp) is incremented exactly once per bit set,
 // nmap.cpp:447-468)
 __global__ void __launch_bounds__(256) k_count(const uint32_t* __restrict__ wts, int nulong, long p0,
@@ -269,7 +370,9 @@ bool nmap_plan(int bands, int Nx, int Ny, int method, NmapGeometry* g) {
             }
         }
     }
-    return false;
+    // no tile fits: the global-memory kernel (tile_w = 0 marks it)
+    g->tile_w = 0; g->tile_h = 0; g->smem_bytes = 0; g->table_in_smem = false;
+    return true;
 }
 
 cudaError_t launch_nmap(const float* amp, const uint8_t* valid, int cols, int lines, int bands,
@@ -283,9 +386,15 @@ cudaError_t launch_nmap(const float* amp, const uint8_t* valid, int cols, int li
     a.Nx = Nx; a.Ny = Ny; a.nulong = ((2 * Ny + 1) * (2 * Nx + 1) + 31) / 32;
     a.kcrit = kcrit; a.scrit = scrit; a.ad_table = ad_table; a.table_in_smem = g.table_in_smem ? 1 : 0;
     a.count = count; a.wts = wts;
+    cudaError_t e;
+    if (g.tile_w == 0) {                                   // tile does not fit shared memory
+        dim3 gblock(128), ggrid((cols + 127) / 128, nrows);
+        if (method == 0) k_nmap_global<0><<<ggrid, gblock, 0, st>>>(a);
+        else k_nmap_global<1><<<ggrid, gblock, 0, st>>>(a);
+        return cudaGetLastError();
+    }
     dim3 block(g.tile_w, g.tile_h);
     dim3 grid((cols + g.tile_w - 1) / g.tile_w, (nrows + g.tile_h - 1) / g.tile_h);
-    cudaError_t e;
     if (method == 0) {
         e = cudaFuncSetAttribute(k_nmap<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes);
         if (e != cudaSuccess) return e;

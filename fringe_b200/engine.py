@@ -96,9 +96,14 @@ class Context:
         return int(lib.fringe_launch_count(self._h))
 
     def evd_stats(self) -> dict:
-        arr = (C.c_int64 * 4)()
+        arr = (C.c_int64 * 8)()
         self._check(lib.fringe_evd_stats(self._h, arr))
-        return {"pixels": arr[0], "power_iterations": arr[1], "fp64_pixels": arr[2], "capped": arr[3]}
+        return {"pixels": arr[0], "power_iterations": arr[1], "fp64_pixels": arr[2], "capped": arr[3],
+                "factorisations": arr[4]}
+
+    def force_generic(self, on: bool) -> None:
+        """Profiling / A-B tests only: send evd calls to the generic any-N kernel."""
+        self._check(lib.fringe_prof_force_generic(self._h, 1 if on else 0))
 
     KERNELS = {"amp_sort": 0, "nmap": 1, "transpose": 2, "evd": 3, "cmul": 4, "despeck": 5, "ampdispersion": 6}
 
@@ -109,7 +114,12 @@ class Context:
 
     def fp32_peak_tflops(self) -> float:
         t = C.c_double(0)
-        self._check(lib.fringe_fp32_peak(self._h, C.byref(t)))
+        self._check(_lib.prof_lib().fringe_prof_fp32_peak(self.device, C.byref(t)))
+        return float(t.value)
+
+    def fp64_peak_tflops(self) -> float:
+        t = C.c_double(0)
+        self._check(_lib.prof_lib().fringe_prof_fp64_peak(self.device, C.byref(t)))
         return float(t.value)
 
     # ---- host arrays -----------------------------------------------------------------------

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define FRINGE_ABI_VERSION 1
+#define FRINGE_ABI_VERSION 2
 
 /* status codes */
 enum {
@@ -181,41 +181,6 @@ int fringe_despeck_block_device(fringe_ctx* ctx, const float* z1, const float* z
 
 /* Largest `bands` the evd kernels accept for the given method. */
 int fringe_evd_max_bands(int method, int variant);
-
-/* ---- measurement hooks ----------------------------------------------------------------
- * Device time of the most recent launch of one kernel, from CUDA events recorded on the
- * stream it was launched on (synchronises on the closing event). */
-enum {
-    FRINGE_KERNEL_AMP_SORT = 0,   /* amplitude + per-pixel sort */
-    FRINGE_KERNEL_NMAP = 1,       /* window pair tests */
-    FRINGE_KERNEL_TRANSPOSE = 2,  /* band-major -> pixel-major re-layout */
-    FRINGE_KERNEL_EVD = 3,        /* covariance + eigen + post-processing */
-    FRINGE_KERNEL_CMUL = 4,       /* datum adjustment product */
-    FRINGE_KERNEL_DESPECK = 5,    /* despeck preparation + SHP-weighted average */
-    FRINGE_KERNEL_AMPDISP = 6,    /* amplitude dispersion */
-    FRINGE_KERNEL_COUNT = 7
-};
-int fringe_last_kernel_ms(fringe_ctx* ctx, int kernel, float* ms);
-/* FP32 FMA throughput of the device measured with a register-resident FMA loop; the roofline
- * denominator for the covariance + eigen kernel (MEASURED_PEAKS.json carries no FP32 figure). */
-int fringe_fp32_peak(fringe_ctx* ctx, double* tflops);
-/* FP32 rate of a register-resident 6x6 complex block update (the covariance inner step with loads
- * and address arithmetic removed): the practical ceiling of that loop, [0] interleaved and [1] de-interleaved scalar FFMA, [2] packed fma.rn.f32x2. */
-int fringe_block_fma_rate(fringe_ctx* ctx, double tflops[3]);
-/* Dense TF32 TFLOP/s of the warp-level mma.sync.m16n8k8 path (12 independent accumulator tiles per
- * warp): the tensor-pipe alternative the covariance was weighed against. */
-int fringe_mma_tf32_rate(fringe_ctx* ctx, double* tflops);
-
-/* Per-pixel solver statistics of the most recent evd call on this context (debug/bench):
- * stats[0] pixels solved, [1] total FP32 power iterations, [2] pixels that took the FP64
- * certified path, [3] pixels that hit an iteration cap.  Synchronises the context. */
-int fringe_evd_stats(fringe_ctx* ctx, int64_t stats[4]);
-/* Per-phase warp cycles of the most recent register-blocked evd launch (summed over warps):
- * [0] SHP lists, [1] covariance accumulation, [2] normalisation + hand-off to shared memory,
- * [3] row load + start vector, [4] power iteration, [5] epilogue, [6..7] spare.  All zero unless
- * the library was built with -DFRINGE_PHASE_CLOCKS (python -m fringe_b200.build --phase-clocks);
- * a profiling build, not for timing. */
-int fringe_evd_phase_cycles(fringe_ctx* ctx, int64_t cycles[8]);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,21 @@ def test_library_exports_every_declared_symbol():
     raw = C.CDLL(_lib.LIB_PATH)
     for n in names:
         assert hasattr(raw, n), n
-    assert _lib.lib.fringe_abi_version() == 1
+    assert _lib.lib.fringe_abi_version() == 2
+    # profiling header: context-bound hooks live in the main library, the microbenchmarks in their own
+    prof = C.CDLL(_lib.PROF_LIB_PATH)
+    for n in _lib.declared_symbols(_lib.PROF_HEADER_PATH):
+        assert hasattr(prof if n.startswith("fringe_prof_") and n != "fringe_prof_force_generic" else raw, n), n
+    # nothing measurement-related is left in the drop-in header
+    assert not [n for n in names if "peak" in n or "rate" in n or "stats" in n or "cycles" in n]
+
+
+def test_nmap_cuda_h_shim_is_exported_with_the_reference_linkage():
+    """src/nmap/nmap_cuda.h:13-17 declares plain C++ functions: the library must export exactly those mangled names
+    so that nmap.cpp built with -DBUILD_NMAP_WITH_CUDA links against it."""
+    raw = C.CDLL(_lib.LIB_PATH)
+    for sym in ("_Z16nmapProcessBlockPfPhiiiPiPjidii", "_Z7lockGPUv", "_Z9unlockGPUv"):
+        assert hasattr(raw, sym), sym
 
 
 def test_no_torch_or_oracle_in_the_product_library():

@@ -187,15 +187,40 @@ def test_tensor_kernel_wide_window(ctx, oracle_lib):
     assert oracle_lib.nmap_block(slc, 10, 10)[0].max() > 64
 
 
-def test_fp32_kernel_switch(ctx, oracle_lib, monkeypatch):
-    # FRINGE_EVD_FP32 routes the same call to the FP32-FMA kernel (evd_fast.cu); both meet the gates
-    slc = synth.make_stack(30, 32, 64, seed=8, region=32)
+def test_generic_kernel_agrees_with_the_specialised_ones(ctx, oracle_lib):
+    """The any-N kernel (profiling switch fringe_prof_force_generic) and the specialised kernels (tensor-pipe EVD,
+    register-sweep MLE) both meet the gates on the same call -- and really are different kernels."""
+    slc = synth.make_stack(20, 32, 64, seed=8, region=32)
     wts = _nmap(oracle_lib, slc, 5, 2)
-    ref = oracle_lib.evd_block(slc, wts, 5, 2, method=0)
-    tensor = ctx.evd_block(slc, wts, 5, 2, method="EVD")
-    monkeypatch.setenv("FRINGE_EVD_FP32", "1")
-    fp32 = ctx.evd_block(slc, wts, 5, 2, method="EVD")
-    monkeypatch.delenv("FRINGE_EVD_FP32")
-    _compare(ref, tensor)
-    _compare(ref, fp32)
-    assert not np.array_equal(tensor[0], fp32[0])          # really two different kernels
+    for method, code in (("EVD", 0), ("MLE", 1)):
+        ref = oracle_lib.evd_block(slc, wts, 5, 2, method=code)
+        fast = ctx.evd_block(slc, wts, 5, 2, method=method)
+        ctx.force_generic(True)
+        try:
+            generic = ctx.evd_block(slc, wts, 5, 2, method=method)
+        finally:
+            ctx.force_generic(False)
+        _compare(ref, fast, borderline=3)
+        _compare(ref, generic, borderline=3)
+        assert not np.array_equal(fast[0], generic[0])
+
+
+@pytest.mark.parametrize("method,variant,bands", [("EVD", 0, 12), ("MLE", 0, 12), ("MLE", 1, 12), ("MLE", 0, 40)])
+def test_sequential_default_window_59x19(ctx, oracle_lib, method, variant, bands):
+    """src/sequential/sequential.py:27-30 defaults -x 29 -y 9: 1121 window pixels, 36 mask words (more than one
+    word per lane) through the tensor-pipe, MLE and generic kernels."""
+    slc = synth.make_stack(bands, 26, 80, seed=60 + bands, region=16)
+    wts = _nmap(oracle_lib, slc, 29, 9)
+    assert wts.shape[-1] == 36
+    code = {"EVD": 0, "MLE": 1}[method]
+    ref = oracle_lib.evd_block(slc, wts, 29, 9, method=code, variant=variant, min_neighbors=5)
+    gpu = ctx.evd_block(slc, wts, 29, 9, method=method, variant=variant, min_neighbors=5)
+    _compare(ref, gpu, borderline=3)
+
+
+def test_workflow_window_23x11(ctx, oracle_lib):
+    # docs/workflows.md:28 passes -x 11 -y 5 as half windows: 23 x 11 = 253 pixels, 8 words
+    slc = synth.make_stack(30, 30, 64, seed=23, region=32)
+    wts = _nmap(oracle_lib, slc, 11, 5)
+    for method, code in (("EVD", 0), ("MLE", 1)):
+        _compare(oracle_lib.evd_block(slc, wts, 11, 5, method=code), ctx.evd_block(slc, wts, 11, 5, method=method), borderline=3)

@@ -99,3 +99,46 @@ def test_unknown_method_status(ctx):
     with pytest.raises(FringeError) as e:
         ctx.nmap_block(slc, 1, 1, method="XYZ")
     assert e.value.status == 1      # same code nmap_process returns for an unknown method
+
+
+# ---- windows and band counts beyond the shared-memory tile / the 32-word mask (the reference's own
+# sequential defaults, 59 x 19 = 1121 pixels = 36 words, used to be rejected) -------------------------------
+@pytest.mark.parametrize("Nx,Ny,method", [(29, 9, "KS2"), (11, 5, "KS2"), (11, 5, "AD2"), (29, 9, "AD2")])
+def test_wide_windows_sequential_defaults(ctx, oracle_lib, Nx, Ny, method):
+    slc = synth.make_stack(12, 30, 90, seed=5, region=16)
+    c = _check(ctx, oracle_lib, slc, Nx, Ny, method)
+    if (Nx, Ny) == (29, 9):
+        from fringe_b200 import engine
+        assert engine.nulong(Nx, Ny) == 36
+
+
+@pytest.mark.parametrize("method", ["KS2", "AD2"])
+def test_200_bands_global_memory_kernel(ctx, oracle_lib, method):
+    """BASELINE configs[3]: the SHP input of the 200-date sequential case.  With the 59 x 19 window no tile of 200
+    ranks fits shared memory: the pair tests run from global memory, results unchanged."""
+    slc = synth.make_stack(200, 24, 70, seed=9, region=16)
+    _check(ctx, oracle_lib, slc, 29, 9, method)
+    _check(ctx, oracle_lib, slc, 5, 2, method)
+
+
+def test_nmap_process_block_shim(oracle_lib):
+    """The reference's own C-style boundary (src/nmap/nmap_cuda.h:13-17): amplitudes in, KS2, host pointers."""
+    import ctypes as C
+    from fringe_b200 import _lib
+    raw = C.CDLL(_lib.LIB_PATH)
+    fn = getattr(raw, "_Z16nmapProcessBlockPfPhiiiPiPjidii")
+    fn.restype = None
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int]
+    slc = synth.make_stack(20, 48, 80, seed=11, region=16)
+    bands, lines, cols = slc.shape
+    c_ref, w_ref, amp_sorted = oracle_lib.nmap_block(slc, 5, 2, want_amp=True)
+    # what nmap.cpp:370-381 hands over: unsorted amplitudes [pixel][band] and the validity mask
+    amp = np.ascontiguousarray(np.abs(slc).transpose(1, 2, 0).astype(np.float32))
+    valid = np.ascontiguousarray((np.abs(slc) != 0).all(axis=0).astype(np.uint8))
+    amp[valid == 0] = 0
+    cnt = np.zeros((lines, cols), np.int32)
+    wts = np.zeros((lines, cols, 2), np.uint32)
+    getattr(raw, "_Z7lockGPUv")()
+    fn(amp.ctypes.data, valid.ctypes.data, cols, lines, bands, cnt.ctypes.data, wts.ctypes.data, 2, 0.05, 5, 2)
+    getattr(raw, "_Z9unlockGPUv")()
+    assert np.array_equal(cnt, c_ref) and np.array_equal(wts, w_ref)
