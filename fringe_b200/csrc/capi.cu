@@ -41,6 +41,7 @@ struct fringe_ctx {
     // workspaces reused across blocks
     DevBuf amp, valid, zpix, adtab, alpha, stats, scratch;
     DevBuf in_slc, in_mask, in_wts, o_count, o_wts, o_out, o_tcorr, o_comp;
+    DevBuf seq_stack[2], seq_comp, seq_mini, seq_datum;     // fringe_sequential_block
     // cached AD2 table key
     int adtab_bands = -1;
     // CUDA events bracketing the most recent launch of each kernel (on its launching stream)
@@ -225,7 +226,8 @@ int fringe_destroy(fringe_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf* all[] = {&c->amp, &c->valid, &c->zpix, &c->adtab, &c->alpha, &c->stats, &c->scratch, &c->in_slc, &c->in_mask,
-                     &c->in_wts, &c->o_count, &c->o_wts, &c->o_out, &c->o_tcorr, &c->o_comp};
+                     &c->in_wts, &c->o_count, &c->o_wts, &c->o_out, &c->o_tcorr, &c->o_comp, &c->seq_stack[0], &c->seq_stack[1],
+                     &c->seq_comp, &c->seq_mini, &c->seq_datum};
     for (DevBuf* b : all) b->release();
     for (int k = 0; k < FRINGE_KERNEL_COUNT; ++k)
         for (int j = 0; j < 2; ++j) if (c->ev[k][j]) cudaEventDestroy(c->ev[k][j]);
@@ -775,6 +777,131 @@ int fringe_nmap_evd_block(fringe_ctx* ctx, const float* slc, const uint8_t* mask
             CU(cudaMemcpyAsync(tcorr + eoff, (float*)ctx->o_tcorr.p + eoff, ecnt * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_out));
             CU(cudaMemcpyAsync((float2*)comp + eoff, (float2*)ctx->o_comp.p + eoff, ecnt * sizeof(float2), cudaMemcpyDeviceToHost, ctx->s_out));
         }
+    }
+    CU(cudaStreamSynchronize(ctx->s_out));
+    CU(cudaStreamSynchronize(st));
+    return FRINGE_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------
+// sequential estimator on the device (src/sequential/sequential.py:190-254 + python/adjustMiniStacks.py)
+// ---------------------------------------------------------------------------------------
+int fringe_sequential_halo(int n_dates, int mini_stack_size, int Ny) {
+    if (n_dates <= 0 || mini_stack_size <= 0 || Ny < 0) return 0;
+    const int nmini = (n_dates + mini_stack_size - 1) / mini_stack_size;
+    return (nmini + 1) * Ny;
+}
+
+int fringe_sequential_block(fringe_ctx* ctx, const float* slc, const uint32_t* wts, int cols, int lines, int n_dates,
+                            int Nx, int Ny, int first_line, int n_lines, int mini_stack_size, int method, int bandwidth,
+                            float* out_mini, float* tcorr_mini, float* comp, float* out_datum, float* tcorr_datum,
+                            float* adjusted) {
+    if (!ctx) return FRINGE_ERR_ARGUMENT;
+    if (!slc || !wts || !out_mini || !tcorr_mini || !comp || !out_datum || !tcorr_datum)
+        return fail(ctx, FRINGE_ERR_ARGUMENT, "null pointer");
+    if (mini_stack_size < 2 || n_dates < 2) return fail(ctx, FRINGE_ERR_ARGUMENT, "need >= 2 dates per ministack");
+    const int s = mini_stack_size;
+    const int nmini = (n_dates + s - 1) / s;
+    if (n_dates - (nmini - 1) * s < 2 && nmini > 1)
+        return fail(ctx, FRINGE_ERR_ARGUMENT, "the last ministack would hold a single acquisition");
+    const int max_bands = (nmini - 1) + s;                       // compressed SLCs + own acquisitions of the last ministack
+    int rc = check_evd(ctx, cols, lines, max_bands, Nx, Ny, first_line, n_lines, method, bandwidth, 1, FRINGE_VARIANT_EVD);
+    if (rc) return rc;
+    if (nmini < 2) return fail(ctx, FRINGE_ERR_ARGUMENT, "fewer than two ministacks: nothing to connect (run fringe_evd_block)");
+    if (nmini > fringe::evd_max_bands(method, FRINGE_VARIANT_EVD)) return fail(ctx, FRINGE_ERR_UNSUPPORTED, "too many ministacks for the datum connection");
+    if (n_lines == 0) return FRINGE_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t npix = (size_t)cols * lines;
+    const size_t nout = (size_t)cols * n_lines;                  // pixels of the delivered rows
+    const size_t ooff = (size_t)first_line * cols;
+    const int nu = fringe_nulong(Nx, Ny);
+    const int last = first_line + n_lines;
+
+    CU(ctx->in_wts.ensure(npix * nu * sizeof(uint32_t)));
+    for (int b = 0; b < 2; ++b) CU(ctx->seq_stack[b].ensure(npix * max_bands * sizeof(float2)));
+    CU(ctx->seq_comp.ensure(npix * nmini * sizeof(float2)));
+    CU(ctx->seq_mini.ensure(nout * n_dates * sizeof(float2)));
+    CU(ctx->seq_datum.ensure(npix * nmini * sizeof(float2)));
+    CU(ctx->o_out.ensure(npix * max_bands * sizeof(float2)));
+    CU(ctx->o_tcorr.ensure(npix * sizeof(float)));
+    CU(ctx->o_comp.ensure(npix * nmini * sizeof(float)));        // temporal coherence of every ministack
+    CU(cudaMemcpyAsync(ctx->in_wts.p, wts, npix * nu * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->s_in));
+    CU(cudaMemsetAsync(ctx->seq_comp.p, 0, npix * nmini * sizeof(float2), st));
+    size_t ev = 0;
+    cudaEvent_t buf_free[2] = {nullptr, nullptr};                // solve that last read a stack buffer has finished
+    float2* d_out = (float2*)ctx->o_out.p;
+
+    for (int k = 1; k <= nmini; ++k) {
+        const int d0 = (k - 1) * s, d1 = std::min(n_dates, k * s);
+        const int nk = (k - 1) + (d1 - d0);
+        float2* buf = (float2*)ctx->seq_stack[k & 1].p;
+        // rows on which this ministack's compressed SLC is needed: the delivered rows plus one window halo per later
+        // stage (each later ministack and the datum connection look Ny lines further), clipped to the block
+        const int h = (nmini - k + 1) * Ny;
+        const int r0 = std::max(0, first_line - h), r1 = std::min(lines, last + h);
+        const int t0 = std::max(0, r0 - Ny), t1 = std::min(lines, r1 + Ny);
+        // own acquisitions -> planes [k-1, nk) of the buffer (only the rows the solve reads), overlapping the previous solve
+        if (buf_free[k & 1]) CU(cudaStreamWaitEvent(ctx->s_in, buf_free[k & 1], 0));
+        {
+            const size_t off = (size_t)t0 * cols, cnt = (size_t)(t1 - t0) * cols;
+            CU(cudaMemcpy2DAsync(buf + (size_t)(k - 1) * npix + off, npix * sizeof(float2), (const float2*)slc + (size_t)d0 * npix + off,
+                                 npix * sizeof(float2), cnt * sizeof(float2), d1 - d0, cudaMemcpyHostToDevice, ctx->s_in));
+        }
+        cudaEvent_t e_in = ctx->pool_event(ev++);
+        CU(cudaEventRecord(e_in, ctx->s_in));
+        CU(cudaStreamWaitEvent(st, e_in, 0));
+        // compressed SLCs of the earlier ministacks -> planes [0, k-1)
+        if (k > 1) CU(cudaMemcpyAsync(buf, ctx->seq_comp.p, (size_t)(k - 1) * npix * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+        EvdPlan plan;
+        rc = evd_prepare(ctx, cols, lines, nk, method, FRINGE_VARIANT_EVD, st, &plan);
+        if (rc) return rc;
+        rc = evd_launch_rows(ctx, plan, (const float*)buf, (const uint32_t*)ctx->in_wts.p, cols, lines, nk, Nx, Ny, t0, t1 - t0, r0,
+                             r1 - r0, method, bandwidth, k, FRINGE_VARIANT_EVD, 2, (float*)d_out, (float*)ctx->o_comp.p + (size_t)(k - 1) * npix,
+                             (float*)((float2*)ctx->seq_comp.p + (size_t)(k - 1) * npix), st);
+        if (rc) return rc;
+        // keep the phasors of the own acquisitions (delivered rows only) for the adjustment; results to the host
+        CU(cudaMemcpy2DAsync((float2*)ctx->seq_mini.p + (size_t)d0 * nout, nout * sizeof(float2), d_out + (size_t)(k - 1) * npix + ooff,
+                             npix * sizeof(float2), nout * sizeof(float2), d1 - d0, cudaMemcpyDeviceToDevice, st));
+        cudaEvent_t e_done = ctx->pool_event(ev++);
+        CU(cudaEventRecord(e_done, st));
+        buf_free[k & 1] = e_done;
+        CU(cudaStreamWaitEvent(ctx->s_out, e_done, 0));
+        CU(cudaMemcpy2DAsync((float2*)out_mini + (size_t)d0 * npix + ooff, npix * sizeof(float2), (float2*)ctx->seq_mini.p + (size_t)d0 * nout,
+                             nout * sizeof(float2), nout * sizeof(float2), d1 - d0, cudaMemcpyDeviceToHost, ctx->s_out));
+        CU(cudaMemcpyAsync(tcorr_mini + (size_t)(k - 1) * npix + ooff, (float*)ctx->o_comp.p + (size_t)(k - 1) * npix + ooff,
+                           nout * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_out));
+        CU(cudaMemcpyAsync((float2*)comp + (size_t)(k - 1) * npix + ooff, (float2*)ctx->seq_comp.p + (size_t)(k - 1) * npix + ooff,
+                           nout * sizeof(float2), cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    // datum connection: all compressed SLCs, first band is the reference (sequential.py:247-254)
+    {
+        EvdPlan plan;
+        rc = evd_prepare(ctx, cols, lines, nmini, method, FRINGE_VARIANT_EVD, st, &plan);
+        if (rc) return rc;
+        const int t0 = std::max(0, first_line - Ny), t1 = std::min(lines, last + Ny);
+        rc = evd_launch_rows(ctx, plan, (const float*)ctx->seq_comp.p, (const uint32_t*)ctx->in_wts.p, cols, lines, nmini, Nx, Ny, t0,
+                             t1 - t0, first_line, n_lines, method, bandwidth, 1, FRINGE_VARIANT_EVD, 2, (float*)ctx->seq_datum.p,
+                             (float*)ctx->o_tcorr.p, (float*)d_out, st);      // the datum run's own compressed SLC is not used
+        if (rc) return rc;
+        CU(cudaMemcpy2DAsync((float2*)out_datum + ooff, npix * sizeof(float2), (float2*)ctx->seq_datum.p + ooff, npix * sizeof(float2),
+                             nout * sizeof(float2), nmini, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(tcorr_datum + ooff, (float*)ctx->o_tcorr.p + ooff, nout * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    // wrapped time series: ministack phasor x datum phasor of its ministack (adjustMiniStacks.py:180-199)
+    if (adjusted) {
+        for (int k = 1; k <= nmini; ++k) {
+            const int d0 = (k - 1) * s, d1 = std::min(n_dates, k * s);
+            for (int d = d0; d < d1; ++d) {
+                float2* m = (float2*)ctx->seq_mini.p + (size_t)d * nout;
+                // the datum plane has the block's row pitch; the kept ministack phasors are compact: multiply row-compact copies
+                CU(fringe::launch_cmul(m, (const float2*)ctx->seq_datum.p + (size_t)(k - 1) * npix + ooff, m, (long)nout, st));
+                ctx->launches += 1;
+            }
+        }
+        CU(cudaMemcpy2DAsync((float2*)adjusted + ooff, npix * sizeof(float2), ctx->seq_mini.p, nout * sizeof(float2), nout * sizeof(float2),
+                             n_dates, cudaMemcpyDeviceToHost, st));
     }
     CU(cudaStreamSynchronize(ctx->s_out));
     CU(cudaStreamSynchronize(st));

@@ -769,7 +769,15 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
 
                 bool run_evd = !ismle && a.variant == 0;
                 bool failed = false;
-                if (DP && (a.variant == 1 || ismle)) {
+                {   // a band that is zero in every SHP puts NaNs into C.  MLE / phase_link: zheevr ('N') reports failure, the
+                    // reference writes -1 (evd.cpp:608-612; phase_link.cpp:540-545).  EVD / STBAS: zheevr ('V') returns an
+                    // undefined vector and the temporal coherence comes out as NaN; here NaN too, with zero phasors
+                    bool zero = false;
+                    if (DP) { for (int h = 0; h < HR; ++h) { const int t = lane + 32 * h; if (t < N && !(pwd[h] > 0.0)) zero = true; } }
+                    else { for (int t = lane; t < N; t += 32) if (!(w.pw[t] > 0.f)) zero = true; }
+                    if (__any_sync(FULL, zero)) { tc = (ismle || a.variant == 1) ? -1.f : CUDART_NAN_F; failed = true; }
+                }
+                if (DP && (a.variant == 1 || ismle) && !failed) {
                     ++st_dp;
                     // ---- gate 1 (evd.cpp MLE only): lambda_min(C) >= 1e-6 -------------
                     if (a.variant == 0) {

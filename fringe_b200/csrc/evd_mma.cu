@@ -332,6 +332,7 @@ __global__ void __launch_bounds__(512, 1) k_evd_mma(const EvdArgs a) {
         // ------------------------- coherence (evd.cpp:569-582) --------------------------
         // accumulator fragment of tile (I, J): element e is row 16 I + g + 8 (e >> 1), column 8 J + 2 t + (e & 1)
         __syncwarp();
+        bool zero_band = false;
         if (g == 2 * t || g == 2 * t + 1) {
             const bool odd = (g != 2 * t);              // selects, not a runtime index: keeps the tiles in registers
             const float p0 = odd ? cre[0][1] : cre[0][0], p1 = odd ? cre[1][3] : cre[1][2];
@@ -341,7 +342,13 @@ __global__ void __launch_bounds__(512, 1) k_evd_mma(const EvdArgs a) {
             s_pw[g + 8] = (g + 8 < N) ? sqrtf(p1) : CUDART_INF_F;
             s_pw[g + 16] = (g + 16 < N) ? sqrtf(p2) : CUDART_INF_F;
             s_pw[g + 24] = (g + 24 < N) ? sqrtf(p3) : CUDART_INF_F;
+            zero_band = (g < N && !(p0 > 0.f)) || (g + 8 < N && !(p1 > 0.f)) || (g + 16 < N && !(p2 > 0.f)) || (g + 24 < N && !(p3 > 0.f));
         }
+        // a band that is zero in every SHP puts NaNs into C.  The reference hands that matrix to zheevr, which (OpenBLAS)
+        // reports success with an undefined vector; its temporal coherence then comes out as NaN (arg of NaN entries,
+        // evd.cpp:770-786).  Here: temporal coherence NaN as well, phasors and compressed SLC 0 instead of LAPACK's
+        // undefined values.  Arises only when a whole window is zero in one date.
+        zero_band = __any_sync(FULLMASK, zero_band);
         __syncwarp();
         {
             float ir[4], ic[8];
@@ -372,7 +379,8 @@ __global__ void __launch_bounds__(512, 1) k_evd_mma(const EvdArgs a) {
         float2 o = make_float2(0.f, 0.f);
         float tc = 0.f;
         float2 cmp = make_float2(0.f, 0.f);
-        if (solve) {
+        if (solve && zero_band) tc = CUDART_NAN_F;
+        if (solve && !zero_band) {
             ++st_pix;
             const int r = (lane < NE) ? lane : (NE - 1);
             // row r of the matrix as pairs of consecutive columns: cr2[k] = (Re C[r][2k], Re C[r][2k+1])

@@ -396,8 +396,28 @@ __global__ void __launch_bounds__(MleCfg<NT>::WARPS * 32, MleCfg<NT>::MIN_CTAS) 
         if (center_on && npix >= need && !rank_deficient) {
             if (lane == 0) s_work[atomicAdd(&s_nwork, 1)] = (unsigned short)k;
         } else {
+            float code = 0.f;
+            if (center_on && npix >= need) {
+                // rank deficient: -2, unless some band is zero in every SHP -- then the coherence matrix holds NaNs,
+                // LAPACK's zheevr reports failure and the reference writes -1 before it ever looks at the eigenvalue
+                // (evd.cpp:608-612).  Happens in the sequential chain, where compressed SLCs of failed pixels are 0.
+                bool nonzero = false;
+                for (int w = lane; w < a.nulong * 32; w += 32) {
+                    const uint32_t word = __ldg(&mwords[w >> 5]);
+                    const short2 d = s_off[w];
+                    const int yy = row + d.x, xx = col + d.y;
+                    uint32_t V = __ballot_sync(FULLM, ((word >> (w & 31)) & 1u) && yy >= 0 && yy < a.lines && xx >= 0 && xx < a.cols);
+                    while (V) {
+                        const int src = __ffs(V) - 1;
+                        V &= V - 1;
+                        const int qy = __shfl_sync(FULLM, yy, src), qx = __shfl_sync(FULLM, xx, src);
+                        if (live) { const float2 z = __ldg(&a.zpix[((long)qy * a.cols + qx) * NP + lane]); nonzero = nonzero || z.x != 0.f || z.y != 0.f; }
+                    }
+                }
+                code = __all_sync(FULLM, nonzero || !live) ? -2.f : -1.f;
+            }
             if (live) a.out[(long)lane * npix_block + pg] = make_float2(0.f, 0.f);
-            if (lane == 0) { a.tcorr[pg] = (center_on && npix >= need) ? -2.f : 0.f; a.comp[pg] = make_float2(0.f, 0.f); }
+            if (lane == 0) { a.tcorr[pg] = code; a.comp[pg] = make_float2(0.f, 0.f); }
         }
     }
     __syncthreads();
@@ -416,6 +436,8 @@ __global__ void __launch_bounds__(MleCfg<NT>::WARPS * 32, MleCfg<NT>::MIN_CTAS) 
         float tc = 0.f;
         bool have_vec = false;
         double vxr = 0.0, vxi = 0.0;                          // eigenvector component of this lane
+        bool failed = false, run_evd = false, c_in_mp = true, have_inv = false, okr = false;
+        double dmax = 0.0;
 
         // SHP list of mask words w0, w0 + 1 -> s_list, returns its length
         auto build_list = [&](int w0, bool store) -> int {
@@ -434,8 +456,6 @@ __global__ void __launch_bounds__(MleCfg<NT>::WARPS * 32, MleCfg<NT>::MIN_CTAS) 
             return n;
         };
 
-        bool failed = false, run_evd = false, c_in_mp = true, have_inv = false, okr = false;
-        double dmax = 0.0;
         // F = scale * Mp + dadd I on the packed triangle
         auto assemble = [&](double scale, double dadd) {
             for (int e = lane; e < npack; e += 32) { const double2 v = Mp[e]; F[e] = make_double2(scale * v.x, scale * v.y); }
@@ -499,6 +519,9 @@ __global__ void __launch_bounds__(MleCfg<NT>::WARPS * 32, MleCfg<NT>::MIN_CTAS) 
                         }
                     }
                 }
+                // a band that is zero in every SHP: NaNs in the coherence matrix, LAPACK fails, sentinel -1
+                // (evd.cpp:608-612, phase_link.cpp:540-545)
+                if (__any_sync(FULLM, live && !(pw > 0.0))) { tc = -1.f; failed = true; }
                 // coherence (evd.cpp:569-582): C_ij = sum / sqrt(P_i P_j); stored is C(j,i) = conj(C_ij), j > i
                 __syncwarp();
                 if (live) dv[lane] = pw;
@@ -521,7 +544,7 @@ __global__ void __launch_bounds__(MleCfg<NT>::WARPS * 32, MleCfg<NT>::MIN_CTAS) 
         }
         __syncthreads();
         // ================= phase 2: gate 1, lambda_min(C) >= 1e-6 (evd.cpp:608-617) =================
-        if (go && !pl) {
+        if (go && !pl && !failed) {
             assemble(1.0, -1.0e-6);
             ++st_fact;
             if (!chol_c_smem<NT>(F, pan, rsv, N, lane)) { tc = -2.f; failed = true; }

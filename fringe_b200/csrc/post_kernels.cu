@@ -30,6 +30,13 @@ __global__ void __launch_bounds__(256) k_cmul(const float4* __restrict__ a, cons
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) out1[n - 1] = cmul_via_double(a1[n - 1], b1[n - 1]);
 }
 
+// one pixel per thread, for operands that are only 8-byte aligned (odd row offsets inside a larger raster)
+__global__ void __launch_bounds__(256) k_cmul_scalar(const float2* __restrict__ a, const float2* __restrict__ b,
+                                                     float2* __restrict__ out, long n) {
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = cmul_via_double(__ldg(a + i), __ldg(b + i));
+}
+
 cudaError_t launch_cmul(const float2* a, const float2* b, float2* out, long n, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     int dev = 0, nsm = 148;
@@ -40,6 +47,12 @@ cudaError_t launch_cmul(const float2* a, const float2* b, float2* out, long n, c
     const long cap = (long)nsm * 8 * 4;                               // grid-stride above 32 CTAs per SM
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
+    if ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15) != 0) {
+        long sb = (n + 255) / 256;
+        if (sb > cap) sb = cap;
+        k_cmul_scalar<<<(unsigned)sb, 256, 0, st>>>(a, b, out, n);
+        return cudaGetLastError();
+    }
     k_cmul<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b),
                                              reinterpret_cast<float4*>(out), npairs, a, b, out, n);
     return cudaGetLastError();

@@ -192,6 +192,27 @@ class Context:
             wts.ctypes.data if want_mask else None, out.ctypes.data, tcorr.ctypes.data, comp.ctypes.data))
         return count, wts, out, tcorr, comp
 
+    def sequential_block(self, slc, wts, Nx, Ny, mini_stack_size, method="MLE", bandwidth=-1, first_line=0, n_lines=None,
+                         want_adjusted=True):
+        """The whole ministack chain on one upload (``fringe_sequential_block``).
+        slc (n_dates, lines, cols) complex64 -> dict(out_mini, tcorr_mini, comp, out_datum, tcorr_datum, adjusted)."""
+        slc = np.ascontiguousarray(slc, np.complex64)
+        wts = np.ascontiguousarray(wts, np.uint32)
+        n_dates, lines, cols = slc.shape
+        if n_lines is None:
+            n_lines = lines - first_line
+        nmini = -(-n_dates // mini_stack_size)
+        res = {"out_mini": np.zeros((n_dates, lines, cols), np.complex64), "tcorr_mini": np.zeros((nmini, lines, cols), np.float32),
+               "comp": np.zeros((nmini, lines, cols), np.complex64), "out_datum": np.zeros((nmini, lines, cols), np.complex64),
+               "tcorr_datum": np.zeros((lines, cols), np.float32),
+               "adjusted": np.zeros((n_dates, lines, cols), np.complex64) if want_adjusted else None}
+        self._check(lib.fringe_sequential_block(
+            self._h, slc.ctypes.data, wts.ctypes.data, cols, lines, n_dates, Nx, Ny, first_line, n_lines, int(mini_stack_size),
+            _method(METHODS_EVD, method), int(bandwidth), res["out_mini"].ctypes.data, res["tcorr_mini"].ctypes.data,
+            res["comp"].ctypes.data, res["out_datum"].ctypes.data, res["tcorr_datum"].ctypes.data,
+            res["adjusted"].ctypes.data if want_adjusted else None))
+        return res
+
     def ampdispersion_block(self, slc, alpha=None):
         """slc (bands, lines, cols) complex64 -> amplitude dispersion, mean amplitude (float32 each)."""
         slc = np.ascontiguousarray(slc, np.complex64)

@@ -140,6 +140,32 @@ int fringe_nmap_evd_block(fringe_ctx* ctx, const float* slc, const uint8_t* mask
                           int mini_stack_count, int variant, int min_neighbors, int32_t* count,
                           uint32_t* wts, float* out, float* tcorr, float* comp);
 
+/* ---- sequential (ministack) estimator, device resident -------------------------------------
+ * What src/sequential/sequential.py:190-254 does through files -- ministack k links the compressed SLCs of
+ * ministacks 1..k-1 followed by its own `mini_stack_size` acquisitions with miniStackCount = k, then a
+ * "datum connection" run links all compressed SLCs -- followed by the wrapped-phase adjustment of
+ * python/adjustMiniStacks.py:180-199, on one block of lines with the stack uploaded exactly once: the
+ * compressed SLCs never leave the device between the stages.
+ *   slc         complex64 [n_dates][lines*cols]   all acquisitions, in time order
+ *   wts         uint32    [lines*cols][nulong]    SHP mask of the full stack (nmap)
+ *   out_mini    complex64 [n_dates][lines*cols]   phasor of every date from its own ministack (<ministack>/EVD/<date>.slc)
+ *   tcorr_mini  float32   [n_mini][lines*cols]    temporal coherence of every ministack
+ *   comp        complex64 [n_mini][lines*cols]    compressed SLCs (compressedSlc/<last date>/<last date>.slc)
+ *   out_datum   complex64 [n_mini][lines*cols]    datum-connection phasors (Datum_connection/EVD/<last date>.slc)
+ *   tcorr_datum float32   [lines*cols]
+ *   adjusted    complex64 [n_dates][lines*cols]   out_mini(date) * out_datum(its ministack); may be NULL
+ * n_mini = ceil(n_dates / mini_stack_size).  Results are delivered for lines [first_line, first_line + n_lines).
+ * A compressed SLC is needed Ny lines beyond the rows of every later stage, so ministack k is solved on the
+ * delivered rows +- (n_mini - k + 1) * Ny (clipped to the block): results are identical to the file-based chain
+ * when the block carries fringe_sequential_halo() extra lines on each side that is not an image edge; the redundant
+ * rows are recomputed instead of exchanged, which is what lets row tiles run on different GPUs without any
+ * communication.  `method` as in fringe_evd_block (the reference's chain runs the evd binding's default, MLE). */
+int fringe_sequential_halo(int n_dates, int mini_stack_size, int Ny);
+int fringe_sequential_block(fringe_ctx* ctx, const float* slc, const uint32_t* wts, int cols, int lines, int n_dates,
+                            int Nx, int Ny, int first_line, int n_lines, int mini_stack_size, int method, int bandwidth,
+                            float* out_mini, float* tcorr_mini, float* comp, float* out_datum, float* tcorr_datum,
+                            float* adjusted);
+
 /* ---- datum adjustment of the sequential estimator ----------------------------------------
  * out[i] = a[i] * b[i] on n complex64 pixels: the wrapped time series
  * adjusted(date) = ministack phasor(date) * datum phasor(ministack), which

@@ -224,3 +224,30 @@ def test_workflow_window_23x11(ctx, oracle_lib):
     wts = _nmap(oracle_lib, slc, 11, 5)
     for method, code in (("EVD", 0), ("MLE", 1)):
         _compare(oracle_lib.evd_block(slc, wts, 11, 5, method=code), ctx.evd_block(slc, wts, 11, 5, method=method), borderline=3)
+
+
+@pytest.mark.parametrize("bands,method,variant", [(12, "EVD", 0), (12, "MLE", 0), (12, "MLE", 1), (40, "EVD", 0), (40, "MLE", 0),
+                                                   (10, "STBAS", 0)])
+def test_band_that_is_zero_over_a_whole_window(ctx, oracle_lib, bands, method, variant):
+    """The sequential chain feeds compressed SLCs that are 0 where an earlier ministack failed.  Where such a band
+    is zero in every SHP of a pixel the coherence matrix holds NaNs: the reference writes -1 (MLE / phase_link, LAPACK
+    reports failure) or a NaN temporal coherence (EVD / STBAS): same here, pixel by pixel."""
+    slc = synth.make_stack(bands, 30, 64, seed=77 + bands, region=16, zero_fraction=0.0)
+    wts = _nmap(oracle_lib, slc, 5, 2)
+    slc = slc.copy()
+    slc[2, 8:22, 10:40] = 0                     # mask unchanged: these pixels stay SHPs of each other
+    code = {"EVD": 0, "MLE": 1, "STBAS": 2}[method]
+    ref = oracle_lib.evd_block(slc, wts, 5, 2, method=code, variant=variant, min_neighbors=3, bandwidth=4)
+    gpu = ctx.evd_block(slc, wts, 5, 2, method=method, variant=variant, min_neighbors=3, bandwidth=4)
+    if method in ("EVD", "STBAS") and variant == 0:
+        # zheevr('V') returns an undefined vector for a NaN matrix and the reference's temporal coherence is NaN: the
+        # NaN pattern must agree; the (undefined) phasors of those pixels are not compared
+        nan_ref, nan_gpu = np.isnan(ref[1]), np.isnan(gpu[1])
+        assert nan_ref.sum() > 50 and np.array_equal(nan_ref, nan_gpu)
+        assert np.all(gpu[0][:, nan_gpu] == 0)
+        ref = (np.where(nan_ref, 0, ref[0]), np.where(nan_ref, 0, ref[1]), np.where(nan_ref, 0, ref[2]))
+        gpu = (gpu[0], np.where(nan_gpu, 0, gpu[1]), gpu[2])
+    else:
+        assert (ref[1] == -1.0).sum() > 50, np.unique(ref[1][ref[1] < 0], return_counts=True)
+        assert np.array_equal(ref[1] == -1.0, gpu[1] == -1.0)
+    _compare(ref, gpu, borderline=3, weak_components=3 if method == "STBAS" else 0)
