@@ -52,6 +52,14 @@ def write_envi(path: str, arr: np.ndarray, metadata: dict | None = None) -> None
             f.write(f"{k} = {v}\n")
 
 
+def write_envi_header(path: str, lines: int, cols: int, bands: int, dtype, metadata: dict | None = None) -> None:
+    with open(path + ".hdr", "w") as f:
+        f.write(f"ENVI\nsamples = {cols}\nlines   = {lines}\nbands   = {bands}\nheader offset = 0\n"
+                f"file type = ENVI Standard\ndata type = {ENVI_TYPES[np.dtype(dtype)]}\ninterleave = bip\nbyte order = 0\n")
+        for k, v in (metadata or {}).items():
+            f.write(f"{k} = {v}\n")
+
+
 def read_envi_header(path: str) -> dict:
     hdr = path + ".hdr" if os.path.exists(path + ".hdr") else os.path.splitext(path)[0] + ".hdr"
     out = {}

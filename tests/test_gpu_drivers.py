@@ -64,8 +64,13 @@ def test_phase_link_cli_and_error_codes(stack, oracle_lib):
     w_ref = stackio.read_envi(wts_path)
     o_ref, t_ref, _ = oracle_lib.evd_block(slc, w_ref, 5, 2, method=1, variant=1, min_neighbors=5)
     tcorr = stackio.read_envi(os.path.join(out_dir, "tcorr.bin"))
-    assert np.array_equal(tcorr < 0, t_ref < 0)
+    assert np.array_equal(np.where(tcorr < 0, tcorr, 0), np.where(t_ref < 0, t_ref, 0))        # sentinel codes, pixel by pixel
     assert np.abs(tcorr - t_ref)[t_ref > 0].max() <= 1e-4
+    dates = stackio.default_dates(12)
+    out = np.stack([stackio.read_envi(os.path.join(out_dir, d + ".slc")) for d in dates])
+    good = t_ref > 0.3
+    assert wrapped_diff(out[:, good], o_ref[:, good]).max() <= 1e-3
+    assert np.all(out[:, ~(t_ref > 0)] == 0)
     # window mismatch between wts metadata and request -> rc 109 (evd.cpp:131-141)
     with pytest.raises(RuntimeError, match="109"):
         evd_cli.main(["-i", vrt, "-w", wts_path, "-o", os.path.join(root, "X1"), "-x", "4", "-y", "2"])
@@ -76,37 +81,55 @@ def test_phase_link_cli_and_error_codes(stack, oracle_lib):
 
 
 def test_sequential_chain(stack, oracle_lib):
-    """BASELINE.json configs[3] in miniature: 12 dates in ministacks of 5 (5+5+2) with compressed-SLC
-    hand-off, then the datum connection; every stage compared with the oracle fed the same inputs."""
+    """BASELINE.json configs[3] in miniature through the command line: 12 dates in ministacks of 5 (5+5+2), several
+    blocks of lines with halos, compressed-SLC hand-off on the device, datum connection, adjusted product.  Every
+    stage's phasors, temporal coherence and compressed SLC are compared with the oracle run on the same inputs."""
     root, slc, vrt = stack
     wts_path = os.path.join(root, "KS2", "nmap")
     out = os.path.join(root, "seq")
-    seq_cli.main(["-i", os.path.join(root, "SLC"), "-w", wts_path, "-o", out, "-x", "5", "-y", "2", "-s", "5", "-r", "2"])
+    # -r 1: a memory budget that forces several blocks of 64 lines for the 150-line image
+    seq_cli.main(["-i", os.path.join(root, "SLC"), "-w", wts_path, "-o", out, "-x", "5", "-y", "2", "-s", "5", "-r", "1"])
     w_ref = stackio.read_envi(wts_path)
     dates = stackio.default_dates(12)
-    comps = []
-    for k, (a, b) in enumerate([(0, 5), (5, 10), (10, 12)], start=1):
-        bands = np.concatenate([np.array(comps).reshape(-1, 150, 96), slc[a:b]]) if comps else slc[a:b]
+    groups = [(0, 5), (5, 10), (10, 12)]
+    comps, minis = [], []
+    for k, (a, b) in enumerate(groups, start=1):
+        bands = np.concatenate([np.array(comps), slc[a:b]]) if comps else slc[a:b]
         o_ref, t_ref, c_ref = oracle_lib.evd_block(bands.astype(np.complex64), w_ref, 5, 2, method=1, mini_stack_count=k)
         d = os.path.join(out, "miniStacks", dates[a] + "_" + dates[b - 1], "EVD")
+        assert os.path.exists(os.path.join(out, "miniStacks", dates[a] + "_" + dates[b - 1], "stack", "stack.vrt"))
         tcorr = stackio.read_envi(os.path.join(d, "tcorr.bin"))
-        assert np.mean((tcorr < 0) == (t_ref < 0)) > 0.999
+        mini = np.stack([stackio.read_envi(os.path.join(d, dates[i] + ".slc")) for i in range(a, b)])
+        code_ref, code_gpu = np.where(t_ref < 0, t_ref, 0), np.where(tcorr < 0, tcorr, 0)
+        flips = np.argwhere(code_ref != code_gpu)
+        assert len(flips) <= 3, [(int(y), int(x), float(t_ref[y, x]), float(tcorr[y, x])) for y, x in flips]
         both = (t_ref > 0) & (tcorr > 0)
         assert np.abs(tcorr - t_ref)[both].max() <= 1e-4
-        comp = stackio.read_envi(os.path.join(out, "compressedSlc", dates[b - 1], dates[b - 1] + ".slc"))
         good = both & (t_ref > 0.3)
+        assert wrapped_diff(mini[:, good], o_ref[k - 1:][:, good]).max() <= 1e-3          # the phasors themselves
+        comp = stackio.read_envi(os.path.join(out, "compressedSlc", dates[b - 1], dates[b - 1] + ".slc"))
         assert np.abs(comp - c_ref)[good].max() <= 2e-3 * np.abs(c_ref[good]).max()
-        comps.append(comp)                       # feed OUR compressed SLC forward, like the chain does
+        comps.append(comp)                       # feed OUR compressed SLC forward: every stage sees what the device saw
+        minis.append(mini)
     dc = os.path.join(out, "Datum_connection", "EVD")
     o_ref, t_ref, _ = oracle_lib.evd_block(np.array(comps).astype(np.complex64), w_ref, 5, 2, method=1, mini_stack_count=1)
     tcorr = stackio.read_envi(os.path.join(dc, "tcorr.bin"))
+    datum = np.stack([stackio.read_envi(os.path.join(dc, dates[b - 1] + ".slc")) for _, b in groups])
     both = (t_ref > 0) & (tcorr > 0)
-    assert np.mean((tcorr < 0) == (t_ref < 0)) > 0.999 and np.abs(tcorr - t_ref)[both].max() <= 1e-4
-    # skip-if-exists resume semantics (sequential.py:206-207): a second run only redoes the datum step
-    import shutil
-    shutil.rmtree(os.path.join(out, "Datum_connection"))
-    seq_cli.main(["-i", os.path.join(root, "SLC"), "-w", wts_path, "-o", out, "-x", "5", "-y", "2", "-s", "5", "-r", "2"])
-    assert os.path.exists(os.path.join(dc, "tcorr.bin"))
+    assert (np.where(t_ref < 0, t_ref, 0) != np.where(tcorr < 0, tcorr, 0)).sum() <= 3
+    assert np.abs(tcorr - t_ref)[both].max() <= 1e-4
+    good = both & (t_ref > 0.3)
+    assert wrapped_diff(datum[:, good], o_ref[:, good]).max() <= 1e-3
+    # the adjusted series is the product of the two rasters on disk, evaluated as adjustMiniStacks.py's VRTs would
+    for k, (a, b) in enumerate(groups):
+        for i in range(a, b):
+            adj = stackio.read_envi(os.path.join(out, "adjusted", dates[i] + ".slc"))
+            want = oracle_lib.cmul(minis[k][i - a], datum[k])
+            assert np.array_equal(adj.view(np.uint32), want.view(np.uint32))
+    # a finished run is left alone (sequential.py:206-207 skips what exists); -f redoes it
+    before = os.path.getmtime(os.path.join(dc, "tcorr.bin"))
+    seq_cli.main(["-i", os.path.join(root, "SLC"), "-w", wts_path, "-o", out, "-x", "5", "-y", "2", "-s", "5", "-r", "1"])
+    assert os.path.getmtime(os.path.join(dc, "tcorr.bin")) == before
 
 
 def test_despeck_cli_multi_block(stack, oracle_lib):
