@@ -827,7 +827,7 @@ int fringe_sequential_block(fringe_ctx* ctx, const float* slc, const uint32_t* w
     CU(ctx->o_out.ensure(npix * max_bands * sizeof(float2)));
     CU(ctx->o_tcorr.ensure(npix * sizeof(float)));
     CU(ctx->o_comp.ensure(npix * nmini * sizeof(float)));        // temporal coherence of every ministack
-    CU(cudaMemcpyAsync(ctx->in_wts.p, wts, npix * nu * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->s_in));
+    CU(cudaMemcpyAsync(ctx->in_wts.p, wts, npix * nu * sizeof(uint32_t), cudaMemcpyDefault, ctx->s_in));
     CU(cudaMemsetAsync(ctx->seq_comp.p, 0, npix * nmini * sizeof(float2), st));
     size_t ev = 0;
     cudaEvent_t buf_free[2] = {nullptr, nullptr};                // solve that last read a stack buffer has finished
@@ -847,7 +847,7 @@ int fringe_sequential_block(fringe_ctx* ctx, const float* slc, const uint32_t* w
         {
             const size_t off = (size_t)t0 * cols, cnt = (size_t)(t1 - t0) * cols;
             CU(cudaMemcpy2DAsync(buf + (size_t)(k - 1) * npix + off, npix * sizeof(float2), (const float2*)slc + (size_t)d0 * npix + off,
-                                 npix * sizeof(float2), cnt * sizeof(float2), d1 - d0, cudaMemcpyHostToDevice, ctx->s_in));
+                                 npix * sizeof(float2), cnt * sizeof(float2), d1 - d0, cudaMemcpyDefault, ctx->s_in));
         }
         cudaEvent_t e_in = ctx->pool_event(ev++);
         CU(cudaEventRecord(e_in, ctx->s_in));
@@ -869,11 +869,11 @@ int fringe_sequential_block(fringe_ctx* ctx, const float* slc, const uint32_t* w
         buf_free[k & 1] = e_done;
         CU(cudaStreamWaitEvent(ctx->s_out, e_done, 0));
         CU(cudaMemcpy2DAsync((float2*)out_mini + (size_t)d0 * npix + ooff, npix * sizeof(float2), (float2*)ctx->seq_mini.p + (size_t)d0 * nout,
-                             nout * sizeof(float2), nout * sizeof(float2), d1 - d0, cudaMemcpyDeviceToHost, ctx->s_out));
+                             nout * sizeof(float2), nout * sizeof(float2), d1 - d0, cudaMemcpyDefault, ctx->s_out));
         CU(cudaMemcpyAsync(tcorr_mini + (size_t)(k - 1) * npix + ooff, (float*)ctx->o_comp.p + (size_t)(k - 1) * npix + ooff,
-                           nout * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_out));
+                           nout * sizeof(float), cudaMemcpyDefault, ctx->s_out));
         CU(cudaMemcpyAsync((float2*)comp + (size_t)(k - 1) * npix + ooff, (float2*)ctx->seq_comp.p + (size_t)(k - 1) * npix + ooff,
-                           nout * sizeof(float2), cudaMemcpyDeviceToHost, ctx->s_out));
+                           nout * sizeof(float2), cudaMemcpyDefault, ctx->s_out));
     }
     // datum connection: all compressed SLCs, first band is the reference (sequential.py:247-254)
     {
@@ -886,8 +886,8 @@ int fringe_sequential_block(fringe_ctx* ctx, const float* slc, const uint32_t* w
                              (float*)ctx->o_tcorr.p, (float*)d_out, st);      // the datum run's own compressed SLC is not used
         if (rc) return rc;
         CU(cudaMemcpy2DAsync((float2*)out_datum + ooff, npix * sizeof(float2), (float2*)ctx->seq_datum.p + ooff, npix * sizeof(float2),
-                             nout * sizeof(float2), nmini, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(tcorr_datum + ooff, (float*)ctx->o_tcorr.p + ooff, nout * sizeof(float), cudaMemcpyDeviceToHost, st));
+                             nout * sizeof(float2), nmini, cudaMemcpyDefault, st));
+        CU(cudaMemcpyAsync(tcorr_datum + ooff, (float*)ctx->o_tcorr.p + ooff, nout * sizeof(float), cudaMemcpyDefault, st));
     }
     // wrapped time series: ministack phasor x datum phasor of its ministack (adjustMiniStacks.py:180-199)
     if (adjusted) {
@@ -901,7 +901,7 @@ int fringe_sequential_block(fringe_ctx* ctx, const float* slc, const uint32_t* w
             }
         }
         CU(cudaMemcpy2DAsync((float2*)adjusted + ooff, npix * sizeof(float2), ctx->seq_mini.p, nout * sizeof(float2), nout * sizeof(float2),
-                             n_dates, cudaMemcpyDeviceToHost, st));
+                             n_dates, cudaMemcpyDefault, st));
     }
     CU(cudaStreamSynchronize(ctx->s_out));
     CU(cudaStreamSynchronize(st));

@@ -159,7 +159,9 @@ int fringe_nmap_evd_block(fringe_ctx* ctx, const float* slc, const uint8_t* mask
  * delivered rows +- (n_mini - k + 1) * Ny (clipped to the block): results are identical to the file-based chain
  * when the block carries fringe_sequential_halo() extra lines on each side that is not an image edge; the redundant
  * rows are recomputed instead of exchanged, which is what lets row tiles run on different GPUs without any
- * communication.  `method` as in fringe_evd_block (the reference's chain runs the evd binding's default, MLE). */
+ * communication.  `method` as in fringe_evd_block (the reference's chain runs the evd binding's default, MLE).
+ * Pointers may be host memory (pinned preferred) or device memory of the context's GPU (unified addressing tells
+ * them apart): with device pointers nothing crosses the host link.  Returns when the results are in place. */
 int fringe_sequential_halo(int n_dates, int mini_stack_size, int Ny);
 int fringe_sequential_block(fringe_ctx* ctx, const float* slc, const uint32_t* wts, int cols, int lines, int n_dates,
                             int Nx, int Ny, int first_line, int n_lines, int mini_stack_size, int method, int bandwidth,
