@@ -72,6 +72,9 @@ def _load() -> C.CDLL:
     lib.fringe_despeck_block_device.argtypes = [vp, vp, vp, vp] + [i] * 7 + [vp, vp]
     lib.fringe_sequential_halo.argtypes = [i, i, i]
     lib.fringe_sequential_block.argtypes = [vp, vp, vp] + [i] * 10 + [vp] * 6
+    lib.fringe_calamp_block.argtypes = [vp, vp, vp, i, i, i, vp, vp]
+    lib.fringe_integrate_ps.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64, vp]
+    lib.fringe_ps_coherence.argtypes = [vp, vp, vp, C.c_int64, C.c_float, vp]
     lib.fringe_cmul.argtypes = [vp, vp, vp, C.c_int64, vp]
     lib.fringe_cmul_device.argtypes = [vp, vp, vp, C.c_int64, vp, vp]
     # context-bound profiling hooks (include/fringe_b200_prof.h, group a)

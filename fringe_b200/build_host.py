@@ -28,7 +28,8 @@ def build(force: bool = False) -> None:
     for mod, src, defs in (("nmaplib", "nmaplib.cpp", []), ("evdlib", "evdlib.cpp", []),
                            ("phase_linklib", "evdlib.cpp", ["-DFRINGE_PHASE_LINK"]),
                            ("despecklib", "despecklib.cpp", []),
-                           ("ampdispersionlib", "ampdispersionlib.cpp", [])):
+                           ("ampdispersionlib", "ampdispersionlib.cpp", []),
+                           ("calamplib", "calamplib.cpp", [])):
         out = os.path.join(BINDINGS, mod + ext)
         if force or _newer(out, [os.path.join(HOST, src), HOST_LIB, __file__] + hdrs):
             _run([HOST_CXX] + common + ["-fvisibility=hidden", "-shared"] + defs + inc +

@@ -1066,6 +1066,71 @@ int fringe_ampdispersion_block(fringe_ctx* ctx, const float* slc, const double* 
     return FRINGE_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// calamp (src/calamp/calamp.cpp:207-226) and PS / DS integration (python/integratePS.py:97-159)
+// ---------------------------------------------------------------------------------------
+int fringe_calamp_block(fringe_ctx* ctx, const float* slc, const uint8_t* mask, int cols, int lines, int bands, double* sums,
+                        double* counts) {
+    if (!ctx) return FRINGE_ERR_ARGUMENT;
+    if (!slc || !sums || !counts) return fail(ctx, FRINGE_ERR_ARGUMENT, "null pointer");
+    if (cols <= 0 || lines <= 0 || bands <= 0) return fail(ctx, FRINGE_ERR_ARGUMENT, "non-positive size");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t npix = (size_t)cols * lines;
+    CU(ctx->in_slc.ensure(npix * bands * sizeof(float2)));
+    CU(ctx->scratch.ensure((size_t)bands * 2 * sizeof(double)));
+    const uint8_t* dmask = nullptr;
+    if (mask) { CU(ctx->in_mask.ensure(npix)); CU(cudaMemcpyAsync(ctx->in_mask.p, mask, npix, cudaMemcpyDefault, st)); dmask = (const uint8_t*)ctx->in_mask.p; }
+    CU(cudaMemcpyAsync(ctx->in_slc.p, slc, npix * bands * sizeof(float2), cudaMemcpyDefault, st));
+    CU(cudaMemsetAsync(ctx->scratch.p, 0, (size_t)bands * 2 * sizeof(double), st));
+    CU(fringe::launch_calamp((const float2*)ctx->in_slc.p, dmask, (long)npix, bands, (double*)ctx->scratch.p, st));
+    ctx->launches += 1;
+    std::vector<double> h((size_t)bands * 2);
+    CU(cudaMemcpyAsync(h.data(), ctx->scratch.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int b = 0; b < bands; ++b) { sums[b] += h[2 * b]; counts[b] += h[2 * b + 1]; }
+    return FRINGE_OK;
+}
+
+int fringe_integrate_ps(fringe_ctx* ctx, const float* ds_i, const float* ds_j, const float* slc_i, const float* slc_j,
+                        const uint8_t* ps, int64_t n, float* out) {
+    if (!ctx) return FRINGE_ERR_ARGUMENT;
+    if (n < 0 || (n > 0 && (!ds_i || !ds_j || !slc_i || !slc_j || !ps || !out))) return fail(ctx, FRINGE_ERR_ARGUMENT, "null pointer or negative size");
+    if (n == 0) return FRINGE_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CU(ctx->in_slc.ensure((size_t)n * 4 * sizeof(float2)));
+    CU(ctx->in_mask.ensure((size_t)n));
+    CU(ctx->o_out.ensure((size_t)n * sizeof(float2)));
+    float2* d = (float2*)ctx->in_slc.p;
+    const float* src[4] = {ds_i, ds_j, slc_i, slc_j};
+    for (int k = 0; k < 4; ++k) CU(cudaMemcpyAsync(d + (size_t)k * n, src[k], (size_t)n * sizeof(float2), cudaMemcpyDefault, st));
+    CU(cudaMemcpyAsync(ctx->in_mask.p, ps, (size_t)n, cudaMemcpyDefault, st));
+    CU(fringe::launch_integrate_ps(d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n, (const uint8_t*)ctx->in_mask.p, (long)n, (float2*)ctx->o_out.p, st));
+    ctx->launches += 1;
+    CU(cudaMemcpyAsync(out, ctx->o_out.p, (size_t)n * sizeof(float2), cudaMemcpyDefault, st));
+    CU(cudaStreamSynchronize(st));
+    return FRINGE_OK;
+}
+
+int fringe_ps_coherence(fringe_ctx* ctx, const float* tcorr, const uint8_t* ps, int64_t n, float ps_value, float* out) {
+    if (!ctx) return FRINGE_ERR_ARGUMENT;
+    if (n < 0 || (n > 0 && (!tcorr || !ps || !out))) return fail(ctx, FRINGE_ERR_ARGUMENT, "null pointer or negative size");
+    if (n == 0) return FRINGE_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CU(ctx->o_tcorr.ensure((size_t)n * 2 * sizeof(float)));
+    CU(ctx->in_mask.ensure((size_t)n));
+    float* d = (float*)ctx->o_tcorr.p;
+    CU(cudaMemcpyAsync(d, tcorr, (size_t)n * sizeof(float), cudaMemcpyDefault, st));
+    CU(cudaMemcpyAsync(ctx->in_mask.p, ps, (size_t)n, cudaMemcpyDefault, st));
+    CU(fringe::launch_ps_coherence(d, (const uint8_t*)ctx->in_mask.p, (long)n, ps_value, d + n, st));
+    ctx->launches += 1;
+    CU(cudaMemcpyAsync(out, d + n, (size_t)n * sizeof(float), cudaMemcpyDefault, st));
+    CU(cudaStreamSynchronize(st));
+    return FRINGE_OK;
+}
+
 int fringe_last_kernel_ms(fringe_ctx* ctx, int kernel, float* ms) {
     if (!ctx || !ms || kernel < 0 || kernel >= FRINGE_KERNEL_COUNT) return FRINGE_ERR_ARGUMENT;
     if (!ctx->ev_valid[kernel]) return fail(ctx, FRINGE_ERR_ARGUMENT, "kernel has not been launched on this context");

@@ -85,6 +85,12 @@ cudaError_t launch_cmul(const float2* a, const float2* b, float2* out, long n, c
 // ampdispersion: slc [bands][npix], alpha [bands] device doubles or nullptr; da, meanamp [npix]
 cudaError_t launch_ampdispersion(const float2* slc, const double* alpha, long npix, int bands, float* da, float* meanamp,
                                  cudaStream_t st);
+// calamp: acc [bands][2] doubles (sum of amplitudes, number of valid pixels), accumulated; mask may be nullptr
+cudaError_t launch_calamp(const float2* slc, const uint8_t* mask, long npix, int bands, double* acc, cudaStream_t st);
+// PS / DS integration of one pair and the PS-aware coherence raster (python/integratePS.py)
+cudaError_t launch_integrate_ps(const float2* ds_i, const float2* ds_j, const float2* slc_i, const float2* slc_j, const uint8_t* ps,
+                                long n, float2* out, cudaStream_t st);
+cudaError_t launch_ps_coherence(const float* tcorr, const uint8_t* ps, long n, float value, float* out, cudaStream_t st);
 // despeck: mode 0 one band, 1 interferogram, 2 interferogram coherence, 3 one band with the coherence flag;
 // d1, d2: npix float2 of scratch each (d2 only read in mode 2); out written for lines [first_line, +n_lines)
 cudaError_t launch_despeck(const float2* z1, const float2* z2, const uint32_t* wts, int cols, int lines, int Nx,

@@ -549,3 +549,138 @@ int ampdispersion_process(ampdispersionOptions* opts) {
     wmean.close_file();
     return 0;
 }
+
+// =====================================================================================================
+// calamp_process: src/calamp/calamp.cpp:14-275 -- amplitude calibration constant of every band (mean amplitude of
+// its valid pixels), written as <MDI key="amplitudeConstant"> into the slc metadata domain of a copy of the stack VRT
+// (the producer side of nmap.cpp:204-233 / ampdispersion.cpp:100-127).  Same checks and error codes (102 open, 104-106
+// mask size, 107 / 108 read errors); blocks do not overlap.
+namespace {
+// copy of the VRT text with amplitudeConstant set per band and relative source paths made absolute (the copy may live
+// in another folder; GDAL's CreateCopy does the same)
+std::string vrt_with_constants(const std::string& txt, const std::string& src_dir, const std::vector<std::string>& values) {
+    std::string out;
+    size_t pos = 0;
+    int band = 0;
+    while (true) {
+        const size_t a = txt.find("<VRTRasterBand", pos);
+        if (a == std::string::npos) { out += txt.substr(pos); break; }
+        const size_t z = txt.find("</VRTRasterBand>", a);
+        if (z == std::string::npos) { out += txt.substr(pos); break; }
+        out += txt.substr(pos, a - pos);
+        std::string body = txt.substr(a, z - a);
+        // relative source paths -> absolute
+        size_t q = 0;
+        while ((q = body.find("relativeToVRT=\"1\"", q)) != std::string::npos) {
+            const size_t gt = body.find('>', q), lt = body.find('<', gt);
+            if (gt == std::string::npos || lt == std::string::npos) break;
+            const std::string fn = fringe_host::trim(body.substr(gt + 1, lt - gt - 1));
+            body.replace(gt + 1, lt - gt - 1, fringe_host::join_path(src_dir, fn));
+            body.replace(q, 17, "relativeToVRT=\"0\"");
+            q += 17;
+        }
+        const std::string mdi = "<MDI key=\"amplitudeConstant\">" + values[band] + "</MDI>";
+        size_t m = body.find("<Metadata domain=\"slc\">");
+        if (m != std::string::npos) {
+            const size_t me = body.find("</Metadata>", m);
+            // drop an existing constant
+            const size_t old = body.find("<MDI key=\"amplitudeConstant\">", m);
+            if (old != std::string::npos && old < me) {
+                const size_t oe = body.find("</MDI>", old);
+                body.erase(old, oe + 6 - old);
+            }
+            const size_t me2 = body.find("</Metadata>", m);
+            body.insert(me2, "    " + mdi + "\n        ");
+        } else {
+            body += "    <Metadata domain=\"slc\">\n            " + mdi + "\n        </Metadata>\n    ";
+        }
+        out += body + "</VRTRasterBand>";
+        pos = z + 16;
+        ++band;
+        if (band >= (int)values.size()) { out += txt.substr(pos); break; }
+    }
+    return out;
+}
+}  // namespace
+
+int calamp_process(calampOptions* opts) {
+    opts->print();
+    Raster in;
+    if (!in.open(opts->inputDS)) {
+        std::cout << "Cannot open stack file { " << opts->inputDS << " } for reading: " << in.error << "\nExiting with error code .... (102) \n";
+        return 102;
+    }
+    if (!in.is_cfloat32_stack()) {
+        std::cout << "Input stack { " << opts->inputDS << " } is not a VRT with one flat CFloat32 file per band\nExiting with error code .... (102) \n";
+        return 102;
+    }
+    const int cols = in.cols, rows = in.rows, nbands = in.count();
+    std::cout << "Number of rows  = " << rows << "\nNumber of cols  = " << cols << "\nNumber of bands = " << nbands << "\n";
+    Raster msk;
+    bool have_mask = false;
+    if (!opts->maskDS.empty()) {
+        if (!msk.open(opts->maskDS)) { std::cout << "Cannot open mask file { " << opts->maskDS << " } for reading. \nExiting with error code .... (102) \n"; return 102; }
+        int code = 0;
+        if (msk.cols != cols) { std::cout << "Mask file width does not match stack size width \n"; code = 104; }
+        if (msk.rows != rows) { std::cout << "Mask file length does not match stack size length \n"; code = 105; }
+        if (msk.count() != 1) { std::cout << "Mask file has more than one band \n"; code = 106; }
+        if (code) { std::cout << "Exiting with error code .... (" << code << ")\n"; return code; }
+        have_mask = true;
+    }
+    const int ngpu = visible_gpus();
+    if (ngpu <= 0) { std::cout << "No CUDA device available and there is no CPU path.\n"; return 200 + FRINGE_ERR_NO_DEVICE; }
+    // the reference keeps one band of a block in memory (calamp.cpp:107), this driver all of them (pinned)
+    int blockysize = opts->blocksize * (int((opts->memsize * 1.0e6) / cols) / (opts->blocksize * 8 * std::max(1, nbands)));
+    if (blockysize < opts->blocksize) blockysize = opts->blocksize;
+    if (blockysize > rows) blockysize = rows;
+    std::cout << "Block size = " << blockysize << " lines \n";
+    std::cout << "Total number of blocks to process: " << (rows + blockysize - 1) / blockysize << "\n";
+
+    std::vector<double> totalsum(nbands, 0.0), norms(nbands, 0.0);
+    fringe_ctx* ctx = nullptr;
+    if (fringe_create(0, &ctx) != FRINGE_OK) return 200 + FRINGE_ERR_NO_DEVICE;
+    const size_t bp = (size_t)cols * blockysize;
+    Pinned slc, mask;
+    std::vector<char> mask_scratch;
+    if (!slc.alloc(bp * nbands * 8) || !mask.alloc(bp)) { fringe_destroy(ctx); return 200 + FRINGE_ERR_MEMORY; }
+    int rc = 0;
+    for (int yoff = 0; yoff < rows && rc == 0; yoff += blockysize) {
+        const int inysize = std::min(blockysize, rows - yoff);
+        const size_t np = (size_t)cols * inysize;
+        if (have_mask && !msk.read_mask_lines(yoff, inysize, (uint8_t*)mask.p, mask_scratch)) {
+            std::cout << "Error reading mask at line " << yoff << "\nExiting with error code .... (107) \n"; rc = 107; break;
+        }
+        for (int band = 0; band < nbands; ++band)
+            if (!in.read_band_lines(band, yoff, inysize, (char*)slc.p + (size_t)band * np * 8, 8)) {
+                std::cout << "Error reading data from band " << band + 1 << " at line " << yoff << "\nExiting with error code .... (108) \n"; rc = 108; break;
+            }
+        if (rc) break;
+        const int st = fringe_calamp_block(ctx, (const float*)slc.p, have_mask ? (const uint8_t*)mask.p : nullptr, cols, inysize, nbands,
+                                           totalsum.data(), norms.data());
+        if (st != FRINGE_OK) { std::cout << "Device error: " << fringe_last_error(ctx) << "\n"; rc = 200 + st; }
+    }
+    fringe_destroy(ctx);
+    if (rc) return rc;
+
+    std::cout << "Normalization coefficients \n";
+    std::vector<std::string> values(nbands);
+    for (int b = 0; b < nbands; ++b) {
+        if (norms[b] == 0) { std::cout << "No valid data found in Band " << b + 1 << ". Set to 1.0 \n"; totalsum[b] = 1.0; }
+        else {
+            totalsum[b] /= norms[b];
+            std::cout << "Band " << b + 1 << ":" << totalsum[b] << "  from  " << int(10000 * norms[b] / (1.0 * rows * cols)) / 100.0 << " % of image \n";
+        }
+        std::ostringstream strs;                       // calamp.cpp:258-260: default stream formatting (6 significant digits)
+        strs << totalsum[b];
+        values[b] = strs.str();
+    }
+    std::string txt;
+    if (!fringe_host::slurp(opts->inputDS, txt)) return 102;
+    std::ofstream o(opts->outputDS.c_str());
+    if (!o) { std::cout << "Could not create output VRT {" << opts->outputDS << "}\n"; return 103; }
+    // dirname of the input, absolute
+    std::string dir = fringe_host::dirname_of(opts->inputDS);
+    if (dir.empty() || dir[0] != '/') { char buf[4096]; if (::getcwd(buf, sizeof(buf))) dir = std::string(buf) + "/" + dir; }
+    o << vrt_with_constants(txt, dir, values);
+    return o ? 0 : 103;
+}

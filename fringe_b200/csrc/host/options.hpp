@@ -107,6 +107,26 @@ struct ampdispersionOptions {
     }
 };
 
+// src/calamp/calamp.hpp:27-56
+struct calampOptions {
+    std::string inputDS;     // input VRT with SLCs as bands
+    std::string maskDS;      // optional mask raster
+    std::string outputDS;    // output VRT: copy of the input with amplitudeConstant in every band's slc metadata
+    double defaultValue;     // carried like the reference's (calamp.cpp never reads it: bands without valid data get 1.0)
+    bool applySqrt;          // likewise unused by the reference's loop
+    int blocksize, memsize;
+
+    calampOptions() : defaultValue(1.0), applySqrt(false), blocksize(128), memsize(256) {}
+    void print() const {
+        std::cout << "Input Dataset: " << inputDS << std::endl;
+        std::cout << "Output Dataset: " << outputDS << std::endl;
+        if (!maskDS.empty()) std::cout << "Mask Dataset: " << maskDS << std::endl;
+        std::cout << "Memsize: " << memsize << " Mb \n";
+        std::cout << "Blocksize: " << blocksize << " lines \n";
+        std::cout << "Default norm: " << defaultValue << " \n";
+    }
+};
+
 // Block drivers (drivers.cpp).  Return 0 or the reference's error codes
 // (nmap: 1,102,104,105,106,108,111; evd: 101,102,105-110,112-121), plus 200+status when the
 // device library reports an error (there is no CPU fallback).
@@ -115,3 +135,4 @@ int evd_process(evdOptions* opts);            // src/evd/evd.cpp control flow
 int phase_link_process(evdOptions* opts);     // src/phase_link/phase_link.cpp control flow
 int despeck_process(despeckOptions* opts);    // src/despeck/despeck.cpp: 102, 104-110, 200+status
 int ampdispersion_process(ampdispersionOptions* opts);   // src/ampdispersion/ampdispersion.cpp: 102-104, 108-110
+int calamp_process(calampOptions* opts);                 // src/calamp/calamp.cpp: 102-108

@@ -3,6 +3,10 @@
 // python/adjustMiniStacks.py:180-199 leaves that product to GDAL's "mul" VRT pixel function (complex
 // sources are multiplied in double and written back as CFloat32); here it is one streaming kernel.
 // HBM-bound: 16 bytes in, 8 bytes out per pixel.
+#include <algorithm>
+
+#include <math_constants.h>
+
 #include "common.cuh"
 
 namespace fringe {
@@ -205,6 +209,107 @@ cudaError_t launch_ampdispersion(const float2* slc, const double* alpha, long np
                                  cudaStream_t st) {
     if (npix <= 0) return cudaSuccess;
     k_ampdispersion<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(slc, alpha, npix, bands, da, meanamp);
+    return cudaGetLastError();
+}
+
+
+// ---------------------------------------------------------------------------------------
+// calamp: per-band amplitude calibration constant = mean |z| over the valid pixels
+// (src/calamp/calamp.cpp:207-226: float hypot, NaN -> 0, valid = amplitude != 0 and mask > 0; double sums).
+// The reference's OpenMP reduction has no fixed summation order, so its own result is only defined to
+// rounding; here: per-thread double partials, warp and block reduction, one atomicAdd per block.
+// acc: [bands][2] doubles (sum, count), accumulated across calls (the driver walks the image in blocks).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_calamp(const float2* __restrict__ slc, const uint8_t* __restrict__ mask, long npix,
+                                                double* __restrict__ acc) {
+    const int b = blockIdx.y;
+    const float2* z = slc + (long)b * npix;
+    double sum = 0.0, cnt = 0.0;
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
+        float h = hypotf_exact(__ldg(z + i));
+        if (isnan(h)) h = 0.f;
+        const bool valid = (h != 0.f) && (mask ? mask[i] > 0 : true);
+        if (valid) { sum += (double)h; cnt += 1.0; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+    __shared__ double s_sum[8], s_cnt[8];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { s_sum[w] = sum; s_cnt[w] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, c = 0.0;
+        for (int k = 0; k < 8; ++k) { a += s_sum[k]; c += s_cnt[k]; }
+        atomicAdd(&acc[2 * b], a);
+        atomicAdd(&acc[2 * b + 1], c);
+    }
+}
+
+cudaError_t launch_calamp(const float2* slc, const uint8_t* mask, long npix, int bands, double* acc, cudaStream_t st) {
+    if (npix <= 0 || bands <= 0) return cudaSuccess;
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    long bx = (npix + 255) / 256;
+    const long cap = std::max<long>(1, (long)nsm * 16 / bands);           // ~16 CTAs per SM over all bands
+    if (bx > cap) bx = cap;
+    k_calamp<<<dim3((unsigned)bx, (unsigned)bands), 256, 0, st>>>(slc, mask, npix, acc);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// PS / DS integration (python/integratePS.py:97-130 and :134-159): the wrapped interferogram of a
+// pair (i, j) is the product of the adjusted DS phasors, ds_j * conj(ds_i), except at PS pixels, where it is the
+// full-resolution interferogram reduced to unit modulus, exp(1j * angle(slc_j * conj(slc_i))); the coherence raster
+// gets a fixed value at PS pixels.  All arithmetic in complex64 / float32 like the numpy expressions; the unit phasor
+// is formed as z / |z| (angle(0) = 0 gives 1 + 0j).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_integrate_ps(const float2* __restrict__ ds_i, const float2* __restrict__ ds_j,
+                                                      const float2* __restrict__ slc_i, const float2* __restrict__ slc_j,
+                                                      const uint8_t* __restrict__ ps, long n, float2* __restrict__ out) {
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const bool is_ps = ps[k] == 1;
+        const float2 a = __ldg((is_ps ? slc_j : ds_j) + k), b = __ldg((is_ps ? slc_i : ds_i) + k);
+        // complex64 product a * conj(b), each operation rounded to float (numpy's complex64 multiply)
+        float re = __fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
+        float im = __fsub_rn(__fmul_rn(a.y, b.x), __fmul_rn(a.x, b.y));
+        if (is_ps) {
+            const float m = hypotf_exact(make_float2(re, im));
+            if (m > 0.f && !isinf(m)) { re = __fdiv_rn(re, m); im = __fdiv_rn(im, m); }
+            else if (m == 0.f) { re = 1.f; im = 0.f; }
+            else { re = CUDART_NAN_F; im = CUDART_NAN_F; }
+        }
+        out[k] = make_float2(re, im);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_ps_coherence(const float* __restrict__ tcorr, const uint8_t* __restrict__ ps, long n,
+                                                      float value, float* __restrict__ out) {
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) out[k] = (ps[k] == 1) ? value : tcorr[k];
+}
+
+static unsigned stream_grid(long n) {
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    long b = (n + 255) / 256;
+    if (b > (long)nsm * 32) b = (long)nsm * 32;
+    return (unsigned)std::max<long>(b, 1);
+}
+
+cudaError_t launch_integrate_ps(const float2* ds_i, const float2* ds_j, const float2* slc_i, const float2* slc_j, const uint8_t* ps,
+                                long n, float2* out, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    k_integrate_ps<<<stream_grid(n), 256, 0, st>>>(ds_i, ds_j, slc_i, slc_j, ps, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ps_coherence(const float* tcorr, const uint8_t* ps, long n, float value, float* out, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    k_ps_coherence<<<stream_grid(n), 256, 0, st>>>(tcorr, ps, n, value, out);
     return cudaGetLastError();
 }
 

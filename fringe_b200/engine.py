@@ -238,6 +238,32 @@ class Context:
             da.data_ptr(), mean.data_ptr(), self._stream()))
         return da, mean
 
+    def calamp_block(self, slc, mask=None):
+        """Sum of valid amplitudes and number of valid pixels per band (``fringe_calamp_block``)."""
+        slc = np.ascontiguousarray(slc, np.complex64)
+        bands, lines, cols = slc.shape
+        sums, counts = np.zeros(bands), np.zeros(bands)
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, np.uint8)
+        self._check(lib.fringe_calamp_block(self._h, slc.ctypes.data, None if mask is None else mask.ctypes.data, cols, lines,
+                                            bands, sums.ctypes.data, counts.ctypes.data))
+        return sums, counts
+
+    def integrate_ps(self, ds_i, ds_j, slc_i, slc_j, ps):
+        """Wrapped PS + DS interferogram of one pair (``fringe_integrate_ps``)."""
+        arrs = [np.ascontiguousarray(a, np.complex64) for a in (ds_i, ds_j, slc_i, slc_j)]
+        ps = np.ascontiguousarray(ps, np.uint8)
+        out = np.empty_like(arrs[0])
+        self._check(lib.fringe_integrate_ps(self._h, *[a.ctypes.data for a in arrs], ps.ctypes.data, out.size, out.ctypes.data))
+        return out
+
+    def ps_coherence(self, tcorr, ps, value=0.95):
+        tcorr = np.ascontiguousarray(tcorr, np.float32)
+        ps = np.ascontiguousarray(ps, np.uint8)
+        out = np.empty_like(tcorr)
+        self._check(lib.fringe_ps_coherence(self._h, tcorr.ctypes.data, ps.ctypes.data, out.size, float(value), out.ctypes.data))
+        return out
+
     def despeck_block(self, z1, wts, Nx, Ny, z2=None, coherence=False, first_line=0, n_lines=None):
         """SHP-weighted average (``fringe_despeck_block``): z1 [, z2] (lines, cols) complex64 -> complex64."""
         z1 = np.ascontiguousarray(z1, np.complex64)

@@ -111,6 +111,34 @@ def write_stack_vrt(stack_vrt: str, sources: list[tuple[str, str]], size: tuple[
         f.write("</VRTDataset>")
 
 
+def read_stack_vrt(stack_vrt: str):
+    """[(date, reader)] of a stack VRT written by write_stack_vrt / tops2vrt.py: reader() returns that band's
+    (lines, cols) complex64 array (SrcRect crop applied)."""
+    txt = open(stack_vrt).read()
+    m = re.search(r'rasterXSize="(\d+)"\s+rasterYSize="(\d+)"', txt)
+    xsize, ysize = int(m.group(1)), int(m.group(2))
+    out = []
+    for band in re.findall(r"<VRTRasterBand.*?</VRTRasterBand>", txt, flags=re.S):
+        src = re.search(r"<SourceFilename[^>]*>(.*?)</SourceFilename>", band).group(1).strip()
+        if not os.path.isabs(src):
+            src = os.path.join(os.path.dirname(os.path.abspath(stack_vrt)), src)
+        rect = re.search(r'<SrcRect xOff="(\d+)" yOff="(\d+)"', band)
+        x0, y0 = (int(rect.group(1)), int(rect.group(2))) if rect else (0, 0)
+        date = re.search(r'<MDI key="Date">(.*?)</MDI>', band).group(1).strip()
+
+        def reader(src=src, x0=x0, y0=y0):
+            raw = open(src).read()
+            path = re.search(r"<SourceFilename[^>]*>(.*?)</SourceFilename>", raw).group(1).strip() if src.endswith(".vrt") else src
+            w = int(re.search(r'rasterXSize="(\d+)"', raw).group(1)) if src.endswith(".vrt") else raster_size(src)[0]
+            h = int(re.search(r'rasterYSize="(\d+)"', raw).group(1)) if src.endswith(".vrt") else raster_size(src)[1]
+            if not os.path.isabs(path):
+                path = os.path.join(os.path.dirname(src), path)
+            arr = np.memmap(path, dtype=np.complex64, mode="r", shape=(h, w))
+            return np.ascontiguousarray(arr[y0:y0 + ysize, x0:x0 + xsize])
+        out.append((date, reader))
+    return out
+
+
 def default_dates(n: int, start: str = "20200101", step_days: int = 12) -> list[str]:
     import datetime
     d0 = datetime.datetime.strptime(start, "%Y%m%d")

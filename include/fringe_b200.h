@@ -190,6 +190,20 @@ int fringe_ampdispersion_block(fringe_ctx* ctx, const float* slc, const double* 
 int fringe_ampdispersion_block_device(fringe_ctx* ctx, const float* slc, const double* alpha, int cols,
                                       int lines, int bands, float* da, float* meanamp, void* stream);
 
+/* ---- amplitude calibration (calamp) -------------------------------------------------------
+ * Adds, for every band of one block, the sum of the amplitudes of its valid pixels to sums[band] and their number
+ * to counts[band] (valid: amplitude neither 0 nor NaN and mask > 0; mask may be NULL); the calibration constant of
+ * src/calamp/calamp.cpp:228-243 is sums / counts once all blocks are in.  The caller zeroes sums / counts. */
+int fringe_calamp_block(fringe_ctx* ctx, const float* slc, const uint8_t* mask, int cols, int lines, int bands,
+                        double* sums, double* counts);
+
+/* ---- PS / DS integration (python/integratePS.py:97-130, :134-159) ----------------------------
+ * out = ds_j * conj(ds_i), except where ps == 1: there exp(1j * angle(slc_j * conj(slc_i))).  n complex64 pixels each;
+ * host or device pointers.  fringe_ps_coherence: out = ps == 1 ? ps_value : tcorr (the reference uses 0.95). */
+int fringe_integrate_ps(fringe_ctx* ctx, const float* ds_i, const float* ds_j, const float* slc_i, const float* slc_j,
+                        const uint8_t* ps, int64_t n, float* out);
+int fringe_ps_coherence(fringe_ctx* ctx, const float* tcorr, const uint8_t* ps, int64_t n, float ps_value, float* out);
+
 /* ---- despeck: SHP-weighted average ----------------------------------------------------------
  * One block of `lines` lines; replaces the preparation and pixel loops of
  * src/despeck/despeck.cpp:321-361 and :387-432.  z1, z2: the two bands ([lines*cols] complex64) the

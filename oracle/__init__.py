@@ -76,6 +76,10 @@ class Oracle:
         lib.oracle_despeck_block.argtypes = [fp, fp, u32] + [C.c_int] * 7 + [fp]
         lib.oracle_cmul.argtypes = [fp, fp, C.c_long, fp]
         lib.oracle_cmul.restype = None
+        lib.oracle_calamp_block.argtypes = [fp, u8, C.c_long, C.c_int, dp, dp]
+        lib.oracle_calamp_block.restype = None
+        lib.oracle_integrate_ps.argtypes = [fp, fp, fp, fp, u8, C.c_long, fp]
+        lib.oracle_integrate_ps.restype = None
         self.kind = lib.oracle_kind().decode()
 
     # -- helpers -------------------------------------------------------------------
@@ -205,6 +209,27 @@ class Oracle:
                                            self._p(wts, C.c_uint32), cols, lines, Nx, Ny, first_line, n_lines,
                                            1 if coherence else 0, self._p(out.view(np.float32), C.c_float))
         assert rc == 0
+        return out
+
+    def calamp_block(self, slc, mask=None):
+        """Per band: sum of the valid amplitudes, number of valid pixels (src/calamp/calamp.cpp:207-226)."""
+        slc = np.ascontiguousarray(slc, np.complex64)
+        bands = slc.shape[0]
+        npix = slc[0].size
+        sums, counts = np.zeros(bands), np.zeros(bands)
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, np.uint8)
+        self.lib.oracle_calamp_block(self._p(slc.view(np.float32), C.c_float), self._p(mask, C.c_uint8), npix, bands,
+                                     self._p(sums, C.c_double), self._p(counts, C.c_double))
+        return sums, counts
+
+    def integrate_ps(self, ds_i, ds_j, slc_i, slc_j, ps):
+        """python/integratePS.py:97-130 for one pair."""
+        arrs = [np.ascontiguousarray(a, np.complex64) for a in (ds_i, ds_j, slc_i, slc_j)]
+        ps = np.ascontiguousarray(ps, np.uint8)
+        out = np.empty_like(arrs[0])
+        self.lib.oracle_integrate_ps(*[self._p(a.view(np.float32), C.c_float) for a in arrs], self._p(ps, C.c_uint8), out.size,
+                                     self._p(out.view(np.float32), C.c_float))
         return out
 
     def cmul(self, a, b):

@@ -127,4 +127,41 @@ void oracle_cmul(const float* a, const float* b, long n, float* out) {
     }
 }
 
+
+// calamp: src/calamp/calamp.cpp:207-226 -- per band, sum of the valid amplitudes and their number (float hypot, NaN -> 0,
+// valid = amplitude != 0 and mask > 0).  Serial double sums in raster order: the reference's OpenMP reduction has no
+// defined order, so its own result is reproducible only to rounding (parity gate: relative 1e-12 on the sums).
+void oracle_calamp_block(const float* slc, const unsigned char* mask, long npix, int bands, double* sums, double* counts) {
+    const oracle::cfloat* z = reinterpret_cast<const oracle::cfloat*>(slc);
+    for (int bb = 0; bb < bands; ++bb) {
+        double blocksum = 0.0, blocknorm = 0.0;
+        for (long ii = 0; ii < npix; ++ii) {
+            double absval = std::abs(z[(long)bb * npix + ii]);
+            absval = std::isnan(absval) ? 0.0 : absval;
+            const int valid = (absval != 0.0) * (mask ? (mask[ii] > 0) : 1);
+            blocksum += valid * absval;
+            blocknorm += valid;
+        }
+        sums[bb] += blocksum;
+        counts[bb] += blocknorm;
+    }
+}
+
+// PS / DS integration, python/integratePS.py:97-130: numpy expressions restated in float arithmetic
+// (complex64 product, angle, exp(1j * angle)); the reference evaluates them with numpy, whose float32 atan2 / sincos are
+// not bit-reproducible across builds: parity gate 1e-6 absolute.
+void oracle_integrate_ps(const float* ds_i, const float* ds_j, const float* slc_i, const float* slc_j, const unsigned char* ps,
+                         long n, float* out) {
+    for (long k = 0; k < n; ++k) {
+        const bool is_ps = ps[k] == 1;
+        const float* a = (is_ps ? slc_j : ds_j) + 2 * k;
+        const float* b = (is_ps ? slc_i : ds_i) + 2 * k;
+        volatile float p0 = a[0] * b[0], p1 = a[1] * b[1], p2 = a[1] * b[0], p3 = a[0] * b[1];
+        float re = p0 + p1, im = p2 - p3;                       // a * conj(b)
+        if (is_ps) { const float ang = std::atan2(im, re); re = std::cos(ang); im = std::sin(ang); }
+        out[2 * k] = re;
+        out[2 * k + 1] = im;
+    }
+}
+
 }  // extern "C"
