@@ -263,7 +263,7 @@ cudaError_t launch_calamp(const float2* slc, const uint8_t* mask, long npix, int
 // pair (i, j) is the product of the adjusted DS phasors, ds_j * conj(ds_i), except at PS pixels, where it is the
 // full-resolution interferogram reduced to unit modulus, exp(1j * angle(slc_j * conj(slc_i))); the coherence raster
 // gets a fixed value at PS pixels.  All arithmetic in complex64 / float32 like the numpy expressions; the unit phasor
-// is formed as z / |z| (angle(0) = 0 gives 1 + 0j).
+// is formed as z / |z| (a zero product gives +-1 by the sign of its real part, as atan2 does).
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_integrate_ps(const float2* __restrict__ ds_i, const float2* __restrict__ ds_j,
                                                       const float2* __restrict__ slc_i, const float2* __restrict__ slc_j,
@@ -278,7 +278,12 @@ __global__ void __launch_bounds__(256) k_integrate_ps(const float2* __restrict__
         if (is_ps) {
             const float m = hypotf_exact(make_float2(re, im));
             if (m > 0.f && !isinf(m)) { re = __fdiv_rn(re, m); im = __fdiv_rn(im, m); }
-            else if (m == 0.f) { re = 1.f; im = 0.f; }
+            else if (m == 0.f) {
+                // angle of a zero product: atan2(+-0, +0) = +-0 -> 1 + 0j, but atan2(+-0, -0) = +-pi -> exp(1j * (float)pi)
+                // = -1 -+ 8.74e-8j (the float32 pi is not pi).  A zero SLC sample times a negative one gives -0.
+                if (signbit(re)) { im = signbit(im) ? 8.742278e-8f : -8.742278e-8f; re = -1.f; }
+                else { re = 1.f; }
+            }
             else { re = CUDART_NAN_F; im = CUDART_NAN_F; }
         }
         out[k] = make_float2(re, im);
