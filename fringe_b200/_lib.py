@@ -93,7 +93,7 @@ lib = _load()
 def prof_lib() -> C.CDLL:
     """libfringe_b200_prof.so: the stand-alone microbenchmarks (bench.py, scripts/)."""
     p = C.CDLL(PROF_LIB_PATH)
-    for name in ("fringe_prof_fp32_peak", "fringe_prof_mma_tf32_rate", "fringe_prof_fp64_peak"):
+    for name in ("fringe_prof_fp32_peak", "fringe_prof_mma_tf32_rate", "fringe_prof_mma_f16_rate", "fringe_prof_mma_f16_k8_rate", "fringe_prof_fp64_peak"):
         getattr(p, name).argtypes = [C.c_int, C.POINTER(C.c_double)]
     p.fringe_prof_block_fma_rate.argtypes = [C.c_int, C.POINTER(C.c_double)]
     return p

@@ -55,6 +55,7 @@ def build_cuda(force: bool = False, verbose_ptxas: bool = False, phase_clocks: b
             flags += ["-Xptxas", "-v"]
         if phase_clocks:                     # profiling build: fringe_evd_phase_cycles
             flags += ["-DFRINGE_PHASE_CLOCKS"]
+        flags += os.environ.get("FRINGE_NVCC_DEFS", "").split()      # A/B experiments only (extra -D switches)
         objdir = os.path.join(LIBDIR, "obj")
         os.makedirs(objdir, exist_ok=True)
         procs = []

@@ -39,7 +39,7 @@ struct fringe_ctx {
     int64_t launches = 0;
     bool prof_generic = false;            // fringe_prof_force_generic: A/B comparisons only
     // workspaces reused across blocks
-    DevBuf amp, valid, zpix, adtab, alpha, stats, scratch;
+    DevBuf amp, valid, zpix, zflags, zscale, adtab, alpha, stats, scratch;
     DevBuf in_slc, in_mask, in_wts, o_count, o_wts, o_out, o_tcorr, o_comp;
     DevBuf seq_stack[2], seq_comp, seq_mini, seq_datum;     // fringe_sequential_block
     // cached AD2 table key
@@ -225,7 +225,7 @@ int fringe_destroy(fringe_ctx* c) {
     if (!c) return FRINGE_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf* all[] = {&c->amp, &c->valid, &c->zpix, &c->adtab, &c->alpha, &c->stats, &c->scratch, &c->in_slc, &c->in_mask,
+    DevBuf* all[] = {&c->amp, &c->valid, &c->zpix, &c->zflags, &c->zscale, &c->adtab, &c->alpha, &c->stats, &c->scratch, &c->in_slc, &c->in_mask,
                      &c->in_wts, &c->o_count, &c->o_wts, &c->o_out, &c->o_tcorr, &c->o_comp, &c->seq_stack[0], &c->seq_stack[1],
                      &c->seq_comp, &c->seq_mini, &c->seq_datum};
     for (DevBuf* b : all) b->release();
@@ -557,7 +557,7 @@ static int check_evd(fringe_ctx* ctx, int cols, int lines, int bands, int Nx, in
 
 namespace {
 
-struct EvdPlan { int NP = 0; int zblock = 0; bool generic = false; };
+struct EvdPlan { int NP = 0; int zblock = 0; bool generic = false; bool scaled = false; };
 
 int evd_prepare(fringe_ctx* ctx, int cols, int lines, int bands, int method, int variant, cudaStream_t st,
                 EvdPlan* plan) {
@@ -566,8 +566,10 @@ int evd_prepare(fringe_ctx* ctx, int cols, int lines, int bands, int method, int
     plan->NP = (bands + 1) & ~1;
     plan->generic = ctx->prof_generic;
     if (!plan->generic && variant == FRINGE_VARIANT_EVD && method != FRINGE_EVD_MLE && fringe::evd_mma_order(bands) > 0) {
-        plan->NP = 64;                        // 128 floats per pixel: TF32 hi and lo parts of 32 bands
+        plan->NP = 32;                        // 64 words per pixel: FP16 hi and lo parts of 32 bands
         plan->zblock = -1;
+        CU(ctx->zflags.ensure(npix + 1));
+        CU(ctx->zscale.ensure(32 * sizeof(float)));
     }
     // one extra, all-zero sample vector behind the image: the register-blocked kernel points
     // exhausted / out-of-block SHP slots at it instead of branching
@@ -579,16 +581,22 @@ int evd_prepare(fringe_ctx* ctx, int cols, int lines, int bands, int method, int
 }
 
 // re-layout of input rows [t0, t0+tn), then the solve for output rows [first_line, first_line+n_lines)
-int evd_launch_rows(fringe_ctx* ctx, const EvdPlan& plan, const float* slc, const uint32_t* wts, int cols,
+int evd_launch_rows(fringe_ctx* ctx, EvdPlan& plan, const float* slc, const uint32_t* wts, int cols,
                     int lines, int bands, int Nx, int Ny, int t0, int tn, int first_line, int n_lines,
                     int method, int bandwidth, int mini_stack_count, int variant, int min_neighbors,
                     float* out, float* tcorr, float* comp, cudaStream_t st) {
     const size_t npix = (size_t)cols * lines;
     CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_TRANSPOSE][0], st));
-    if (plan.zblock < 0)
+    if (plan.zblock < 0) {
+        if (!plan.scaled && tn > 0) {          // per-band scales from the first rows of this block that reach the device
+            CU(fringe::launch_band_scale((const float2*)slc, (long)npix, (long)t0 * cols, (long)tn * cols, bands,
+                                         (float*)ctx->zscale.p, st));
+            plan.scaled = true;
+            ctx->launches += 1;
+        }
         CU(fringe::launch_transpose_mma((const float2*)slc, (long)npix, (long)t0 * cols, (long)tn * cols, bands,
-                                        (float2*)ctx->zpix.p, st));
-    else
+                                        (const float*)ctx->zscale.p, (float2*)ctx->zpix.p, (unsigned char*)ctx->zflags.p, st));
+    } else
         CU(fringe::launch_transpose((const float2*)slc, (long)npix, (long)t0 * cols, (long)tn * cols, bands, plan.NP,
                                     plan.zblock, (float2*)ctx->zpix.p, st));
     CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_TRANSPOSE][1], st));
@@ -602,6 +610,7 @@ int evd_launch_rows(fringe_ctx* ctx, const EvdPlan& plan, const float* slc, cons
     a.out = (float2*)out; a.tcorr = tcorr; a.comp = (float2*)comp;
     a.stats = (unsigned long long*)ctx->stats.p;
     a.zblock = plan.zblock; a.tile_pairs = 0; a.scratch = nullptr;
+    a.flags = (const unsigned char*)ctx->zflags.p;
     if (plan.zblock >= 0) {
         int gw; long gg; size_t gs; bool use_scratch;
         fringe::evd_generic_plan(a, &gw, &gg, &gs, &use_scratch);

@@ -1,24 +1,25 @@
-// Tensor-pipe covariance (3xTF32 mma.sync) + in-register power iteration (sm_100a), bands <= 32.
+// Tensor-pipe covariance (two-term FP16 split on mma.sync.m16n8k16) + in-register power iteration (sm_100a), bands <= 32.
 //
-// Same arithmetic contract and the same eigen solve / epilogue as experimental/evd_fast_fp32_fma.cu (EVD / STBAS,
-// evd.cpp control flow); only the masked Gram product C = sum_k z_k z_k^H moves from FP32 FMAs
-// to the warp-level tensor path:
+// EVD / STBAS with evd.cpp's control flow.  The masked Gram product C = sum_k z_k z_k^H runs on the warp-level tensor
+// path, the eigen solve and the epilogue on FP32 FMAs:
 //
-//   layout      k_transpose_mma splits every sample into a TF32 "hi" part and a TF32 "lo"
-//               remainder (x = hi + lo to ~2^-22) and stores a pixel's 32 (zero padded) bands as
-//               128 floats: for g = 0..7 two quads (re, re', im, im') of bands (g, g+8) and
-//               (g+16, g+24) -- each quad is an A fragment as loaded -- then lo in the same order.
-//               Lane (g, t) of a warp therefore fetches everything it needs of one SHP with four
-//               16-byte loads, and the eight lanes that share t read the SHP's 512 bytes
-//               contiguously.
-//   covariance  One warp per pixel.  Four SHPs form one k-chunk of m16n8k8: k = 0..3 are the real
-//               parts of the four samples, k = 4..7 their imaginary parts, so
-//                   Re C = [Zr|Zi] [Zr|Zi]^T          Im C = [Zr|Zi] [-Zi|Zr]^T
-//               and the B fragments of the second product are the first one's with the two
-//               registers swapped and one sign flipped.  Only the 6 of 8 16x8 tiles that touch the
-//               upper triangle are computed: 12 accumulator tiles (48 registers) x 3 products
-//               (hi*hi + hi*lo + lo*hi) = 36 mma.sync per 4 SHPs, issued product-major so that no
-//               instruction waits for the one before it.
+//   layout      k_layout_f16 multiplies every band by a power of two (k_band_scale: the band's typical magnitude lands
+//               near 2^6, so FP16's range covers +-57 dB around it; the coherence is invariant to a per-band factor) and
+//               splits every sample into an FP16 "hi" part and an FP16 "lo" remainder (x = hi + lo to ~2^-22, the same
+//               accuracy as the 3xTF32 split this replaces, at half the tensor work and half the bytes).  A pixel's 32
+//               (zero padded) bands are 64 words: word 4 g + q = half2(re, im) of band g + 8 q, first all hi (128 B),
+//               then all lo.  Lane (g, t) of a warp fetches its share of one SHP with four 8-byte loads (bands g, g+8 and
+//               g+16, g+24, hi and lo), and the eight lanes that share t read the SHP's 128-byte hi (lo) row contiguously.
+//               Pixels whose scaled samples leave the FP16 range (|x| >= 65504, NaN, or everything below 2^-8) are
+//               flagged; a pixel with a flagged SHP recomputes its Gram product from the original planes on FP32 FMAs.
+//   covariance  One warp per pixel.  Eight SHPs form one k-chunk of m16n8k16: k = (2t, 2t+1) are (re, im) of SHP t,
+//               k = (2t+8, 2t+9) those of SHP t+4, so a half2 sample *is* an A-fragment register (an A quad = the 8-byte
+//               loads of SHP t and SHP t+4 side by side, no assembly) and
+//                   Re C = A B,  B[(re,im) of q][j] = ( re_j,  im_j)  -- the same registers again
+//                   Im C = A B', B'[(re,im) of q][j] = (-im_j,  re_j)  -- halves swapped, one sign flipped
+//               Only the 6 of 8 16x8 tiles that touch the upper triangle are computed: 12 accumulator tiles
+//               (48 registers) x 3 products (hi*hi + hi*lo + lo*hi) = 36 mma.sync per 8 SHPs, issued product-major so
+//               that no instruction waits for the one before it.
 //   hand-off    accumulator fragments -> coherence -> planar (re | im) Hermitian matrix in shared
 //               memory.
 //   eigen       lane = row; the row lives in registers as pairs of consecutive columns and the
@@ -29,6 +30,7 @@
 //   schedule    one 16-warp CTA per SM; a CTA owns a band of 4 rows x a column segment and its warps
 //               draw pixels from a shared counter in column-major order, so the union of their
 //               windows stays in L1.
+#include <cuda_fp16.h>
 #include <math_constants.h>
 
 #include <cstdlib>
@@ -61,64 +63,67 @@ __device__ __forceinline__ float fast_rcp(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
+// SHPs per k-chunk of m16n8k16.  (Every mma.sync shape costs the same tensor-pipe time on this part -- m16n8k8 TF32,
+// m16n8k8 FP16 and m16n8k16 FP16 all measure one instruction per 8.5 cycles and SM sub-partition, fringe_prof_mma_* -- so
+// the k = 16 shape halves the pipe time of the product; an m16n8k8 FP16 version, whose operands need no assembly at all,
+// measured 210 ms per 30 M pixels against 199 ms for this one.)
+constexpr int CHUNK = 8;
 
-// D(16x8) += A(16x8, row) * B(8x8, col), TF32 inputs, FP32 accumulate
-__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
-                                         uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+// D(16x8) += A(16x16, row) * B(16x8, col), FP16 inputs, FP32 accumulate
+__device__ __forceinline__ void mma_f16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                        uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-
-// One SHP's share of a lane: bands g, g+8, g+16, g+24, hi and lo parts, stored so that each
-// 16-byte load is an A fragment as it stands: quad I = (re, re', im, im') of bands 16 I + g and
-// 16 I + g + 8.
+// m16n8k16: the A quad of row block I is (bands 16 I + g, 16 I + g + 8 of SHP t | the same of SHP t + 4): two 8-byte loads
+// whose destinations can sit side by side, so the quads need no assembly
 struct MmaOperands {
-    uint4 ah[2], al[2];
-    __device__ __forceinline__ void load(const float* __restrict__ zq, int g) {
-        const uint4* p = reinterpret_cast<const uint4*>(zq) + 2 * g;
-        ah[0] = __ldg(p); ah[1] = __ldg(p + 1); al[0] = __ldg(p + 16); al[1] = __ldg(p + 17);
+    uint2 h[2][2], l[2][2];            // [row block I][SHP slot]
+    __device__ __forceinline__ void load(const uint32_t* __restrict__ zh, const int (&idx)[2], int g) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const uint2* p = reinterpret_cast<const uint2*>(zh + (long)idx[k] * 64) + 2 * g;
+            h[0][k] = __ldg(p); h[1][k] = __ldg(p + 1); l[0][k] = __ldg(p + 16); l[1][k] = __ldg(p + 17);
+        }
     }
+    // band 8 J + g of SHP slot k
+    __device__ __forceinline__ uint32_t bh(int J, int k) const { return (J & 1) ? h[J >> 1][k].y : h[J >> 1][k].x; }
+    __device__ __forceinline__ uint32_t bl(int J, int k) const { return (J & 1) ? l[J >> 1][k].y : l[J >> 1][k].x; }
 };
+// (re, im) -> (-im, re)
+__device__ __forceinline__ uint32_t rot90(uint32_t w) { return __byte_perm(w, 0, 0x1032) ^ 0x00008000u; }
 
 // tiles (I, J) on or above the diagonal of the 2 x 4 grid of 16 x 8 tiles
 __device__ __forceinline__ constexpr int tile_i(int tl) { return tl < 4 ? 0 : 1; }
 __device__ __forceinline__ constexpr int tile_j(int tl) { return tl < 4 ? tl : tl - 2; }
 
-// 4 SHPs (one per t) into the 6 real and 6 imaginary accumulator tiles: 36 mma.sync
+// CHUNK SHPs into the 6 real and 6 imaginary accumulator tiles: 36 mma.sync.
+// Row block I of A = bands 16 I + g and 16 I + g + 8; column block J of B = band 8 J + g of the lane's own samples; the
+// imaginary product takes B rotated by 90 degrees.
 __device__ __forceinline__ void mma_chunk(float (&cre)[6][4], float (&cim)[6][4], const MmaOperands& o) {
-    // B fragments of column block J (band 8 J + g), every role in its own register pair so that the
-    // pairs stay put across the instructions that use them: real product (re, im), imaginary
-    // product (-im, re); hi and lo
     uint32_t bh[4][2], bl[4][2], nh[4][2], nl[4][2];
 #pragma unroll
-    for (int I = 0; I < 2; ++I) {
-        bh[2 * I][0] = o.ah[I].x; bh[2 * I][1] = o.ah[I].z; bh[2 * I + 1][0] = o.ah[I].y; bh[2 * I + 1][1] = o.ah[I].w;
-        bl[2 * I][0] = o.al[I].x; bl[2 * I][1] = o.al[I].z; bl[2 * I + 1][0] = o.al[I].y; bl[2 * I + 1][1] = o.al[I].w;
-    }
-#pragma unroll
     for (int J = 0; J < 4; ++J) {
-        nh[J][0] = bh[J][1] ^ 0x80000000u; nh[J][1] = bh[J][0];
-        nl[J][0] = bl[J][1] ^ 0x80000000u; nl[J][1] = bl[J][0];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            bh[J][k] = o.bh(J, k); bl[J][k] = o.bl(J, k);
+            nh[J][k] = rot90(o.bh(J, k)); nl[J][k] = rot90(o.bl(J, k));
+        }
     }
     // products outermost: the 12 accumulator tiles are independent, so consecutive mma.sync never
     // wait for each other (with the tile loop outermost every instruction would depend on the one
     // issued two slots earlier and the tensor pipe would idle for the mma latency)
 #pragma unroll
-    for (int prod = 0; prod < 3; ++prod) {
+    for (int prod = 0; prod < 3; ++prod) {                               // hi * hi, hi * lo, lo * hi
 #pragma unroll
         for (int tl = 0; tl < 6; ++tl) {
             const int I = tile_i(tl), J = tile_j(tl);
-            const uint4 av = (prod == 2) ? o.al[I] : o.ah[I];            // hi * hi, hi * lo, lo * hi
+            const uint2 a0 = (prod == 2) ? o.l[I][0] : o.h[I][0], a1 = (prod == 2) ? o.l[I][1] : o.h[I][1];
             const uint32_t* bv = (prod == 1) ? bl[J] : bh[J];
             const uint32_t* nv = (prod == 1) ? nl[J] : nh[J];
-            mma_tf32(cre[tl], av.x, av.y, av.z, av.w, bv[0], bv[1]);
-            mma_tf32(cim[tl], av.x, av.y, av.z, av.w, nv[0], nv[1]);
+            mma_f16(cre[tl], a0.x, a0.y, a1.x, a1.y, bv[0], bv[1]);
+            mma_f16(cim[tl], a0.x, a0.y, a1.x, a1.y, nv[0], nv[1]);
         }
     }
 }
@@ -130,7 +135,8 @@ struct MmaCfg {
     // coherence matrix in shared memory: real and imaginary planes, rows NS floats apart;
     // NS = 4 (mod 8) keeps rows 16-byte aligned and spreads the hand-off stores over the banks
     static constexpr int NS = ((NE + 3) / 4 * 4) % 8 == 4 ? (NE + 3) / 4 * 4 : (NE + 3) / 4 * 4 + 4;
-    static constexpr int PLANE = NE * NS;               // floats per plane
+    // floats per plane; orders below 32 keep one extra, permanently zero row for the lanes beyond the matrix
+    static constexpr int PLANE = (NE < 32 ? NE + 1 : NE) * NS;
     // per warp: two planes, two broadcast vectors (double buffered, re | im planes of 32),
     // 32 powers, 64 list slots
     static constexpr int SMEM_PER_WARP =
@@ -157,39 +163,101 @@ __device__ __forceinline__ u64 pack2(float x, float y) {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------
-// re-layout: [bands][npix] -> [npix][hi 64 | lo 64] floats (see the header of this file)
+// per-band power-of-two scale: 2^(5 - E), E = rounded mean binary exponent of the finite non-zero components of a
+// sample of the rows at hand (a geometric mean: one absurd value cannot move it).  For Gaussian components of standard
+// deviation s the mean exponent is log2(s) - 1.4, so s lands near 2^6.4.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_transpose_mma(const float2* __restrict__ slc, long npix, long first,
-                                                       long pend, int bands, float* __restrict__ zf) {
-    const int pix = threadIdx.x & 31, g = threadIdx.x >> 5;
-    const long p = first + (long)blockIdx.x * 32 + pix;
-    if (p >= pend) return;
-    // quad I = (re, re', im, im') of bands 16 I + g and 16 I + g + 8
-    uint32_t h[8], l[8];
+__global__ void __launch_bounds__(256) k_band_scale(const float2* __restrict__ slc, long npix, long first, long count,
+                                                    float* __restrict__ scale) {
+    const int b = blockIdx.x;
+    const long groups = (count + 3) / 4;                       // 4 consecutive pixels = one 32-byte sector
+    const long want = 16384;                                   // sectors sampled per band
+    const long step = groups > want ? groups / want : 1;
+    long esum = 0; int n = 0;
+    for (long gi = threadIdx.x; gi * step < groups; gi += blockDim.x) {
+        const long p0 = first + gi * step * 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (p0 + k >= first + count) break;
+            const float2 v = __ldg(&slc[(long)b * npix + p0 + k]);
+            const uint32_t ex = (__float_as_uint(v.x) >> 23) & 0xffu, ey = (__float_as_uint(v.y) >> 23) & 0xffu;
+            if (ex > 0 && ex < 255) { esum += (int)ex - 127; ++n; }
+            if (ey > 0 && ey < 255) { esum += (int)ey - 127; ++n; }
+        }
+    }
+    __shared__ long s_sum[256];
+    __shared__ int s_n[256];
+    s_sum[threadIdx.x] = esum; s_n[threadIdx.x] = n;
+    __syncthreads();
+    for (int s2 = 128; s2 > 0; s2 >>= 1) {
+        if (threadIdx.x < s2) { s_sum[threadIdx.x] += s_sum[threadIdx.x + s2]; s_n[threadIdx.x] += s_n[threadIdx.x + s2]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        int e = 0;
+        if (s_n[0] > 0) e = 5 - (int)floor((double)s_sum[0] / (double)s_n[0] + 0.5);
+        e = max(-100, min(100, e));
+        scale[b] = exp2f((float)e);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// re-layout: [bands][npix] -> [npix][hi 32 | lo 32] half2 words (see the header of this file) + range flags
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_layout_f16(const float2* __restrict__ slc, long npix, long first, long pend, int bands,
+                                                    const float* __restrict__ scale, uint32_t* __restrict__ zh,
+                                                    unsigned char* __restrict__ flags) {
+    // lane = 8 * (pixel & 3) + g: a warp reads eight 32-byte sectors per band group and writes four 128-byte rows
+    const int g = threadIdx.x & 7, sub = threadIdx.x >> 3;
+    const long p = first + (long)blockIdx.x * 32 + sub;
+    const bool live = p < pend;
+    uint32_t h[4], l[4];
+    float top = 0.f;
+    bool hot = false;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int b = g + 8 * q;
         float2 v = make_float2(0.f, 0.f);
-        if (b < bands) v = __ldg(&slc[(long)b * npix + p]);
-        const uint32_t hx = to_tf32(v.x), hy = to_tf32(v.y);
-        const float rx = v.x - __uint_as_float(hx), ry = v.y - __uint_as_float(hy);
-        const int k = 4 * (q >> 1) + (q & 1);
-        h[k] = hx; h[k + 2] = hy;
-        l[k] = isfinite(rx) ? to_tf32(rx) : 0u;
-        l[k + 2] = isfinite(ry) ? to_tf32(ry) : 0u;
+        if (live && b < bands) {
+            v = __ldg(&slc[(long)b * npix + p]);
+            const float sc = __ldg(&scale[b]);
+            v.x *= sc; v.y *= sc;
+        }
+        const float ax = fabsf(v.x), ay = fabsf(v.y);
+        if (!(ax < 65504.f) || !(ay < 65504.f)) { hot = true; v = make_float2(0.f, 0.f); }      // also NaN
+        top = fmaxf(top, fmaxf(ax, ay));
+        const __half2 hi = __floats2half2_rn(v.x, v.y);
+        const float2 hf = __half22float2(hi);
+        const __half2 lo = __floats2half2_rn(v.x - hf.x, v.y - hf.y);                           // exact differences
+        h[q] = *reinterpret_cast<const uint32_t*>(&hi);
+        l[q] = *reinterpret_cast<const uint32_t*>(&lo);
     }
-    uint4* o = reinterpret_cast<uint4*>(zf + p * 128) + 2 * g;
+    // a pixel = 8 consecutive lanes
+#pragma unroll
+    for (int s2 = 1; s2 < 8; s2 <<= 1) {
+        top = fmaxf(top, __shfl_xor_sync(FULLMASK, top, s2));
+        hot = hot | (__shfl_xor_sync(FULLMASK, (int)hot, s2) != 0);
+    }
+    if (!live) return;
+    const bool cold = top > 0.f && top < 0.00390625f;          // everything below 2^-8: the lo parts are gone
+    if (hot) { h[0] = h[1] = h[2] = h[3] = 0u; l[0] = l[1] = l[2] = l[3] = 0u; }
+    uint4* o = reinterpret_cast<uint4*>(zh + p * 64) + g;
     o[0] = make_uint4(h[0], h[1], h[2], h[3]);
-    o[1] = make_uint4(h[4], h[5], h[6], h[7]);
-    o[16] = make_uint4(l[0], l[1], l[2], l[3]);
-    o[17] = make_uint4(l[4], l[5], l[6], l[7]);
+    o[8] = make_uint4(l[0], l[1], l[2], l[3]);
+    if (g == 0) flags[p] = (hot || cold) ? 1 : 0;
 }
 
-cudaError_t launch_transpose_mma(const float2* slc, long npix, long first, long count, int bands, float2* zpix,
-                                 cudaStream_t st) {
+cudaError_t launch_band_scale(const float2* slc, long npix, long first, long count, int bands, float* scale, cudaStream_t st) {
+    if (count <= 0 || bands <= 0) return cudaSuccess;
+    k_band_scale<<<(unsigned)bands, 256, 0, st>>>(slc, npix, first, count, scale);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_transpose_mma(const float2* slc, long npix, long first, long count, int bands, const float* scale,
+                                 float2* zpix, unsigned char* flags, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
-    k_transpose_mma<<<(unsigned)((count + 31) / 32), 256, 0, st>>>(slc, npix, first, first + count, bands,
-                                                                  reinterpret_cast<float*>(zpix));
+    k_layout_f16<<<(unsigned)((count + 31) / 32), 256, 0, st>>>(slc, npix, first, first + count, bands, scale,
+                                                               reinterpret_cast<uint32_t*>(zpix), flags);
     return cudaGetLastError();
 }
 
@@ -221,6 +289,10 @@ __global__ void __launch_bounds__(512, 1) k_evd_mma(const EvdArgs a) {
     float* s_pw = s_vec + 128;                                             // [32]
     int* s_list = reinterpret_cast<int*>(s_pw + 32);                       // [64]
 
+    if (NE < 32) {                               // the zero row (never written again)
+        for (int e = lane; e < NS; e += 32) { s_re[NE * NS + e] = 0.f; s_im[NE * NS + e] = 0.f; }
+        __syncwarp();
+    }
     const int k0 = a.mini_stack_count - 1;
     const bool isstbas = (a.method == 2);
     const int BW = a.bandwidth;
@@ -236,7 +308,7 @@ __global__ void __launch_bounds__(512, 1) k_evd_mma(const EvdArgs a) {
         inv_pairs = 1.0f / (float)cnt;
     }
     const long npix_block = (long)a.cols * a.lines;
-    const float* zf = reinterpret_cast<const float*>(a.zpix);
+    const uint32_t* zh = reinterpret_cast<const uint32_t*>(a.zpix);
 
     // Work: the CTA owns a band of BAND rows x a segment of columns and its warps draw pixels from
     // a shared counter in column-major order inside the band (k -> row k % rows, column k / rows).
@@ -253,7 +325,7 @@ __global__ void __launch_bounds__(512, 1) k_evd_mma(const EvdArgs a) {
     const int row0 = a.first_line + band * Cfg::BAND;
     const int rows = min(Cfg::BAND, a.first_line + a.n_lines - row0);
     const int total = (c1 - c0) * rows;
-    unsigned long long st_pix = 0, st_it = 0, st_cap = 0;
+    unsigned long long st_pix = 0, st_it = 0, st_cap = 0, st_hot = 0;
     PHASE_DECL
 
     auto draw = [&]() -> int {
@@ -294,6 +366,7 @@ __global__ void __launch_bounds__(512, 1) k_evd_mma(const EvdArgs a) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) { cre[tl][e] = 0.f; cim[tl][e] = 0.f; }
         int npix = 0;
+        bool hot = false;
 #pragma unroll 1
         for (int w0 = 0; w0 < a.nulong; w0 += 2) {
             int n = 0;
@@ -310,19 +383,25 @@ __global__ void __launch_bounds__(512, 1) k_evd_mma(const EvdArgs a) {
                 n += __popc(V);
             }
             npix += n;
-            const int chunks = (n + 3) >> 2;                   // 4 SHPs per chunk
-            if (lane < 4 && n + lane < 4 * chunks) s_list[n + lane] = zero_idx;
+            const int chunks = (n + CHUNK - 1) / CHUNK;
+            if (lane < CHUNK && n + lane < CHUNK * chunks) s_list[n + lane] = zero_idx;
             __syncwarp();
+            // range flags of the SHPs (k_layout_f16): any flagged sample sends the pixel to the FP32 recomputation below
+            if (lane < n && __ldg(&a.flags[s_list[lane]])) hot = true;
+            if (lane + 32 < n && __ldg(&a.flags[s_list[lane + 32]])) hot = true;
             PHASE_MARK(0)
-            // no register double buffering of the operands: at 126 registers four CTAs fit per SM and
-            // the other 15 warps cover the load latency (measured equal to the prefetching version at
-            // 166 registers / 3 CTAs); only the next list entry is fetched ahead
+            // no register double buffering of the operands: the other 15 warps cover the load latency (measured equal
+            // to a prefetching version with fewer resident warps); only the next list entries are fetched ahead
             MmaOperands op;
-            int idx = s_list[t];
+            int idx[CHUNK / 4];
+#pragma unroll
+            for (int k = 0; k < CHUNK / 4; ++k) idx[k] = s_list[t + 4 * k];
 #pragma unroll 1
             for (int c = 0; c < chunks; ++c) {
-                op.load(zf + (long)idx * 128, g);
-                idx = s_list[4 * min(c + 1, chunks - 1) + t];
+                op.load(zh, idx, g);
+                const int cn = CHUNK * min(c + 1, chunks - 1) + t;
+#pragma unroll
+                for (int k = 0; k < CHUNK / 4; ++k) idx[k] = s_list[cn + 4 * k];
                 mma_chunk(cre, cim, op);
             }
             PHASE_MARK(1)
@@ -333,43 +412,90 @@ __global__ void __launch_bounds__(512, 1) k_evd_mma(const EvdArgs a) {
         // accumulator fragment of tile (I, J): element e is row 16 I + g + 8 (e >> 1), column 8 J + 2 t + (e & 1)
         __syncwarp();
         bool zero_band = false;
-        if (g == 2 * t || g == 2 * t + 1) {
-            const bool odd = (g != 2 * t);              // selects, not a runtime index: keeps the tiles in registers
-            const float p0 = odd ? cre[0][1] : cre[0][0], p1 = odd ? cre[1][3] : cre[1][2];
-            const float p2 = odd ? cre[4][1] : cre[4][0], p3 = odd ? cre[5][3] : cre[5][2];
-            // padded bands get +inf so that their scaled entries come out as exact zeros
-            s_pw[g] = (g < N) ? sqrtf(p0) : CUDART_INF_F;
-            s_pw[g + 8] = (g + 8 < N) ? sqrtf(p1) : CUDART_INF_F;
-            s_pw[g + 16] = (g + 16 < N) ? sqrtf(p2) : CUDART_INF_F;
-            s_pw[g + 24] = (g + 24 < N) ? sqrtf(p3) : CUDART_INF_F;
-            zero_band = (g < N && !(p0 > 0.f)) || (g + 8 < N && !(p1 > 0.f)) || (g + 16 < N && !(p2 > 0.f)) || (g + 24 < N && !(p3 > 0.f));
-        }
-        // a band that is zero in every SHP puts NaNs into C.  The reference hands that matrix to zheevr, which (OpenBLAS)
-        // reports success with an undefined vector; its temporal coherence then comes out as NaN (arg of NaN entries,
-        // evd.cpp:770-786).  Here: temporal coherence NaN as well, phasors and compressed SLC 0 instead of LAPACK's
-        // undefined values.  Arises only when a whole window is zero in one date.
-        zero_band = __any_sync(FULLMASK, zero_band);
-        __syncwarp();
-        {
-            float ir[4], ic[8];
+        hot = __any_sync(FULLMASK, hot);
+        if (!hot) {
+            if (g == 2 * t || g == 2 * t + 1) {
+                const bool odd = (g != 2 * t);              // selects, not a runtime index: keeps the tiles in registers
+                const float p0 = odd ? cre[0][1] : cre[0][0], p1 = odd ? cre[1][3] : cre[1][2];
+                const float p2 = odd ? cre[4][1] : cre[4][0], p3 = odd ? cre[5][3] : cre[5][2];
+                // padded bands get +inf so that their scaled entries come out as exact zeros
+                s_pw[g] = (g < N) ? sqrtf(p0) : CUDART_INF_F;
+                s_pw[g + 8] = (g + 8 < N) ? sqrtf(p1) : CUDART_INF_F;
+                s_pw[g + 16] = (g + 16 < N) ? sqrtf(p2) : CUDART_INF_F;
+                s_pw[g + 24] = (g + 24 < N) ? sqrtf(p3) : CUDART_INF_F;
+                zero_band = (g < N && !(p0 > 0.f)) || (g + 8 < N && !(p1 > 0.f)) || (g + 16 < N && !(p2 > 0.f)) || (g + 24 < N && !(p3 > 0.f));
+            }
+            // a band that is zero in every SHP puts NaNs into C.  The reference hands that matrix to zheevr, which (OpenBLAS)
+            // reports success with an undefined vector; its temporal coherence then comes out as NaN (arg of NaN entries,
+            // evd.cpp:770-786).  Here: temporal coherence NaN as well, phasors and compressed SLC 0 instead of LAPACK's
+            // undefined values.  Arises only when a whole window is zero in one date.
+            zero_band = __any_sync(FULLMASK, zero_band);
+            __syncwarp();
+            {
+                float ir[4], ic[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) ir[q] = fast_rcp(s_pw[g + 8 * q]);
+                for (int q = 0; q < 4; ++q) ir[q] = fast_rcp(s_pw[g + 8 * q]);
 #pragma unroll
-            for (int J = 0; J < 4; ++J) { ic[2 * J] = fast_rcp(s_pw[8 * J + 2 * t]); ic[2 * J + 1] = fast_rcp(s_pw[8 * J + 2 * t + 1]); }
+                for (int J = 0; J < 4; ++J) { ic[2 * J] = fast_rcp(s_pw[8 * J + 2 * t]); ic[2 * J + 1] = fast_rcp(s_pw[8 * J + 2 * t + 1]); }
 #pragma unroll
-            for (int tl = 0; tl < 6; ++tl) {
-                const int I = tile_i(tl), J = tile_j(tl);
+                for (int tl = 0; tl < 6; ++tl) {
+                    const int I = tile_i(tl), J = tile_j(tl);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int r = 16 * I + g + 8 * (e >> 1), c = 8 * J + 2 * t + (e & 1);
-                    const float s = ir[2 * I + (e >> 1)] * ic[2 * J + (e & 1)];
-                    if (c > r && c < NE) {                   // strict upper entry and its mirror
-                        const float vr = cre[tl][e] * s, vi = cim[tl][e] * s;
-                        s_re[r * NS + c] = vr; s_im[r * NS + c] = vi;
-                        s_re[c * NS + r] = vr; s_im[c * NS + r] = -vi;
+                    for (int e = 0; e < 4; ++e) {
+                        const int r = 16 * I + g + 8 * (e >> 1), c = 8 * J + 2 * t + (e & 1);
+                        const float s = ir[2 * I + (e >> 1)] * ic[2 * J + (e & 1)];
+                        if (c > r && c < NE) {                   // strict upper entry and its mirror
+                            const float vr = cre[tl][e] * s, vi = cim[tl][e] * s;
+                            s_re[r * NS + c] = vr; s_im[r * NS + c] = vi;
+                            s_re[c * NS + r] = vr; s_im[c * NS + r] = -vi;
+                        }
                     }
                 }
+                if (lane < NE) { s_re[lane * NS + lane] = (lane < N) ? 1.f : 0.f; s_im[lane * NS + lane] = 0.f; }
             }
+        } else {
+            ++st_hot;
+            // A sample of this pixel's neighbourhood left the FP16 range: FP32 recomputation from the original planes
+            // (evd.cpp:537-582 on FMAs).  Lane j accumulates column j of the upper triangle in shared memory.
+            for (int e = lane; e < 2 * Cfg::PLANE; e += 32) s_re[e] = 0.f;          // both planes (contiguous)
+            float* zv = s_vec;
+            __syncwarp();
+            for (int w = 0; w < a.nulong; ++w) {
+                uint32_t word = mask_word(w);
+                while (word) {                                                         // warp-uniform
+                    const int bit = __ffs(word) - 1;
+                    word &= word - 1;
+                    const short2 d = s_off[w * 32 + bit];
+                    const int yy = row + d.x, xx = col + d.y;
+                    if (yy < 0 || yy >= a.lines || xx < 0 || xx >= a.cols) continue;
+                    float2 z = make_float2(0.f, 0.f);
+                    if (lane < N) z = __ldg(&a.slc[(long)lane * npix_block + (long)yy * a.cols + xx]);
+                    __syncwarp();
+                    zv[lane] = z.x; zv[32 + lane] = z.y;
+                    __syncwarp();
+                    if (lane < N)
+                        for (int i = 0; i <= lane; ++i) {
+                            const float zr = zv[i], zi = zv[32 + i];
+                            s_re[i * NS + lane] += zr * z.x + zi * z.y;                 // z_i * conj(z_j)
+                            s_im[i * NS + lane] += zi * z.x - zr * z.y;
+                        }
+                }
+            }
+            __syncwarp();
+            const float pw = (lane < N) ? sqrtf(s_re[min(lane, NE - 1) * NS + min(lane, NE - 1)]) : CUDART_INF_F;
+            s_pw[lane] = pw;
+            zero_band = __any_sync(FULLMASK, lane < N && !(pw > 0.f));
+            __syncwarp();
+            if (lane < N) {
+                const float ij = 1.0f / pw;
+                for (int i = 0; i < lane; ++i) {
+                    const float sc = ij / s_pw[i];
+                    const float vr = s_re[i * NS + lane] * sc, vi = s_im[i * NS + lane] * sc;
+                    s_re[i * NS + lane] = vr; s_im[i * NS + lane] = vi;
+                    s_re[lane * NS + i] = vr; s_im[lane * NS + i] = -vi;
+                }
+            }
+            __syncwarp();
             if (lane < NE) { s_re[lane * NS + lane] = (lane < N) ? 1.f : 0.f; s_im[lane * NS + lane] = 0.f; }
         }
         __syncwarp();
@@ -382,7 +508,7 @@ __global__ void __launch_bounds__(512, 1) k_evd_mma(const EvdArgs a) {
         if (solve && zero_band) tc = CUDART_NAN_F;
         if (solve && !zero_band) {
             ++st_pix;
-            const int r = (lane < NE) ? lane : (NE - 1);
+            const int r = (lane < NE) ? lane : NE;           // lanes beyond the matrix read the zero row
             // row r of the matrix as pairs of consecutive columns: cr2[k] = (Re C[r][2k], Re C[r][2k+1])
             constexpr int NP2 = NE / 2;
             u64 cr2[NP2], ci2[NP2];
@@ -399,8 +525,7 @@ __global__ void __launch_bounds__(512, 1) k_evd_mma(const EvdArgs a) {
                     ci2[NP2 - 1] = *reinterpret_cast<const u64*>(s_im + r * NS + NE - 2);
                 }
             }
-            // rows >= N of the padded matrix are exact zeros; only lanes beyond the padded
-            // order (which re-read the last row) have to be silenced
+            // rows >= N of the padded matrix are exact zeros, and so is the row of the lanes beyond the padded order
             const float live = (lane < NE) ? 1.f : 0.f;
             if (isstbas) {                                   // evd.cpp:695-706 band limit
 #pragma unroll
@@ -417,7 +542,8 @@ __global__ void __launch_bounds__(512, 1) k_evd_mma(const EvdArgs a) {
             float2 x;
             {
                 const int ks = N >> 1;
-                const float2 v = make_float2(s_re[ks * NS + r], s_im[ks * NS + r]);
+                const int rc = min(lane, NE - 1);
+                const float2 v = make_float2(s_re[ks * NS + rc], s_im[ks * NS + rc]);
                 const float keep = (isstbas && abs(ks - lane) > BW) ? 0.f : live;
                 x = make_float2(v.x * keep, -v.y * keep);
                 const float m2 = x.x * x.x + x.y * x.y;
@@ -462,11 +588,12 @@ __global__ void __launch_bounds__(512, 1) k_evd_mma(const EvdArgs a) {
                     C0 = fma2(cr2[NP2 - 1], qi, C0); D0 = fma2(ci2[NP2 - 1], qr, D0);
                 }
                 float yr, yi;
-                {
-                    const float2 a0 = unpack2(A0), a1 = unpack2(A1), b0 = unpack2(B0), b1 = unpack2(B1);
-                    const float2 c0 = unpack2(C0), c1 = unpack2(C1), d0 = unpack2(D0), d1 = unpack2(D1);
-                    yr = (((a0.x + a0.y) + (a1.x + a1.y)) - ((b0.x + b0.y) + (b1.x + b1.y))) * live;
-                    yi = (((c0.x + c0.y) + (c1.x + c1.y)) + ((d0.x + d0.y) + (d1.x + d1.y))) * live;
+                {                                                  // fold the accumulator pairs with packed operations too
+                    const u64 one2 = pack2(1.f, 1.f), neg2 = pack2(-1.f, -1.f);
+                    const float2 re = unpack2(fma2(fma2(B1, one2, B0), neg2, fma2(A1, one2, A0)));
+                    const float2 im = unpack2(fma2(fma2(D1, one2, D0), one2, fma2(C1, one2, C0)));
+                    yr = re.x + re.y;
+                    yi = im.x + im.y;
                 }
                 if (it < next_chk - 1) {
                     const float2 xn = make_float2(fmaf(-beta, xp.x, yr * inv_lam), fmaf(-beta, xp.y, yi * inv_lam));
@@ -620,6 +747,7 @@ __global__ void __launch_bounds__(512, 1) k_evd_mma(const EvdArgs a) {
         atomicAdd(&a.stats[0], st_pix);
         atomicAdd(&a.stats[1], st_it);
         atomicAdd(&a.stats[3], st_cap);
+        atomicAdd(&a.stats[5], st_hot);
     }
 }
 

@@ -288,6 +288,78 @@ cudaError_t measure_mma_tf32(cudaStream_t st, double* tflops) {
     return cudaGetLastError();
 }
 
+
+// The same 12-tile pattern on mma.sync.m16n8k16 FP16 (FP32 accumulate): twice the k extent per instruction.
+template <bool K16>
+__global__ void __launch_bounds__(128, 4) k_mma_f16(float* out, int iters, float seed) {
+    uint32_t afr[2][4], bfr[4][2];
+    float acc[12][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) afr[i][r] = 0x3c003c00u ^ ((threadIdx.x + 4 * i + r) & 0x3ffu) ^ (__float_as_uint(seed) & 0x30u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) bfr[j][r] = 0x34003400u ^ ((threadIdx.x + 2 * j + r) & 0x3ffu);
+#pragma unroll
+    for (int t = 0; t < 12; ++t)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[t][r] = 0.f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int t = 0; t < 12; ++t) {
+            const int i = t & 1, j = (t >> 1) & 3;
+            if (K16)
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+f"(acc[t][0]), "+f"(acc[t][1]), "+f"(acc[t][2]), "+f"(acc[t][3])
+                             : "r"(afr[i][0]), "r"(afr[i][1]), "r"(afr[i][2]), "r"(afr[i][3]), "r"(bfr[j][0]), "r"(bfr[j][1]));
+            else
+                asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                             : "+f"(acc[t][0]), "+f"(acc[t][1]), "+f"(acc[t][2]), "+f"(acc[t][3])
+                             : "r"(afr[i][0]), "r"(afr[i][1]), "r"(bfr[j][0]));
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < 12; ++t)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) s += acc[t][r];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <bool K16>
+static cudaError_t measure_mma_f16_t(cudaStream_t st, double* tflops) {
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = nsm * 4 * 2, threads = 128, iters = 20000;
+    float* out = nullptr;
+    cudaError_t e = cudaMalloc(&out, (size_t)blocks * threads * sizeof(float));
+    if (e != cudaSuccess) return e;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0, st);
+        k_mma_f16<K16><<<blocks, threads, 0, st>>>(out, iters, 1e-3f);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        // 12 tiles x (16 x 8 x 16 or 8 MACs) x 2 flops per warp and iteration
+        const double tf = 2.0 * 12.0 * (K16 ? 2048.0 : 1024.0) * iters * (double)blocks * (threads / 32) / (ms * 1e-3) * 1e-12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    *tflops = best;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    return cudaGetLastError();
+}
+
+cudaError_t measure_mma_f16(cudaStream_t st, double* tflops) { return measure_mma_f16_t<true>(st, tflops); }
+cudaError_t measure_mma_f16_k8(cudaStream_t st, double* tflops) { return measure_mma_f16_t<false>(st, tflops); }
+
 }  // namespace fringe
 
 // ---------------------------------------------------------------------------------------------------
@@ -350,5 +422,7 @@ static int prof_run(int device, cudaError_t (*fn)(cudaStream_t, double*), double
 int fringe_prof_fp32_peak(int device, double* tflops) { return prof_run(device, fringe::measure_fp32_peak, tflops); }
 int fringe_prof_block_fma_rate(int device, double tflops[3]) { return prof_run(device, fringe::measure_block_fma, tflops); }
 int fringe_prof_mma_tf32_rate(int device, double* tflops) { return prof_run(device, fringe::measure_mma_tf32, tflops); }
+int fringe_prof_mma_f16_rate(int device, double* tflops) { return prof_run(device, fringe::measure_mma_f16, tflops); }
+int fringe_prof_mma_f16_k8_rate(int device, double* tflops) { return prof_run(device, fringe::measure_mma_f16_k8, tflops); }
 int fringe_prof_fp64_peak(int device, double* tflops) { return prof_run(device, fringe::measure_fp64_peak, tflops); }
 }

@@ -99,7 +99,7 @@ class Context:
         arr = (C.c_int64 * 8)()
         self._check(lib.fringe_evd_stats(self._h, arr))
         return {"pixels": arr[0], "power_iterations": arr[1], "fp64_pixels": arr[2], "capped": arr[3],
-                "factorisations": arr[4]}
+                "factorisations": arr[4], "fp32_recomputed": arr[5]}
 
     def force_generic(self, on: bool) -> None:
         """Profiling / A-B tests only: send evd calls to the generic any-N kernel."""

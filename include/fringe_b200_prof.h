@@ -34,7 +34,8 @@ int fringe_last_kernel_ms(fringe_ctx* ctx, int kernel, float* ms);
 /* Per-pixel solver statistics of the most recent evd call on this context:
  * stats[0] pixels solved, [1] FP32 power iterations (EVD) or inverse-iteration solves (MLE),
  * [2] pixels that took the FP64 path, [3] pixels that hit an iteration cap or took the certified
- * fall-back, [4] Cholesky factorisations of the MLE eigen solver and its gates, [5..7] spare.
+ * fall-back, [4] Cholesky factorisations of the MLE eigen solver and its gates, [5] pixels of the tensor-pipe EVD
+ * kernel whose Gram product was recomputed on FP32 FMAs (a sample outside the FP16 range), [6..7] spare.
  * Synchronises the device. */
 int fringe_evd_stats(fringe_ctx* ctx, int64_t stats[8]);
 /* Per-phase warp cycles of the most recent tensor-pipe evd launch (summed over warps):
@@ -59,6 +60,10 @@ int fringe_prof_block_fma_rate(int device, double tflops[3]);
 /* Dense TF32 TFLOP/s of the warp-level mma.sync.m16n8k8 path (12 independent accumulator tiles per
  * warp). */
 int fringe_prof_mma_tf32_rate(int device, double* tflops);
+/* The same on mma.sync.m16n8k16 FP16 with FP32 accumulate (the two-term FP16 split of the Gram product). */
+int fringe_prof_mma_f16_rate(int device, double* tflops);
+/* ... and on mma.sync.m16n8k8 FP16 (half the k extent per instruction; the Gram kernel's shape). */
+int fringe_prof_mma_f16_k8_rate(int device, double* tflops);
 /* FP64 FMA throughput (register-resident DFMA loop): denominator for the MLE kernel. */
 int fringe_prof_fp64_peak(int device, double* tflops);
 

@@ -251,3 +251,25 @@ def test_band_that_is_zero_over_a_whole_window(ctx, oracle_lib, bands, method, v
         assert (ref[1] == -1.0).sum() > 50, np.unique(ref[1][ref[1] < 0], return_counts=True)
         assert np.array_equal(ref[1] == -1.0, gpu[1] == -1.0)
     _compare(ref, gpu, borderline=3, weak_components=3 if method == "STBAS" else 0)
+
+
+def test_samples_outside_the_fp16_range_take_the_fp32_recomputation(ctx, oracle_lib):
+    """The tensor-pipe kernel works on band-scaled FP16 hi/lo parts; a neighbourhood holding a sample that leaves that
+    range (a scatterer 130 dB above the scene, or a patch 180 dB below it) is recomputed from the original planes.  Full
+    windows as SHP masks so that every pixel around the odd samples is affected."""
+    from fringe_b200.engine import nulong
+    bands, lines, cols, Nx, Ny = 30, 40, 64, 5, 2
+    slc = synth.make_stack(bands, lines, cols, seed=77, region=32, zero_fraction=0.0)
+    slc[:, 9, 20] *= np.float32(3.0e6)                      # one very bright pixel
+    slc[:, 24:36, 40:56] *= np.float32(1.0e-9)              # a very dark patch
+    slc[3, 30, 45] = 0                                      # with a hole
+    W = (2 * Nx + 1) * (2 * Ny + 1)
+    nu = nulong(Nx, Ny)
+    bits = np.zeros(nu * 32, np.uint8); bits[:W] = 1
+    words = np.packbits(bits.reshape(nu, 32)[:, ::-1], axis=1).view(">u4").astype(np.uint32).reshape(nu)
+    wts = np.broadcast_to(words, (lines, cols, nu)).copy()
+    ref = oracle_lib.evd_block(slc, wts, Nx, Ny, method=0)
+    gpu = ctx.evd_block(slc, wts, Nx, Ny, method="EVD")
+    _compare(ref, gpu)
+    stats = ctx.evd_stats()
+    assert stats["fp32_recomputed"] >= (2 * Ny + 1) * (2 * Nx + 1) + 12 * 16, stats
