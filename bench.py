@@ -327,8 +327,16 @@ def main():
         except Exception:
             pass
     bytes_px = 16 * BANDS + 4 * nu + 12
-    # DRAM traffic of the dominant kernel: ncu --set full captures under profiles/ (bytes per pixel of that launch, scaled)
-    traffic_px = {"c2": 1012.0}.get(args.config)
+    # DRAM traffic of the dominant kernel: dram__bytes_read + dram__bytes_write of its launch in the committed ncu --set full
+    # capture of this config (profiles/r2_traffic_<config>.json, written by scripts/ncu_traffic.py), scaled by pixels
+    traffic_px, traffic_src = None, None
+    tfile = os.path.join(ROOT, "profiles", f"r2_traffic_{args.config}.json")
+    if os.path.exists(tfile):
+        try:
+            tj = json.load(open(tfile))
+            traffic_px, traffic_src = float(tj["bytes_per_pixel"]), f"profiles/{os.path.basename(tfile)} ({tj['kernel']}, {tj['pixels']} px captured)"
+        except Exception:
+            pass
     roofline = {"kernel": kernel, "bound": "fp64" if is_dp else "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak if peak > 0 else None,
                 "peak_source": ("FP64" if is_dp else "FP32") + " FMA microbenchmark run inside this bench (libfringe_b200_prof.so); "
@@ -342,8 +350,8 @@ def main():
                 "solver": {"iterations_per_pixel": stats["power_iterations"] / max(stats["pixels"], 1),
                            "factorisations_per_pixel": stats["factorisations"] / max(stats["pixels"], 1)},
                 "traffic": traffic_px * my_pixels if traffic_px else None,
-                "traffic_note": "DRAM bytes per launch from the ncu --set full capture of a 100-line launch of this kernel "
-                                "(profiles/), scaled by pixels; null where no capture of this config exists"}
+                "traffic_note": ("DRAM bytes (read + write) per launch: bytes per pixel of the ncu --set full capture in " + traffic_src +
+                                 ", times the pixels of this launch") if traffic_src else "no ncu capture of this config under profiles/"}
 
     # ---- end to end through the host C ABI --------------------------------------------------
     e2e = None

@@ -341,7 +341,7 @@ int nmap_prepare(fringe_ctx* ctx, int cols, int lines, int bands, int Nx, int Ny
             ctx->adtab_bands = bands;
         }
     }
-    CU(ctx->amp.ensure(npix * bands * sizeof(float)));
+    CU(ctx->amp.ensure((size_t)fringe::nmap_amp_pitch(cols) * lines * bands * sizeof(float)));
     CU(ctx->valid.ensure(npix));
     return FRINGE_OK;
 }
@@ -519,7 +519,7 @@ void nmapProcessBlock(float* amp, unsigned char* msk, int cols, int lines, int b
     cu(cudaMemcpyAsync(ctx->in_slc.p, amp, npix * bands * sizeof(float), cudaMemcpyHostToDevice, st), "upload amp");
     cu(cudaMemcpyAsync(ctx->in_mask.p, msk, npix, cudaMemcpyHostToDevice, st), "upload mask");
     cu(cudaMemsetAsync(ctx->o_wts.p, 0, npix * wtslen * sizeof(uint32_t), st), "clear wts");
-    cu(fringe::launch_amp_in_sort((const float*)ctx->in_slc.p, (const uint8_t*)ctx->in_mask.p, (long)npix, bands,
+    cu(fringe::launch_amp_in_sort((const float*)ctx->in_slc.p, (const uint8_t*)ctx->in_mask.p, cols, lines, bands,
                                   (float*)ctx->amp.p, (uint8_t*)ctx->valid.p, st), "sort");
     cu(fringe::launch_nmap((const float*)ctx->amp.p, (const uint8_t*)ctx->valid.p, cols, lines, bands, Nx, Ny, FRINGE_NMAP_KS2,
                            plan.kcrit, plan.scrit, (const double*)ctx->adtab.p, plan.g, (int32_t*)ctx->o_count.p,

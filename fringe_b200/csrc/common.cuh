@@ -6,8 +6,8 @@
 namespace fringe {
 
 // ---- nmap_kernels.cu ------------------------------------------------------------------
-// amp   : float [bands][npix]  ascending per valid pixel (rank-major so that the window tile
-//         of one rank is a set of contiguous row segments)
+// amp   : float [bands][lines][nmap_amp_pitch(cols)]  ascending per valid pixel, all zero for invalid ones (rank-major:
+//         the window tile of one rank is one TMA box of the 3-D tensor; rows padded to whole 16-byte units)
 // valid : uint8 [npix]
 // rows [row0, row0+nrows) of the block are processed (plane stride stays lines*cols)
 cudaError_t launch_amp_sort(const float2* slc, const uint8_t* mask, const double* alpha, int cols,
@@ -15,11 +15,13 @@ cudaError_t launch_amp_sort(const float2* slc, const uint8_t* mask, const double
                             cudaStream_t st);
 
 // the same from amplitudes handed over pixel-major [pixel][band] with the reference's validity mask (nmapProcessBlock)
-cudaError_t launch_amp_in_sort(const float* amp_in, const uint8_t* msk, long npix, int bands, float* amp, uint8_t* valid,
-                               cudaStream_t st);
+cudaError_t launch_amp_in_sort(const float* amp_in, const uint8_t* msk, int cols, int lines, int bands, float* amp,
+                               uint8_t* valid, cudaStream_t st);
+int nmap_amp_pitch(int cols);
 
 struct NmapGeometry {
     int tile_w, tile_h;      // output pixels per CTA (0 x 0: the global-memory kernel, no tile fits)
+    int plane_stride;        // words between the rank planes of the staged tile (one of the instantiated strides)
     size_t smem_bytes;
     bool table_in_smem;      // AD2 term table staged in shared memory
 };

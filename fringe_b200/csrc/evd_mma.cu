@@ -69,6 +69,11 @@ __device__ __forceinline__ float fast_rcp(float x) {
 // measured 210 ms per 30 M pixels against 199 ms for this one.)
 constexpr int CHUNK = 8;
 
+// warps per CTA (one CTA per SM).  16 leaves 128 registers per thread; 20 would leave 96 and spills ~100 bytes per thread
+#ifndef FRINGE_MMA_WARPS
+#define FRINGE_MMA_WARPS 16
+#endif
+
 // D(16x8) += A(16x16, row) * B(16x8, col), FP16 inputs, FP32 accumulate
 __device__ __forceinline__ void mma_f16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                         uint32_t b0, uint32_t b1) {
@@ -130,7 +135,7 @@ __device__ __forceinline__ void mma_chunk(float (&cre)[6][4], float (&cim)[6][4]
 
 template <int NE>
 struct MmaCfg {
-    static constexpr int WARPS = 16;                    // one CTA per SM: its warps share one moving window in L1
+    static constexpr int WARPS = FRINGE_MMA_WARPS;      // one CTA per SM: its warps share one moving window in L1
     static constexpr int BAND = 4;                      // rows of a CTA's pixel band
     // coherence matrix in shared memory: real and imaginary planes, rows NS floats apart;
     // NS = 4 (mod 8) keeps rows 16-byte aligned and spreads the hand-off stores over the banks
@@ -263,7 +268,7 @@ cudaError_t launch_transpose_mma(const float2* slc, long npix, long first, long 
 
 // ---------------------------------------------------------------------------------------
 template <int NE>
-__global__ void __launch_bounds__(512, 1) k_evd_mma(const EvdArgs a) {
+__global__ void __launch_bounds__(FRINGE_MMA_WARPS * 32, 1) k_evd_mma(const EvdArgs a) {
     typedef MmaCfg<NE> Cfg;
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

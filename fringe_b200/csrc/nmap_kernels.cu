@@ -9,9 +9,12 @@
 //   k_amp_sort   one thread per pixel; the N amplitudes of a pixel live in a shared-memory
 //                column (bank = thread), are insertion-sorted there and written rank-major
 //                ([rank][pixel]) so later tile loads are contiguous row segments.
-//   k_nmap<M>    one CTA per tile of pixels; the sorted vectors of tile + forward halo are
-//                staged in shared memory once as integer keys; one thread per pixel walks the
-//                forward half of its window.
+//   k_nmap<M,PS> one CTA per tile of pixels; the sorted vectors of tile + forward halo are staged in
+//                shared memory by TMA: one cp.async.bulk.tensor box (tile + halo, one rank) per rank
+//                from the 3-D tensor [rank][line][column] into planes PS words apart, all arriving on
+//                one mbarrier; out-of-image parts of a box are zero-filled by the copy engine, and a
+//                zero top rank *is* the validity flag (k_amp_sort writes zeros for invalid pixels).
+//                One thread per pixel then walks the forward half of its window on integer keys.
 //                KS2: the p-value threshold is turned into an integer bound k on
 //                     max_v |#{a<=v} - #{b<=v}| on the host (fringe_ks2_critical_count); that
 //                     bound holds iff b[i-k] <= a[i] and a[i-k] <= b[i] for all i >= k, so the
@@ -24,6 +27,7 @@
 //   Each unordered pair is tested once (forward half-plane, as nmap.cpp:404-409) and sets both
 //   pixels' bits with atomic ORs into a pre-zeroed mask: order-independent, hence deterministic
 //   and equal to the race-free reading of the reference loop; counts = popcounts (k_count).
+#include <cuda.h>
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -39,7 +43,7 @@ namespace fringe {
 __global__ void __launch_bounds__(128) k_amp_sort(const float2* __restrict__ slc,
                                                   const uint8_t* __restrict__ mask,
                                                   const double* __restrict__ alpha, long npix,
-                                                  long p0, long pcount,
+                                                  long p0, long pcount, int cols, int apitch, long aplane,
                                                   int bands, float* __restrict__ amp,
                                                   uint8_t* __restrict__ valid) {
     extern __shared__ float s_col[];   // [bands][blockDim.x]
@@ -72,8 +76,88 @@ __global__ void __launch_bounds__(128) k_amp_sort(const float2* __restrict__ slc
             s_col[(j + 1) * nt + tid] = key;
         }
     }
-    for (int b = 0; b < bands; ++b) amp[(long)b * npix + p] = ok ? s_col[b * nt + tid] : 0.f;
+    const long ap = (p / cols) * apitch + (p % cols);     // rows of the rank planes are apitch floats apart (TMA: 16-byte rows)
+    for (int b = 0; b < bands; ++b) amp[(long)b * aplane + ap] = ok ? s_col[b * nt + tid] : 0.f;
     valid[p] = ok ? 1 : 0;
+}
+
+// Batcher's odd-even merge sort as a compare-exchange network on NB register-resident keys (NB a power of two): every
+// index is a compile-time constant after unrolling, so the keys never leave the registers, there is no divergence and no
+// shared memory.  191 exchanges (two integer min / max each) for NB = 32, where the insertion sort above executes ~7 000
+// instructions per pixel with two thirds of the lanes active.  Amplitudes of a valid pixel are positive and NaN-free, so
+// their bit patterns order like unsigned integers; unused slots hold 0xFFFFFFFF and stay at the top.
+template <int NB>
+__device__ __forceinline__ void sort_network(uint32_t (&v)[NB]) {
+#pragma unroll
+    for (int p = 1; p < NB; p *= 2)
+#pragma unroll
+        for (int k = p; k >= 1; k /= 2)
+#pragma unroll
+            for (int j = k % p; j <= NB - 1 - k; j += 2 * k)
+#pragma unroll
+                for (int i = 0; i <= (k - 1 < NB - j - k - 1 ? k - 1 : NB - j - k - 1); ++i)
+                    if ((i + j) / (2 * p) == (i + j + k) / (2 * p)) {
+                        const uint32_t lo = min(v[i + j], v[i + j + k]), hi = max(v[i + j], v[i + j + k]);
+                        v[i + j] = lo; v[i + j + k] = hi;
+                    }
+}
+
+// amplitude + validity + sort for bands <= NB: one thread per pixel, everything in registers.  PIXEL_MAJOR: the
+// amplitudes are handed over as [pixel][band] floats with the reference's validity mask (nmapProcessBlock).
+template <int NB, bool PIXEL_MAJOR>
+__global__ void __launch_bounds__(128) k_amp_sort_net(const float2* __restrict__ slc, const float* __restrict__ amp_in,
+                                                      const uint8_t* __restrict__ mask, const double* __restrict__ alpha,
+                                                      long npix, long p0, long pcount, int cols, int apitch, long aplane,
+                                                      int bands, float* __restrict__ amp, uint8_t* __restrict__ valid) {
+    const long p = p0 + (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= p0 + pcount) return;
+    bool ok = mask ? (mask[p] != 0) : true;
+    uint32_t v[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        v[b] = 0xFFFFFFFFu;
+        if (b < bands) {
+            float x;
+            if (PIXEL_MAJOR) {
+                x = amp_in[p * bands + b];
+            } else {
+                const float2 z = __ldg(&slc[(long)b * npix + p]);
+                float h;
+                if (isinf(z.x) || isinf(z.y)) h = CUDART_INF_F;
+                else h = (float)__dsqrt_rn(__dadd_rn(__dmul_rn((double)z.x, (double)z.x), __dmul_rn((double)z.y, (double)z.y)));
+                // no calibration constants: (float)((double)h / 1.0) == h, skip the double division
+                x = alpha ? (float)__ddiv_rn((double)h, alpha[b]) : h;
+                ok = ok && (x != 0.f) && !isnan(x);
+            }
+            v[b] = __float_as_uint(x);
+        }
+    }
+    if (ok) sort_network<NB>(v);
+    const long ap = (p / cols) * apitch + (p % cols);
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+        if (b < bands) amp[(long)b * aplane + ap] = ok ? __uint_as_float(v[b]) : 0.f;
+    valid[p] = ok ? 1 : 0;
+}
+
+template <bool PIXEL_MAJOR>
+static bool launch_sort_net(const float2* slc, const float* amp_in, const uint8_t* mask, const double* alpha, long npix, long p0,
+                            long pcount, int cols, int lines, int bands, float* amp, uint8_t* valid, cudaStream_t st) {
+    const int apitch = nmap_amp_pitch(cols);
+    const long aplane = (long)apitch * lines;
+    const unsigned nblk = (unsigned)((pcount + 127) / 128);
+#define FRINGE_SORT_CASE(NB_)                                                                                              \
+    if (bands <= NB_) {                                                                                                    \
+        k_amp_sort_net<NB_, PIXEL_MAJOR><<<nblk, 128, 0, st>>>(slc, amp_in, mask, alpha, npix, p0, pcount, cols, apitch, aplane, \
+                                                              bands, amp, valid);                                          \
+        return true;                                                                                                       \
+    }
+    FRINGE_SORT_CASE(8)
+    FRINGE_SORT_CASE(16)
+    FRINGE_SORT_CASE(32)
+    FRINGE_SORT_CASE(64)
+#undef FRINGE_SORT_CASE
+    return false;                       // more than 64 bands: the shared-memory insertion sort
 }
 
 cudaError_t launch_amp_sort(const float2* slc, const uint8_t* mask, const double* alpha, int cols,
@@ -82,13 +166,15 @@ cudaError_t launch_amp_sort(const float2* slc, const uint8_t* mask, const double
     const long npix = (long)cols * lines;
     const long p0 = (long)row0 * cols, pcount = (long)nrows * cols;
     if (pcount <= 0) return cudaSuccess;
+    if (launch_sort_net<false>(slc, nullptr, mask, alpha, npix, p0, pcount, cols, lines, bands, amp, valid, st)) return cudaGetLastError();
     int nt = 128;
     while (nt > 32 && (size_t)nt * bands * sizeof(float) > 160 * 1024) nt >>= 1;
     const size_t smem = (size_t)nt * bands * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(k_amp_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     const long nblk = (pcount + nt - 1) / nt;
-    k_amp_sort<<<(unsigned)nblk, nt, smem, st>>>(slc, mask, alpha, npix, p0, pcount, bands, amp, valid);
+    const int apitch = nmap_amp_pitch(cols);
+    k_amp_sort<<<(unsigned)nblk, nt, smem, st>>>(slc, mask, alpha, npix, p0, pcount, cols, apitch, (long)apitch * lines, bands, amp, valid);
     return cudaGetLastError();
 }
 
@@ -96,8 +182,8 @@ cudaError_t launch_amp_sort(const float2* slc, const uint8_t* mask, const double
 // as nmapProcessBlock receives them (src/nmap/nmap_cuda.h:13-17, runSortAmp nmap_cuda.cu:243-255): same
 // shared-memory insertion sort, output rank-major like k_amp_sort.  msk is the reference's zeromask.
 __global__ void __launch_bounds__(128) k_amp_in_sort(const float* __restrict__ amp_in, const uint8_t* __restrict__ msk,
-                                                     long npix, int bands, float* __restrict__ amp,
-                                                     uint8_t* __restrict__ valid) {
+                                                     long npix, int cols, int apitch, long aplane, int bands,
+                                                     float* __restrict__ amp, uint8_t* __restrict__ valid) {
     extern __shared__ float s_col[];   // [bands][blockDim.x]
     const int tid = threadIdx.x, nt = blockDim.x;
     const long p = (long)blockIdx.x * nt + tid;
@@ -117,18 +203,23 @@ __global__ void __launch_bounds__(128) k_amp_in_sort(const float* __restrict__ a
             s_col[(j + 1) * nt + tid] = key;
         }
     }
-    for (int b = 0; b < bands; ++b) amp[(long)b * npix + p] = ok ? s_col[b * nt + tid] : 0.f;
+    const long ap = (p / cols) * apitch + (p % cols);
+    for (int b = 0; b < bands; ++b) amp[(long)b * aplane + ap] = ok ? s_col[b * nt + tid] : 0.f;
     valid[p] = ok ? 1 : 0;
 }
 
-cudaError_t launch_amp_in_sort(const float* amp_in, const uint8_t* msk, long npix, int bands, float* amp, uint8_t* valid,
+cudaError_t launch_amp_in_sort(const float* amp_in, const uint8_t* msk, int cols, int lines, int bands, float* amp, uint8_t* valid,
                                cudaStream_t st) {
+    const long npix = (long)cols * lines;
+    const int apitch = nmap_amp_pitch(cols);
     if (npix <= 0) return cudaSuccess;
+    if (launch_sort_net<true>(nullptr, amp_in, msk, nullptr, npix, 0, npix, cols, lines, bands, amp, valid, st)) return cudaGetLastError();
     int nt = 128;
     while (nt > 32 && (size_t)nt * bands * sizeof(float) > 160 * 1024) nt >>= 1;
     cudaError_t e = cudaFuncSetAttribute(k_amp_in_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    k_amp_in_sort<<<(unsigned)((npix + nt - 1) / nt), nt, (size_t)nt * bands * sizeof(float), st>>>(amp_in, msk, npix, bands, amp, valid);
+    k_amp_in_sort<<<(unsigned)((npix + nt - 1) / nt), nt, (size_t)nt * bands * sizeof(float), st>>>(amp_in, msk, npix, cols, apitch,
+                                                                                                  (long)apitch * lines, bands, amp, valid);
     return cudaGetLastError();
 }
 
@@ -139,6 +230,7 @@ struct NmapKernelArgs {
     const float* amp;
     const uint8_t* valid;
     int cols, lines, bands, Nx, Ny, nulong;
+    int apitch;               // floats between rows of a rank plane of amp
     int row0, row1;           // output rows [row0, row1) of the block are produced by this launch
     int kcrit;
     double scrit;
@@ -162,12 +254,15 @@ struct NmapKernelArgs {
 // (the binding v is a[i] itself; for tied a's the last of them is the binding index and the
 // earlier ones are weaker), and the mirrored inequality gives a[i - k] <= b[i].  So the pair is
 // accepted iff  b[i-k] <= a[i] and a[i-k] <= b[i]  for every i in [k, n): 2 (n - k) integer
-// compares on keys each pixel keeps contiguously ([pixel][rank], odd stride), instead of a 2n-step
-// merge.  pa / pb point at rank 0 of the two pixels.
+// compares instead of a 2n-step merge.  Keys are rank-major with a compile-time plane stride PS
+// ([rank][region pixel], as the TMA boxes land), so rank i of a pixel is an immediate offset from
+// the pixel's rank-0 address and the lanes of a warp (consecutive pixels) never collide on a bank.
+// pa / pb point at rank 0 of the two pixels.
+template <int PS>
 __device__ __forceinline__ bool ks_within(const uint32_t* __restrict__ pa, const uint32_t* __restrict__ pb,
                                           int n, int k) {
-    const uint32_t* __restrict__ ah = pa + k;
-    const uint32_t* __restrict__ bh = pb + k;
+    const uint32_t* __restrict__ ah = pa + k * PS;
+    const uint32_t* __restrict__ bh = pb + k * PS;
     const int m = n - k;
     bool bad = false;                     // no short circuit: all loads of a step issue together
     int i = 0;
@@ -175,11 +270,12 @@ __device__ __forceinline__ bool ks_within(const uint32_t* __restrict__ pa, const
     for (; i + 4 <= m; i += 4) {
         uint32_t a_hi[4], a_lo[4], b_hi[4], b_lo[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { a_hi[u] = ah[i + u]; a_lo[u] = pa[i + u]; b_hi[u] = bh[i + u]; b_lo[u] = pb[i + u]; }
+        for (int u = 0; u < 4; ++u) { a_hi[u] = ah[u * PS]; a_lo[u] = pa[u * PS]; b_hi[u] = bh[u * PS]; b_lo[u] = pb[u * PS]; }
 #pragma unroll
         for (int u = 0; u < 4; ++u) bad |= (b_lo[u] > a_hi[u]) | (a_lo[u] > b_hi[u]);
+        ah += 4 * PS; bh += 4 * PS; pa += 4 * PS; pb += 4 * PS;
     }
-    for (; i < m; ++i) bad |= (pb[i] > ah[i]) | (pa[i] > bh[i]);
+    for (; i < m; ++i) { bad |= (pb[0] > ah[0]) | (pa[0] > bh[0]); ah += PS; bh += PS; pa += PS; pb += PS; }
     return !bad;
 }
 
@@ -207,50 +303,74 @@ __device__ __forceinline__ double ad_inner_sum(const uint32_t* __restrict__ s_ke
     return S;
 }
 
+// ---- TMA / mbarrier (sm_90+ PTX) --------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");      // visible to the async proxy
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one box of the 3-D tensor (x = column, y = line, z = rank) into shared memory; completion counted on bar
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
 // Forward half-plane pair tests (nmap.cpp:404-473): the thread of pixel p tests the neighbours q
 // that follow it in raster order inside the window; an accepted pair sets bit (dy,dx) of p and
 // bit (-dy,-dx) of q, exactly like the reference's symmetric update, but with atomic ORs into the
 // (pre-zeroed) global mask so the result does not depend on scheduling.  Neighbour counts are
 // the popcounts of the finished masks (k_count).
-template <int METHOD>
-__global__ void k_nmap(const NmapKernelArgs a) {
-    extern __shared__ __align__(16) unsigned char s_raw[];
+// PS = words between the rank planes in shared memory (>= region pixels, a multiple of 32).
+template <int METHOD, int PS>
+__global__ void k_nmap(const NmapKernelArgs a, const __grid_constant__ CUtensorMap amp_map) {
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    __shared__ __align__(8) uint64_t s_bar;
     const int N = a.bands, Nx = a.Nx, Ny = a.Ny;
     const int TW = blockDim.x, TH = blockDim.y;
-    const int RW = TW + 2 * Nx, RH = TH + Ny, RP = RW * RH;       // tile + forward halo
+    const int RW = (TW + 2 * Nx + 3) & ~3, RH = TH + Ny;         // tile + forward halo; box rows are whole 16-byte units
     const int tid = threadIdx.y * TW + threadIdx.x, nthr = TW * TH;
-    const long npix = (long)a.cols * a.lines;
 
-    // carve: [double table (optional)] [uint32 keys (N+1)*RP] [uint8 valid RP]
-    // key layout: AD2 [rank][region pixel] + sentinel rank; KS2 [region pixel][rank], odd stride KS
-    double* s_tab = reinterpret_cast<double*>(s_raw);
+    // carve: [uint32 keys (N+1) planes of PS words] [double table (optional)]
+    uint32_t* s_key = reinterpret_cast<uint32_t*>(s_raw);
+    double* s_tab = reinterpret_cast<double*>(s_key + (size_t)(N + 1) * PS);
     const int tab_elems = (METHOD == 1 && a.table_in_smem) ? (2 * N - 1) * (N + 1) : 0;
-    uint32_t* s_key = reinterpret_cast<uint32_t*>(s_tab + tab_elems);
-    uint8_t* s_valid = reinterpret_cast<uint8_t*>(s_key + (size_t)(N + 1) * RP);
-    const int KS = N | 1;
 
-    const int x0 = blockIdx.x * TW - Nx, y0 = a.row0 + blockIdx.y * TH;
-    for (int rp = tid; rp < RP; rp += nthr) {
-        const int gy = y0 + rp / RW, gx = x0 + rp % RW;
-        const bool inb = (gy < a.lines) && (gx >= 0) && (gx < a.cols);
-        s_valid[rp] = inb ? a.valid[(long)gy * a.cols + gx] : 0;
-        if (METHOD == 1) s_key[(size_t)N * RP + rp] = 0xFFFFFFFFu;
+    // A box must start on a 16-byte boundary of its row (measured: an unaligned innermost coordinate faults, negative
+    // and out-of-image boxes are fine and come back zero-filled -- scripts/probes/tma_probe.cu), so the tile grid is
+    // shifted left by (-Nx) mod 4 columns: tile origin - Nx is then a multiple of 4 for every CTA.
+    const int xshift = (4 - (Nx & 3)) & 3;
+    const int x0 = blockIdx.x * TW - xshift - Nx, y0 = a.row0 + blockIdx.y * TH;
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&s_bar, (uint32_t)(N * RW * RH * (int)sizeof(float)));
+        for (int k = 0; k < N; ++k) tma_load_3d(s_key + (size_t)k * PS, &amp_map, x0, y0, k, &s_bar);
     }
-    for (int idx = tid; idx < N * RP; idx += nthr) {
-        const int k = idx / RP, rp = idx - k * RP;
-        const int gy = y0 + rp / RW, gx = x0 + rp % RW;
-        const bool inb = (gy < a.lines) && (gx >= 0) && (gx < a.cols);
-        const uint32_t key = inb ? __float_as_uint(__ldg(&a.amp[(long)k * npix + (long)gy * a.cols + gx])) : 0u;
-        if (METHOD == 1) s_key[idx] = key;
-        else s_key[rp * KS + k] = key;
-    }
+    // meanwhile: the sentinel rank of the AD2 merge and the term table
+    if (METHOD == 1) for (int rp = tid; rp < RW * RH; rp += nthr) s_key[(size_t)N * PS + rp] = 0xFFFFFFFFu;
     for (int i = tid; i < tab_elems; i += nthr) s_tab[i] = a.ad_table[i];
     __syncthreads();
+    mbar_wait(&s_bar, 0);
 
-    const int gx = blockIdx.x * TW + threadIdx.x, gy = y0 + threadIdx.y;
-    if (gx >= a.cols || gy >= a.row1) return;
+    const int gx = blockIdx.x * TW - xshift + threadIdx.x, gy = y0 + threadIdx.y;
+    if (gx < 0 || gx >= a.cols || gy >= a.row1) return;
     const int rp = threadIdx.y * RW + threadIdx.x + Nx;
-    if (!s_valid[rp]) return;                       // mask words stay zero
+    const uint32_t* s_top = s_key + (size_t)(N - 1) * PS;       // largest amplitude: zero <=> invalid or outside the image
+    if (!s_top[rp]) return;                         // mask words stay zero
     const long p = (long)gy * a.cols + gx;
     uint32_t* wp = a.wts + p * a.nulong;
     const double* T = (METHOD == 1) ? (a.table_in_smem ? s_tab : a.ad_table) : nullptr;
@@ -262,10 +382,10 @@ __global__ void k_nmap(const NmapKernelArgs a) {
         if (dx > Nx) { dx = -Nx; ++dy; }
         if ((f & 31) == 0) { atomicOr(&wp[(f - 1) >> 5], word); word = 0u; }
         const int rq = rp + dy * RW + dx;
-        if (s_valid[rq]) {
+        if (s_top[rq]) {
             bool similar;
-            if (METHOD == 0) similar = (a.kcrit >= 0) && ks_within(s_key + rp * KS, s_key + rq * KS, N, kc);
-            else similar = ad_inner_sum(s_key, rp, rq, N, RP, T) <= a.scrit;
+            if (METHOD == 0) similar = (a.kcrit >= 0) && ks_within<PS>(s_key + rp, s_key + rq, N, kc);
+            else similar = ad_inner_sum(s_key, rp, rq, N, PS, T) <= a.scrit;
             if (similar) {
                 word |= (1u << (f & 31));
                 const int fm = W - 1 - f;               // bit of (-dy,-dx) in q's mask
@@ -284,11 +404,12 @@ __global__ void k_nmap(const NmapKernelArgs a) {
 template <int METHOD>
 __global__ void __launch_bounds__(128) k_nmap_global(const NmapKernelArgs a) {
     const int N = a.bands, Nx = a.Nx, Ny = a.Ny;
-    const long npix = (long)a.cols * a.lines;
+    const long plane = (long)a.apitch * a.lines;
     const int gx = blockIdx.x * blockDim.x + threadIdx.x, gy = a.row0 + blockIdx.y;
     if (gx >= a.cols || gy >= a.row1) return;
     const long p = (long)gy * a.cols + gx;
     if (!a.valid[p]) return;
+    const long pa = (long)gy * a.apitch + gx;
     const uint32_t* __restrict__ key = reinterpret_cast<const uint32_t*>(a.amp);
     uint32_t* wp = a.wts + p * a.nulong;
     const int WX = 2 * Nx + 1, W = WX * (2 * Ny + 1), center = Ny * WX + Nx;
@@ -301,26 +422,27 @@ __global__ void __launch_bounds__(128) k_nmap_global(const NmapKernelArgs a) {
         const int qy = gy + dy, qx = gx + dx;
         if (qy < a.lines && qx >= 0 && qx < a.cols) {
             const long q = (long)qy * a.cols + qx;
+            const long qa = (long)qy * a.apitch + qx;
             if (a.valid[q]) {
                 bool similar;
                 if (METHOD == 0) {
                     bool bad = a.kcrit < 0;
                     for (int i = kc; i < N && !bad; ++i) {
-                        const uint32_t a_hi = __ldg(&key[(long)i * npix + p]), a_lo = __ldg(&key[(long)(i - kc) * npix + p]);
-                        const uint32_t b_hi = __ldg(&key[(long)i * npix + q]), b_lo = __ldg(&key[(long)(i - kc) * npix + q]);
+                        const uint32_t a_hi = __ldg(&key[(long)i * plane + pa]), a_lo = __ldg(&key[(long)(i - kc) * plane + pa]);
+                        const uint32_t b_hi = __ldg(&key[(long)i * plane + qa]), b_lo = __ldg(&key[(long)(i - kc) * plane + qa]);
                         bad = (b_lo > a_hi) | (a_lo > b_hi);
                     }
                     similar = !bad;
                 } else {
                     // AD2unique.hpp:211-303 merge (ties: the element of B first), table sum in the reference's order
                     int ia = 0, ib = 0, m2 = 0;
-                    uint32_t va = __ldg(&key[p]), vb = __ldg(&key[q]);
+                    uint32_t va = __ldg(&key[pa]), vb = __ldg(&key[qa]);
                     double S = 0.0;
                     const double* Tj = a.ad_table;
                     for (int j = 0; j < 2 * N - 1; ++j) {
                         const bool ta = (ib >= N) || (ia < N && va < vb);
-                        if (ta) { ++ia; ++m2; va = (ia < N) ? __ldg(&key[(long)ia * npix + p]) : 0xFFFFFFFFu; }
-                        else { ++ib; --m2; vb = (ib < N) ? __ldg(&key[(long)ib * npix + q]) : 0xFFFFFFFFu; }
+                        if (ta) { ++ia; ++m2; va = (ia < N) ? __ldg(&key[(long)ia * plane + pa]) : 0xFFFFFFFFu; }
+                        else { ++ib; --m2; vb = (ib < N) ? __ldg(&key[(long)ib * plane + qa]) : 0xFFFFFFFFu; }
                         S = __dadd_rn(S, Tj[abs(m2)]);
                         Tj += N + 1;
                     }
@@ -349,9 +471,14 @@ __global__ void __launch_bounds__(256) k_count(const uint32_t* __restrict__ wts,
     count[p] = c;
 }
 
-static size_t nmap_smem(int bands, int Nx, int Ny, int tw, int th, bool table) {
-    const size_t RP = (size_t)(tw + 2 * Nx) * (th + Ny);
-    size_t b = (size_t)(bands + 1) * RP * sizeof(float) + RP;
+// rows of the rank planes of amp are padded to whole 16-byte units (a TMA tensor map needs 16-byte strides)
+int nmap_amp_pitch(int cols) { return (cols + 3) & ~3; }
+
+// shared-memory plane strides (words) the staged kernel is instantiated for
+static const int kPlaneStrides[] = {448, 704, 960, 1984};
+
+static size_t nmap_smem(int bands, int ps, bool table) {
+    size_t b = (size_t)(bands + 1) * ps * sizeof(uint32_t);
     if (table) b += (size_t)(2 * bands - 1) * (bands + 1) * sizeof(double);
     return (b + 15) & ~(size_t)15;
 }
@@ -361,18 +488,63 @@ bool nmap_plan(int bands, int Nx, int Ny, int method, NmapGeometry* g) {
     const size_t tab = (size_t)(2 * bands - 1) * (bands + 1) * sizeof(double);
     static const int shapes[][2] = {{32, 8}, {32, 4}, {32, 2}, {32, 1}, {16, 2}, {16, 1}, {8, 1}};
     for (auto& s : shapes) {
+        const int rw = (s[0] + 2 * Nx + 3) & ~3, rh = s[1] + Ny;
+        if (rw > 256 || rh > 256) continue;                       // TMA box limits
+        int ps = 0;
+        for (int c : kPlaneStrides) if (rw * rh <= c) { ps = c; break; }
+        if (!ps) continue;
         for (int t = (method == 1 ? 1 : 0); t >= 0; --t) {
             const bool table = (t == 1) && tab <= 64 * 1024;
-            const size_t need = nmap_smem(bands, Nx, Ny, s[0], s[1], table);
+            const size_t need = nmap_smem(bands, ps, table);
             if (need <= budget) {
-                g->tile_w = s[0]; g->tile_h = s[1]; g->smem_bytes = need; g->table_in_smem = table;
+                g->tile_w = s[0]; g->tile_h = s[1]; g->plane_stride = ps; g->smem_bytes = need; g->table_in_smem = table;
                 return true;
             }
         }
     }
     // no tile fits: the global-memory kernel (tile_w = 0 marks it)
-    g->tile_w = 0; g->tile_h = 0; g->smem_bytes = 0; g->table_in_smem = false;
+    g->tile_w = 0; g->tile_h = 0; g->plane_stride = 0; g->smem_bytes = 0; g->table_in_smem = false;
     return true;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// amp as a 3-D tensor (column, line, rank) of 32-bit keys; one box = tile + halo of one rank
+static cudaError_t make_amp_map(const float* amp, int cols, int lines, int bands, int box_w, int box_h, CUtensorMap* map) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return cudaErrorNotSupported;
+    const cuuint64_t pitch = (cuuint64_t)nmap_amp_pitch(cols);
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)lines, (cuuint64_t)bands};
+    const cuuint64_t strides[2] = {pitch * sizeof(float), pitch * (cuuint64_t)lines * sizeof(float)};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<float*>(amp), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+template <int METHOD, int PS>
+static cudaError_t launch_nmap_staged(const NmapKernelArgs& a, const CUtensorMap& map, dim3 grid, dim3 block, size_t smem,
+                                      cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(k_nmap<METHOD, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_nmap<METHOD, PS><<<grid, block, smem, st>>>(a, map);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_nmap(const float* amp, const uint8_t* valid, int cols, int lines, int bands,
@@ -384,27 +556,33 @@ cudaError_t launch_nmap(const float* amp, const uint8_t* valid, int cols, int li
     a.row0 = row0; a.row1 = row0 + nrows;
     a.amp = amp; a.valid = valid; a.cols = cols; a.lines = lines; a.bands = bands;
     a.Nx = Nx; a.Ny = Ny; a.nulong = ((2 * Ny + 1) * (2 * Nx + 1) + 31) / 32;
+    a.apitch = nmap_amp_pitch(cols);
     a.kcrit = kcrit; a.scrit = scrit; a.ad_table = ad_table; a.table_in_smem = g.table_in_smem ? 1 : 0;
     a.count = count; a.wts = wts;
-    cudaError_t e;
     if (g.tile_w == 0) {                                   // tile does not fit shared memory
         dim3 gblock(128), ggrid((cols + 127) / 128, nrows);
         if (method == 0) k_nmap_global<0><<<ggrid, gblock, 0, st>>>(a);
         else k_nmap_global<1><<<ggrid, gblock, 0, st>>>(a);
         return cudaGetLastError();
     }
+    CUtensorMap map;
+    cudaError_t e = make_amp_map(amp, cols, lines, bands, (g.tile_w + 2 * Nx + 3) & ~3, g.tile_h + Ny, &map);
+    if (e != cudaSuccess) return e;
     dim3 block(g.tile_w, g.tile_h);
-    dim3 grid((cols + g.tile_w - 1) / g.tile_w, (nrows + g.tile_h - 1) / g.tile_h);
-    if (method == 0) {
-        e = cudaFuncSetAttribute(k_nmap<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes);
-        if (e != cudaSuccess) return e;
-        k_nmap<0><<<grid, block, g.smem_bytes, st>>>(a);
-    } else {
-        e = cudaFuncSetAttribute(k_nmap<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes);
-        if (e != cudaSuccess) return e;
-        k_nmap<1><<<grid, block, g.smem_bytes, st>>>(a);
+    const int xshift = (4 - (Nx & 3)) & 3;                  // see k_nmap: tile origins shifted so that boxes start 16-byte aligned
+    dim3 grid((cols + xshift + g.tile_w - 1) / g.tile_w, (nrows + g.tile_h - 1) / g.tile_h);
+#define FRINGE_NMAP_CASE(PS_)                                                                              \
+    case PS_:                                                                                              \
+        return method == 0 ? launch_nmap_staged<0, PS_>(a, map, grid, block, g.smem_bytes, st)              \
+                           : launch_nmap_staged<1, PS_>(a, map, grid, block, g.smem_bytes, st);
+    switch (g.plane_stride) {
+        FRINGE_NMAP_CASE(448)
+        FRINGE_NMAP_CASE(704)
+        FRINGE_NMAP_CASE(960)
+        FRINGE_NMAP_CASE(1984)
     }
-    return cudaGetLastError();
+#undef FRINGE_NMAP_CASE
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_count(const uint32_t* wts, int cols, int nulong, int row0, int nrows, int32_t* count,
