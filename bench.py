@@ -117,6 +117,32 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Bind this process to the CPUs of the NUMA node the GPU hangs off (sysfs), so that the pinned staging buffers of
+    the end-to-end leg are first-touched on that node.  Returns the node number, or None when sysfs does not say or
+    FRINGE_BENCH_NO_NUMA is set (A/B runs)."""
+    if os.environ.get("FRINGE_BENCH_NO_NUMA"):
+        return None
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(index)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def usable_cores() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -356,6 +382,7 @@ def main():
     # ---- end to end through the host C ABI --------------------------------------------------
     e2e = None
     if not args.no_e2e:
+        numa_node = bind_to_gpu_numa_node(local)
         pin = lambda *shape, dtype: torch.empty(shape, dtype=dtype, pin_memory=True)
         h_slc = pin(BANDS, blines, cols, dtype=torch.complex64)
         h_slc.copy_(slc)
@@ -421,6 +448,8 @@ def main():
         del d_a, d_b
         e2e = {"value": total_pixels * args.steps / t_host, "unit": "pixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": t_host * 1e3 / args.steps, "api": api,
+               "pinned_buffers": ("allocated and first touched with the process bound to NUMA node %d (the GPU's)" % numa_node)
+               if numa_node is not None else "allocated where the process ran (no NUMA binding)",
                "host_link": {"gbs_each_way": link_gbs, "note": "pinned copies of %d MB up and down at the same time on every rank, "
                              "max over ranks" % (nb >> 20), "floor_ms_per_step": max(h2d, d2h) / (link_gbs * 1e9) * 1e3}}
 

@@ -6,7 +6,7 @@
 // ENVI rasters with the same names, types, interleave and metadata, return the same error
 // codes.  What differs is where the pixels are computed: every block goes through the C ABI
 // of libfringe_b200.so (fringe_nmap_block / fringe_evd_block) from pinned host buffers, and
-// blocks are dealt to all visible GPUs (one worker thread + context + buffer set per GPU; blocks
+// blocks are dealt to all visible GPUs (two worker threads per GPU, each with its own context + buffer set; blocks
 // are independent, so no inter-GPU traffic).  There is no CPU compute path: if the device
 // library reports an error the driver returns 200 + that status.
 #include <strings.h>
@@ -60,6 +60,10 @@ int block_height(int memsize, int cols, int blocksize, int denom, int rows, int 
     if (h < rows && h <= 2 * Ny) h = std::min(rows, 2 * Ny + blocksize);
     return h;
 }
+
+// Block workers: two per GPU (each with its own context, stream and pinned block), so that one worker's file reads
+// and writes overlap the other's time on the device; the memory budget is shared between all workers.
+int workers_for(int ngpu) { return 2 * ngpu; }
 
 int visible_gpus() {
     int n = 0;
@@ -121,7 +125,7 @@ int nmap_process(nmapOptions* opts) {
     std::cout << "Executing on " << ngpu << " GPU(s)\n";
 
     // every worker (one per GPU) holds its own pinned block: the memory budget is shared between them
-    const int blockysize = block_height(std::max(1, opts->memsize / ngpu), cols, opts->blocksize, 4 * (nbands + 2 + nulong), rows, Ny);
+    const int blockysize = block_height(std::max(1, opts->memsize / workers_for(ngpu)), cols, opts->blocksize, 4 * (nbands + 2 + nulong), rows, Ny);
     std::cout << "Block size = " << blockysize << " lines \n";
     const std::vector<Block> sched = make_schedule(rows, blockysize, Ny);
     std::cout << "Total number of blocks to process: " << sched.size() << "\n";
@@ -201,8 +205,8 @@ int nmap_process(nmapOptions* opts) {
     };
     {
         std::vector<std::thread> th;
-        const int nw = (int)std::min<size_t>(ngpu, sched.size());
-        for (int d = 0; d < nw; ++d) th.emplace_back(worker, d);
+        const int nw = (int)std::min<size_t>(workers_for(ngpu), sched.size());
+        for (int d = 0; d < nw; ++d) th.emplace_back(worker, d % ngpu);
         for (auto& t : th) t.join();
     }
     if (rc != 0) return rc;
@@ -263,7 +267,7 @@ static int evd_driver(evdOptions* opts, int variant) {
     const int ngpu = visible_gpus();
     if (ngpu <= 0) { std::cout << "No CUDA device available and there is no CPU path.\n"; return 200 + FRINGE_ERR_NO_DEVICE; }
 
-    const int blockysize = block_height(std::max(1, opts->memsize / ngpu), cols, opts->blocksize, nbands * 20 + 4 + nulong, rows, Ny);
+    const int blockysize = block_height(std::max(1, opts->memsize / workers_for(ngpu)), cols, opts->blocksize, nbands * 20 + 4 + nulong, rows, Ny);
     std::cout << "Block size = " << blockysize << " lines \n";
     const std::vector<Block> sched = make_schedule(rows, blockysize, Ny);
     std::cout << "Total number of blocks to process: " << sched.size() << "\n";
@@ -341,8 +345,8 @@ static int evd_driver(evdOptions* opts, int variant) {
     };
     {
         std::vector<std::thread> th;
-        const int nw = (int)std::min<size_t>(ngpu, sched.size());
-        for (int d = 0; d < nw; ++d) th.emplace_back(worker, d);
+        const int nw = (int)std::min<size_t>(workers_for(ngpu), sched.size());
+        for (int d = 0; d < nw; ++d) th.emplace_back(worker, d % ngpu);
         for (auto& t : th) t.join();
     }
     if (rc != 0) return rc;
@@ -396,7 +400,7 @@ int despeck_process(despeckOptions* opts) {
     const int ngpu = visible_gpus();
     if (ngpu <= 0) { std::cout << "No CUDA device available and there is no CPU path.\n"; return 200 + FRINGE_ERR_NO_DEVICE; }
 
-    const int blockysize = block_height(std::max(1, opts->memsize / ngpu), cols, opts->blocksize, 4 * (6 + nulong), rows, Ny);   // despeck.cpp:155
+    const int blockysize = block_height(std::max(1, opts->memsize / workers_for(ngpu)), cols, opts->blocksize, 4 * (6 + nulong), rows, Ny);   // despeck.cpp:155
     std::cout << "Block size = " << blockysize << " lines \n";
     const std::vector<Block> sched = make_schedule(rows, blockysize, Ny);
     std::cout << "Total number of blocks to process: " << sched.size() << "\n";
@@ -445,8 +449,8 @@ int despeck_process(despeckOptions* opts) {
     };
     {
         std::vector<std::thread> th;
-        const int nw = (int)std::min<size_t>(ngpu, sched.size());
-        for (int d = 0; d < nw; ++d) th.emplace_back(worker, d);
+        const int nw = (int)std::min<size_t>(workers_for(ngpu), sched.size());
+        for (int d = 0; d < nw; ++d) th.emplace_back(worker, d % ngpu);
         for (auto& t : th) t.join();
     }
     if (rc != 0) return rc;
@@ -540,8 +544,8 @@ int ampdispersion_process(ampdispersionOptions* opts) {
     };
     {
         std::vector<std::thread> th;
-        const int nw = (int)std::min<size_t>(ngpu, sched.size());
-        for (int d = 0; d < nw; ++d) th.emplace_back(worker, d);
+        const int nw = (int)std::min<size_t>(workers_for(ngpu), sched.size());
+        for (int d = 0; d < nw; ++d) th.emplace_back(worker, d % ngpu);
         for (auto& t : th) t.join();
     }
     if (rc != 0) return rc;

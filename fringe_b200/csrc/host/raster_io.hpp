@@ -311,6 +311,12 @@ struct Raster {
         if (rb.elem_bytes != elem_bytes) { error = "unexpected sample type in " + rb.path; return false; }
         char* out = static_cast<char*>(dst);
         const bool packed = rb.pixel_offset == elem_bytes;
+        // whole-width lines stored back to back: the block of this band is one contiguous byte range
+        if (packed && rb.x_off == 0 && rb.line_offset == (long)cols * elem_bytes) {
+            const long off = rb.image_offset + (long)(rb.y_off + yoff) * rb.line_offset;
+            if (!pread_all(rb.fd, out, (size_t)n * cols * elem_bytes, off)) { error = "short read from " + rb.path; return false; }
+            return true;
+        }
         std::vector<char> tmp;
         for (int r = 0; r < n; ++r) {
             const long off = rb.image_offset + (long)(rb.y_off + yoff + r) * rb.line_offset + (long)rb.x_off * rb.pixel_offset;

@@ -86,21 +86,37 @@ __global__ void __launch_bounds__(128) k_amp_sort(const float2* __restrict__ slc
 // shared memory.  191 exchanges (two integer min / max each) for NB = 32, where the insertion sort above executes ~7 000
 // instructions per pixel with two thirds of the lanes active.  Amplitudes of a valid pixel are positive and NaN-free, so
 // their bit patterns order like unsigned integers; unused slots hold 0xFFFFFFFF and stay at the top.
+// odd-even merge of the two sorted halves of v[LO .. LO + N) taken with stride R (Batcher)
+template <int NB, int LO, int N, int R>
+struct OddEvenMerge {
+    static __device__ __forceinline__ void run(uint32_t (&v)[NB]) {
+        constexpr int M = R * 2;
+        if constexpr (M < N) {
+            OddEvenMerge<NB, LO, N, M>::run(v);
+            OddEvenMerge<NB, LO + R, N, M>::run(v);
+#pragma unroll
+            for (int i = LO + R; i + R < LO + N; i += M) {
+                const uint32_t lo = min(v[i], v[i + R]), hi = max(v[i], v[i + R]);
+                v[i] = lo; v[i + R] = hi;
+            }
+        } else {
+            const uint32_t lo = min(v[LO], v[LO + R]), hi = max(v[LO], v[LO + R]);
+            v[LO] = lo; v[LO + R] = hi;
+        }
+    }
+};
+template <int NB, int LO, int N>
+struct OddEvenSort {
+    static __device__ __forceinline__ void run(uint32_t (&v)[NB]) {
+        if constexpr (N > 1) {
+            OddEvenSort<NB, LO, N / 2>::run(v);
+            OddEvenSort<NB, LO + N / 2, N / 2>::run(v);
+            OddEvenMerge<NB, LO, N, 1>::run(v);
+        }
+    }
+};
 template <int NB>
-__device__ __forceinline__ void sort_network(uint32_t (&v)[NB]) {
-#pragma unroll
-    for (int p = 1; p < NB; p *= 2)
-#pragma unroll
-        for (int k = p; k >= 1; k /= 2)
-#pragma unroll
-            for (int j = k % p; j <= NB - 1 - k; j += 2 * k)
-#pragma unroll
-                for (int i = 0; i <= (k - 1 < NB - j - k - 1 ? k - 1 : NB - j - k - 1); ++i)
-                    if ((i + j) / (2 * p) == (i + j + k) / (2 * p)) {
-                        const uint32_t lo = min(v[i + j], v[i + j + k]), hi = max(v[i + j], v[i + j + k]);
-                        v[i + j] = lo; v[i + j + k] = hi;
-                    }
-}
+__device__ __forceinline__ void sort_network(uint32_t (&v)[NB]) { OddEvenSort<NB, 0, NB>::run(v); }
 
 // amplitude + validity + sort for bands <= NB: one thread per pixel, everything in registers.  PIXEL_MAJOR: the
 // amplitudes are handed over as [pixel][band] floats with the reference's validity mask (nmapProcessBlock).
@@ -109,29 +125,32 @@ __global__ void __launch_bounds__(128) k_amp_sort_net(const float2* __restrict__
                                                       const uint8_t* __restrict__ mask, const double* __restrict__ alpha,
                                                       long npix, long p0, long pcount, int cols, int apitch, long aplane,
                                                       int bands, float* __restrict__ amp, uint8_t* __restrict__ valid) {
-    const long p = p0 + (long)blockIdx.x * blockDim.x + threadIdx.x;
+    // amplitudes in a rolled loop through a shared-memory column (bank = thread), then into registers: unrolling the
+    // exact hypot (a double-precision square root with an out-of-line slow path) NB times costs 80 registers and spills
+    __shared__ uint32_t s_col[NB][128];
+    const int tid = threadIdx.x;
+    const long p = p0 + (long)blockIdx.x * blockDim.x + tid;
     if (p >= p0 + pcount) return;
     bool ok = mask ? (mask[p] != 0) : true;
+#pragma unroll 4
+    for (int b = 0; b < bands; ++b) {
+        float x;
+        if (PIXEL_MAJOR) {
+            x = amp_in[p * bands + b];
+        } else {
+            const float2 z = __ldg(&slc[(long)b * npix + p]);
+            float h;
+            if (isinf(z.x) || isinf(z.y)) h = CUDART_INF_F;
+            else h = (float)__dsqrt_rn(__dadd_rn(__dmul_rn((double)z.x, (double)z.x), __dmul_rn((double)z.y, (double)z.y)));
+            // no calibration constants: (float)((double)h / 1.0) == h, skip the double division
+            x = alpha ? (float)__ddiv_rn((double)h, alpha[b]) : h;
+            ok = ok && (x != 0.f) && !isnan(x);
+        }
+        s_col[b][tid] = __float_as_uint(x);
+    }
     uint32_t v[NB];
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
-        v[b] = 0xFFFFFFFFu;
-        if (b < bands) {
-            float x;
-            if (PIXEL_MAJOR) {
-                x = amp_in[p * bands + b];
-            } else {
-                const float2 z = __ldg(&slc[(long)b * npix + p]);
-                float h;
-                if (isinf(z.x) || isinf(z.y)) h = CUDART_INF_F;
-                else h = (float)__dsqrt_rn(__dadd_rn(__dmul_rn((double)z.x, (double)z.x), __dmul_rn((double)z.y, (double)z.y)));
-                // no calibration constants: (float)((double)h / 1.0) == h, skip the double division
-                x = alpha ? (float)__ddiv_rn((double)h, alpha[b]) : h;
-                ok = ok && (x != 0.f) && !isnan(x);
-            }
-            v[b] = __float_as_uint(x);
-        }
-    }
+    for (int b = 0; b < NB; ++b) v[b] = (b < bands) ? s_col[b][tid] : 0xFFFFFFFFu;
     if (ok) sort_network<NB>(v);
     const long ap = (p / cols) * apitch + (p % cols);
 #pragma unroll
