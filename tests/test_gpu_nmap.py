@@ -142,3 +142,20 @@ def test_nmap_process_block_shim(oracle_lib):
     fn(amp.ctypes.data, valid.ctypes.data, cols, lines, bands, cnt.ctypes.data, wts.ctypes.data, 2, 0.05, 5, 2)
     getattr(raw, "_Z9unlockGPUv")()
     assert np.array_equal(cnt, c_ref) and np.array_equal(wts, w_ref)
+
+
+@pytest.mark.parametrize("Nx,Ny", [(6, 1), (7, 3), (9, 2), (2, 0)])
+@pytest.mark.parametrize("method", ["KS2", "AD2"])
+def test_tma_tile_alignment_shifts(ctx, oracle_lib, Nx, Ny, method):
+    """The TMA box of a tile has to start on a 16-byte boundary, so the tile grid is shifted by (-Nx) mod 4 columns
+    (k_nmap): every residue of Nx, an image width that is not a multiple of 4 (padded row pitch of the rank planes) and
+    an image narrower than one tile."""
+    for cols in (61, 23):
+        slc = synth.make_stack(9, 21, cols, seed=10 * Nx + Ny, region=8)
+        _check(ctx, oracle_lib, slc, Nx, Ny, method)
+
+
+def test_more_than_64_bands_takes_the_insertion_sort(ctx, oracle_lib):
+    # the register sorting network covers bands <= 64; beyond that the shared-memory insertion sort
+    slc = synth.make_stack(70, 18, 37, seed=70, region=8)
+    _check(ctx, oracle_lib, slc, 3, 2, "KS2")
