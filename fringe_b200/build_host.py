@@ -3,6 +3,7 @@ Python extension modules nmaplib / evdlib / phase_linklib / despecklib / ampdisp
 from __future__ import annotations
 
 import os
+import shutil
 import subprocess
 import sysconfig
 
@@ -19,9 +20,14 @@ def build(force: bool = False) -> None:
     os.makedirs(BINDINGS, exist_ok=True)
     hdrs = [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".hpp")]
     common = ["-O2", "-std=c++17", "-fPIC", "-pthread", "-Wall"]
+    gdal_link = []
+    gdal_config = shutil.which("gdal-config")
+    if gdal_config and not os.environ.get("FRINGE_NO_GDAL"):          # optional GDAL backend of host/raster_io.hpp
+        common += ["-DFRINGE_WITH_GDAL"] + subprocess.check_output([gdal_config, "--cflags"], text=True).split()
+        gdal_link = subprocess.check_output([gdal_config, "--libs"], text=True).split()
     if force or _newer(HOST_LIB, [os.path.join(HOST, "drivers.cpp"), __file__] + hdrs):
         _run([HOST_CXX] + common + ["-shared", "-o", HOST_LIB, os.path.join(HOST, "drivers.cpp"),
-                                    "-L" + LIBDIR, "-lfringe_b200", "-Wl,-rpath,$ORIGIN"])
+                                    "-L" + LIBDIR, "-lfringe_b200", "-Wl,-rpath,$ORIGIN"] + gdal_link)
     ext = sysconfig.get_config_var("EXT_SUFFIX")
     inc = ["-I" + pybind11.get_include(), "-I" + sysconfig.get_paths()["include"]]
     link = ["-L" + LIBDIR, "-lfringe_host", "-lfringe_b200", "-Wl,-rpath,$ORIGIN/../lib"]

@@ -37,7 +37,7 @@ struct fringe_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     int64_t launches = 0;
-    bool prof_generic = false;            // fringe_prof_force_generic: A/B comparisons only
+    int prof_generic = 0;                 // fringe_prof_force_generic: A/B comparisons only (bit 0; bits 8.. launch-shape overrides)
     // workspaces reused across blocks
     DevBuf amp, valid, zpix, zflags, zscale, adtab, alpha, stats, scratch;
     DevBuf in_slc, in_mask, in_wts, o_count, o_wts, o_out, o_tcorr, o_comp;
@@ -557,14 +557,15 @@ static int check_evd(fringe_ctx* ctx, int cols, int lines, int bands, int Nx, in
 
 namespace {
 
-struct EvdPlan { int NP = 0; int zblock = 0; bool generic = false; bool scaled = false; };
+struct EvdPlan { int NP = 0; int zblock = 0; bool generic = false; bool scaled = false; int prof_bits = 0; };
 
 int evd_prepare(fringe_ctx* ctx, int cols, int lines, int bands, int method, int variant, cudaStream_t st,
                 EvdPlan* plan) {
     CU(cudaSetDevice(ctx->device));
     const size_t npix = (size_t)cols * lines;
     plan->NP = (bands + 1) & ~1;
-    plan->generic = ctx->prof_generic;
+    plan->generic = (ctx->prof_generic & 1) != 0;
+    plan->prof_bits = ctx->prof_generic;
     if (!plan->generic && variant == FRINGE_VARIANT_EVD && method != FRINGE_EVD_MLE && fringe::evd_mma_order(bands) > 0) {
         plan->NP = 32;                        // 64 words per pixel: FP16 hi and lo parts of 32 bands
         plan->zblock = -1;
@@ -610,6 +611,7 @@ int evd_launch_rows(fringe_ctx* ctx, EvdPlan& plan, const float* slc, const uint
     a.out = (float2*)out; a.tcorr = tcorr; a.comp = (float2*)comp;
     a.stats = (unsigned long long*)ctx->stats.p;
     a.zblock = plan.zblock; a.tile_pairs = 0; a.scratch = nullptr;
+    a.force_generic = plan.prof_bits;
     a.flags = (const unsigned char*)ctx->zflags.p;
     if (plan.zblock >= 0) {
         int gw; long gg; size_t gs; bool use_scratch;
@@ -620,7 +622,6 @@ int evd_launch_rows(fringe_ctx* ctx, EvdPlan& plan, const float* slc, const uint
             a.scratch = (unsigned char*)ctx->scratch.p;
         }
     }
-    a.force_generic = plan.generic ? 1 : 0;
     int nl = 0;
     CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_EVD][0], st));
     if (n_lines > 0) CU(fringe::launch_evd(a, st, &nl));
@@ -1171,7 +1172,7 @@ int fringe_evd_stats(fringe_ctx* ctx, int64_t stats[8]) {
 
 int fringe_prof_force_generic(fringe_ctx* ctx, int on) {
     if (!ctx) return FRINGE_ERR_ARGUMENT;
-    ctx->prof_generic = on != 0;
+    ctx->prof_generic = on;
     return FRINGE_OK;
 }
 

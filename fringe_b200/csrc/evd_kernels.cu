@@ -1001,6 +1001,9 @@ void evd_generic_plan(const EvdArgs& a, int* warps, long* grid, size_t* smem, bo
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     const long total = (long)a.n_lines * a.cols;
     long g = (long)nsm * (*use_scratch ? 2 : 4);
+    // profiling overrides (fringe_prof_force_generic bits 8-15: CTAs per SM, bits 16-23: warps per CTA); never set by the product
+    if ((a.force_generic >> 16) & 0xff) w = (a.force_generic >> 16) & 0xff;
+    if ((a.force_generic >> 8) & 0xff) g = (long)nsm * ((a.force_generic >> 8) & 0xff);
     const long maxgrid = (total + w * 8 - 1) / (w * 8);
     if (g > maxgrid) g = maxgrid;
     if (g < 1) g = 1;

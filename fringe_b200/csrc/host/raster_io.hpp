@@ -6,13 +6,20 @@
 //     a band may also be a VRTRawRasterBand directly, or a SimpleSource over an ENVI file;
 //   * ENVI rasters (INTERLEAVE=BIP, SUFFIX=ADD => "<name>.hdr") for every output
 //     (src/nmap/nmap.cpp:237-264, src/evd/evd.cpp:266-366) and for the wts / mask inputs.
-// A GDAL-backed implementation of the same three classes is the deployment alternative
-// (INTEGRATION.md); nothing here touches the device.
+// With -DFRINGE_WITH_GDAL (fringe_b200/build_host.py adds it when `gdal-config` is on the PATH) a raster the built-in
+// reader cannot resolve -- GeoTIFF, non-raw VRT sources, pixel functions -- is opened through GDAL's C API instead and
+// read with GDALRasterIO into the same buffers; outputs stay ENVI, as in the reference.  GDAL is not part of the image
+// this repository is developed in, so that branch is compiled only where GDAL exists.  Nothing here touches the device.
 #pragma once
 #include <errno.h>
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
+
+#ifdef FRINGE_WITH_GDAL
+#include <gdal.h>
+#include <mutex>
+#endif
 
 #include <algorithm>
 #include <cctype>
@@ -192,11 +199,18 @@ struct Raster {
     EnviHeader envi;
     int fd = -1;
     std::string error;
+#ifdef FRINGE_WITH_GDAL
+    GDALDatasetH gdal_ds = nullptr;                    // set when the raster is read through GDAL
+    std::mutex gdal_mu;                                // a GDAL dataset handle is not thread-safe; block workers share it
+#endif
 
     ~Raster() { close_all(); }
     void close_all() {
         for (auto& b : bands) if (b.fd >= 0) { ::close(b.fd); b.fd = -1; }
         if (fd >= 0) { ::close(fd); fd = -1; }
+#ifdef FRINGE_WITH_GDAL
+        if (gdal_ds) { GDALClose(gdal_ds); gdal_ds = nullptr; }
+#endif
     }
     int count() const { return interleaved ? envi.bands : (int)bands.size(); }
 
@@ -263,6 +277,77 @@ struct Raster {
     }
 
     bool open(const std::string& p) {
+        if (open_builtin(p)) return true;
+#ifdef FRINGE_WITH_GDAL
+        const std::string why = error;
+        close_all(); bands.clear(); interleaved = false;
+        if (open_gdal(p)) return true;
+        error = why + "; GDAL: " + error;
+#endif
+        return false;
+    }
+
+#ifdef FRINGE_WITH_GDAL
+    static int envi_type_of(GDALDataType t) {
+        switch (t) {
+            case GDT_Byte: return 1; case GDT_Int16: return 2; case GDT_Int32: return 3; case GDT_Float32: return 4;
+            case GDT_Float64: return 5; case GDT_CFloat32: return 6; case GDT_CFloat64: return 9; case GDT_UInt16: return 12;
+            case GDT_UInt32: return 13; default: return 0;
+        }
+    }
+    // Any raster GDAL can open.  A dataset whose bands are CFloat32 is presented as a band-per-date stack (with the
+    // bands' "slc" metadata domain, evd.cpp:212-221 / nmap.cpp:204-233), anything else as a pixel-interleaved raster
+    // (weights, masks), with the ENVI-domain items the drivers look at (HALFWINDOWX / HALFWINDOWY, nmap.cpp:588-591).
+    bool open_gdal(const std::string& p) {
+        static std::once_flag once;
+        std::call_once(once, [] { GDALAllRegister(); });
+        gdal_ds = GDALOpen(p.c_str(), GA_ReadOnly);
+        if (!gdal_ds) { error = "GDALOpen failed for " + p; return false; }
+        path = p;
+        cols = GDALGetRasterXSize(gdal_ds); rows = GDALGetRasterYSize(gdal_ds);
+        const int nb = GDALGetRasterCount(gdal_ds);
+        if (cols <= 0 || rows <= 0 || nb <= 0) { error = "empty raster " + p; return false; }
+        const GDALDataType t0 = GDALGetRasterDataType(GDALGetRasterBand(gdal_ds, 1));
+        for (int b = 1; b <= nb; ++b) {
+            GDALRasterBandH hb = GDALGetRasterBand(gdal_ds, b);
+            RawBand rb;
+            rb.path = p;
+            rb.dtype = GDALGetDataTypeName(GDALGetRasterDataType(hb));
+            rb.elem_bytes = GDALGetDataTypeSizeBytes(GDALGetRasterDataType(hb));
+            rb.src_width = cols; rb.src_height = rows;
+            if (char** md = GDALGetMetadata(hb, "slc"))
+                for (char** it = md; *it; ++it) {
+                    const std::string kv(*it);
+                    const size_t eq = kv.find('=');
+                    if (eq != std::string::npos) rb.md_slc[kv.substr(0, eq)] = kv.substr(eq + 1);
+                }
+            bands.push_back(rb);
+        }
+        interleaved = (t0 != GDT_CFloat32);
+        if (interleaved) {
+            envi.samples = cols; envi.lines = rows; envi.bands = nb; envi.data_type = envi_type_of(t0); envi.interleave = "bip";
+            for (const char* key : {"HALFWINDOWX", "HALFWINDOWY"})
+                if (const char* v = GDALGetMetadataItem(gdal_ds, key, "ENVI")) envi.fields[lower(key)] = v;
+        }
+        return true;
+    }
+    bool gdal_read(int band /*1-based, 0 = all bands pixel-interleaved*/, int yoff, int n, void* dst, GDALDataType as) {
+        std::lock_guard<std::mutex> g(gdal_mu);
+        const int sz = GDALGetDataTypeSizeBytes(as);
+        CPLErr e;
+        if (band > 0)
+            e = GDALRasterIO(GDALGetRasterBand(gdal_ds, band), GF_Read, 0, yoff, cols, n, dst, cols, n, as, 0, 0);
+        else {
+            const int nb = GDALGetRasterCount(gdal_ds);
+            e = GDALDatasetRasterIO(gdal_ds, GF_Read, 0, yoff, cols, n, dst, cols, n, as, nb, nullptr,
+                                    (GSpacing)sz * nb, (GSpacing)sz * nb * cols, (GSpacing)sz);
+        }
+        if (e != CE_None) { error = "GDAL read failed on " + path; return false; }
+        return true;
+    }
+#endif
+
+    bool open_builtin(const std::string& p) {
         path = p;
         const bool looks_vrt = p.size() > 4 && lower(p.substr(p.size() - 4)) == ".vrt";
         if (looks_vrt) {
@@ -308,6 +393,12 @@ struct Raster {
     bool read_band_lines(int b, int yoff, int n, void* dst, int elem_bytes) {
         if (b < 0 || b >= (int)bands.size()) { error = "band index outside the raster (not a band-per-file stack?)"; return false; }
         const RawBand& rb = bands[b];
+#ifdef FRINGE_WITH_GDAL
+        if (gdal_ds) {
+            if (rb.elem_bytes != elem_bytes) { error = "unexpected sample type in " + rb.path; return false; }
+            return gdal_read(b + 1, yoff, n, dst, GDALGetRasterDataType(GDALGetRasterBand(gdal_ds, b + 1)));
+        }
+#endif
         if (rb.elem_bytes != elem_bytes) { error = "unexpected sample type in " + rb.path; return false; }
         char* out = static_cast<char*>(dst);
         const bool packed = rb.pixel_offset == elem_bytes;
@@ -333,6 +424,9 @@ struct Raster {
     }
     // Read lines of an interleaved (BIP) ENVI file: all bands, pixel-interleaved, packed.
     bool read_interleaved_lines(int yoff, int n, void* dst) {
+#ifdef FRINGE_WITH_GDAL
+        if (gdal_ds) return gdal_read(0, yoff, n, dst, GDALGetRasterDataType(GDALGetRasterBand(gdal_ds, 1)));
+#endif
         const size_t line_bytes = (size_t)cols * envi.bands * envi_type_bytes(envi.data_type);
         if (!pread_all(fd, dst, line_bytes * (size_t)n, (off_t)envi.header_offset + (off_t)yoff * (off_t)line_bytes)) { error = "short read from " + path; return false; }
         return true;
@@ -340,6 +434,12 @@ struct Raster {
     // Lines of a single-band raster of any integer / float type as a byte mask (non-zero -> 1), the
     // conversion GDAL's RasterIO(..., GDT_Byte) applies for nmap.cpp:323-343 in effect.
     bool read_mask_lines(int yoff, int n, uint8_t* dst, std::vector<char>& scratch) {
+#ifdef FRINGE_WITH_GDAL
+        if (gdal_ds) {                                  // GDAL converts to Byte exactly as nmap.cpp:323-343 asks it to
+            if (!gdal_read(1, yoff, n, dst, GDT_Byte)) return false;
+            return true;
+        }
+#endif
         int eb = 0; bool is_float = false;
         if (interleaved) { eb = envi_type_bytes(envi.data_type); is_float = (envi.data_type == 4 || envi.data_type == 5); }
         else if (!bands.empty()) { eb = bands[0].elem_bytes; is_float = lower(bands[0].dtype).find("float") != std::string::npos; }
