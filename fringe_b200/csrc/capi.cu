@@ -39,7 +39,7 @@ struct fringe_ctx {
     int64_t launches = 0;
     int prof_generic = 0;                 // fringe_prof_force_generic: A/B comparisons only (bit 0; bits 8.. launch-shape overrides)
     // workspaces reused across blocks
-    DevBuf amp, valid, zpix, zflags, zscale, adtab, alpha, stats, scratch;
+    DevBuf amp, valid, zpix, zscale, adtab, alpha, stats, scratch;
     DevBuf in_slc, in_mask, in_wts, o_count, o_wts, o_out, o_tcorr, o_comp;
     DevBuf seq_stack[2], seq_comp, seq_mini, seq_datum;     // fringe_sequential_block
     // cached AD2 table key
@@ -225,7 +225,7 @@ int fringe_destroy(fringe_ctx* c) {
     if (!c) return FRINGE_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf* all[] = {&c->amp, &c->valid, &c->zpix, &c->zflags, &c->zscale, &c->adtab, &c->alpha, &c->stats, &c->scratch, &c->in_slc, &c->in_mask,
+    DevBuf* all[] = {&c->amp, &c->valid, &c->zpix, &c->zscale, &c->adtab, &c->alpha, &c->stats, &c->scratch, &c->in_slc, &c->in_mask,
                      &c->in_wts, &c->o_count, &c->o_wts, &c->o_out, &c->o_tcorr, &c->o_comp, &c->seq_stack[0], &c->seq_stack[1],
                      &c->seq_comp, &c->seq_mini, &c->seq_datum};
     for (DevBuf* b : all) b->release();
@@ -569,7 +569,6 @@ int evd_prepare(fringe_ctx* ctx, int cols, int lines, int bands, int method, int
     if (!plan->generic && variant == FRINGE_VARIANT_EVD && method != FRINGE_EVD_MLE && fringe::evd_mma_order(bands) > 0) {
         plan->NP = 32;                        // 64 words per pixel: FP16 hi and lo parts of 32 bands
         plan->zblock = -1;
-        CU(ctx->zflags.ensure(npix + 1));
         CU(ctx->zscale.ensure(32 * sizeof(float)));
     }
     // one extra, all-zero sample vector behind the image: the register-blocked kernel points
@@ -596,7 +595,7 @@ int evd_launch_rows(fringe_ctx* ctx, EvdPlan& plan, const float* slc, const uint
             ctx->launches += 1;
         }
         CU(fringe::launch_transpose_mma((const float2*)slc, (long)npix, (long)t0 * cols, (long)tn * cols, bands,
-                                        (const float*)ctx->zscale.p, (float2*)ctx->zpix.p, (unsigned char*)ctx->zflags.p, st));
+                                        (const float*)ctx->zscale.p, (float2*)ctx->zpix.p, st));
     } else
         CU(fringe::launch_transpose((const float2*)slc, (long)npix, (long)t0 * cols, (long)tn * cols, bands, plan.NP,
                                     plan.zblock, (float2*)ctx->zpix.p, st));
@@ -612,7 +611,6 @@ int evd_launch_rows(fringe_ctx* ctx, EvdPlan& plan, const float* slc, const uint
     a.stats = (unsigned long long*)ctx->stats.p;
     a.zblock = plan.zblock; a.tile_pairs = 0; a.scratch = nullptr;
     a.force_generic = plan.prof_bits;
-    a.flags = (const unsigned char*)ctx->zflags.p;
     if (plan.zblock >= 0) {
         int gw; long gg; size_t gs; bool use_scratch;
         fringe::evd_generic_plan(a, &gw, &gg, &gs, &use_scratch);

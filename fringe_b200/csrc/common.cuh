@@ -62,7 +62,6 @@ struct EvdArgs {
     unsigned char* scratch;      // generic kernel, large bands: per-warp workspaces in global memory (else NULL)
     int tile_pairs;              // set by the launchers of the specialised kernels: columns per CTA segment
     int zblock;                  // 0: zpix is interleaved complex [pix][NP]; -1: the FP16 hi/lo layout of evd_mma.cu
-    const unsigned char* flags;  // zblock = -1: [npix] range flags written by the re-layout (see evd_mma.cu)
 };
 int evd_max_bands(int method, int variant);
 // launch geometry of the generic kernel; *use_scratch = the per-warp workspace does not fit shared
@@ -78,7 +77,7 @@ int evd_mma_order(int bands);
 // scale[b] = the power of two that brings band b's typical magnitude near 2^6 (sampled over pixels [first, first+count))
 cudaError_t launch_band_scale(const float2* slc, long npix, long first, long count, int bands, float* scale, cudaStream_t st);
 cudaError_t launch_transpose_mma(const float2* slc, long npix, long first, long count, int bands, const float* scale,
-                                 float2* zpix, unsigned char* flags, cudaStream_t st);
+                                 float2* zpix, cudaStream_t st);
 cudaError_t launch_evd_mma(const EvdArgs& a, cudaStream_t st);
 // FP64 MLE / phase_link kernel with one Hermitian row per lane in registers (mle_kernels.cu): bands <= 32;
 // same pixel-major layout as the generic kernel (zblock = 0).  evd_mle_order = 0: not covered.

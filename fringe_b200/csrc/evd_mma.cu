@@ -10,8 +10,9 @@
 //               (zero padded) bands are 64 words: word 4 g + q = half2(re, im) of band g + 8 q, first all hi (128 B),
 //               then all lo.  Lane (g, t) of a warp fetches its share of one SHP with four 8-byte loads (bands g, g+8 and
 //               g+16, g+24, hi and lo), and the eight lanes that share t read the SHP's 128-byte hi (lo) row contiguously.
-//               Pixels whose scaled samples leave the FP16 range (|x| >= 65504, NaN, or everything below 2^-8) are
-//               flagged; a pixel with a flagged SHP recomputes its Gram product from the original planes on FP32 FMAs.
+//               Pixels whose scaled samples leave the FP16 range (|x| >= 65504, NaN, or everything below 2^-8) get an
+//               all-NaN hi row; the NaN surfaces in the band powers of every pixel that has such an SHP, and that pixel
+//               recomputes its Gram product from the original planes on FP32 FMAs.
 //   covariance  One warp per pixel.  Eight SHPs form one k-chunk of m16n8k16: k = (2t, 2t+1) are (re, im) of SHP t,
 //               k = (2t+8, 2t+9) those of SHP t+4, so a half2 sample *is* an A-fragment register (an A quad = the 8-byte
 //               loads of SHP t and SHP t+4 side by side, no assembly) and
@@ -207,11 +208,11 @@ __global__ void __launch_bounds__(256) k_band_scale(const float2* __restrict__ s
 }
 
 // ---------------------------------------------------------------------------------------
-// re-layout: [bands][npix] -> [npix][hi 32 | lo 32] half2 words (see the header of this file) + range flags
+// re-layout: [bands][npix] -> [npix][hi 32 | lo 32] half2 words (see the header of this file); out-of-range pixels get
+// an all-NaN hi row, which marks every Gram product they enter
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_layout_f16(const float2* __restrict__ slc, long npix, long first, long pend, int bands,
-                                                    const float* __restrict__ scale, uint32_t* __restrict__ zh,
-                                                    unsigned char* __restrict__ flags) {
+                                                    const float* __restrict__ scale, uint32_t* __restrict__ zh) {
     // lane = 8 * (pixel & 3) + g: a warp reads eight 32-byte sectors per band group and writes four 128-byte rows
     const int g = threadIdx.x & 7, sub = threadIdx.x >> 3;
     const long p = first + (long)blockIdx.x * 32 + sub;
@@ -245,11 +246,10 @@ __global__ void __launch_bounds__(256) k_layout_f16(const float2* __restrict__ s
     }
     if (!live) return;
     const bool cold = top > 0.f && top < 0.00390625f;          // everything below 2^-8: the lo parts are gone
-    if (hot) { h[0] = h[1] = h[2] = h[3] = 0u; l[0] = l[1] = l[2] = l[3] = 0u; }
+    if (hot || cold) { h[0] = h[1] = h[2] = h[3] = 0x7e007e00u; l[0] = l[1] = l[2] = l[3] = 0u; }     // FP16 NaNs
     uint4* o = reinterpret_cast<uint4*>(zh + p * 64) + g;
     o[0] = make_uint4(h[0], h[1], h[2], h[3]);
     o[8] = make_uint4(l[0], l[1], l[2], l[3]);
-    if (g == 0) flags[p] = (hot || cold) ? 1 : 0;
 }
 
 cudaError_t launch_band_scale(const float2* slc, long npix, long first, long count, int bands, float* scale, cudaStream_t st) {
@@ -259,10 +259,10 @@ cudaError_t launch_band_scale(const float2* slc, long npix, long first, long cou
 }
 
 cudaError_t launch_transpose_mma(const float2* slc, long npix, long first, long count, int bands, const float* scale,
-                                 float2* zpix, unsigned char* flags, cudaStream_t st) {
+                                 float2* zpix, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
     k_layout_f16<<<(unsigned)((count + 31) / 32), 256, 0, st>>>(slc, npix, first, first + count, bands, scale,
-                                                               reinterpret_cast<uint32_t*>(zpix), flags);
+                                                               reinterpret_cast<uint32_t*>(zpix));
     return cudaGetLastError();
 }
 
@@ -371,7 +371,6 @@ __global__ void __launch_bounds__(FRINGE_MMA_WARPS * 32, 1) k_evd_mma(const EvdA
 #pragma unroll
             for (int e = 0; e < 4; ++e) { cre[tl][e] = 0.f; cim[tl][e] = 0.f; }
         int npix = 0;
-        bool hot = false;
 #pragma unroll 1
         for (int w0 = 0; w0 < a.nulong; w0 += 2) {
             int n = 0;
@@ -391,9 +390,6 @@ __global__ void __launch_bounds__(FRINGE_MMA_WARPS * 32, 1) k_evd_mma(const EvdA
             const int chunks = (n + CHUNK - 1) / CHUNK;
             if (lane < CHUNK && n + lane < CHUNK * chunks) s_list[n + lane] = zero_idx;
             __syncwarp();
-            // range flags of the SHPs (k_layout_f16): any flagged sample sends the pixel to the FP32 recomputation below
-            if (lane < n && __ldg(&a.flags[s_list[lane]])) hot = true;
-            if (lane + 32 < n && __ldg(&a.flags[s_list[lane + 32]])) hot = true;
             PHASE_MARK(0)
             // no register double buffering of the operands: the other 15 warps cover the load latency (measured equal
             // to a prefetching version with fewer resident warps); only the next list entries are fetched ahead
@@ -417,12 +413,18 @@ __global__ void __launch_bounds__(FRINGE_MMA_WARPS * 32, 1) k_evd_mma(const EvdA
         // accumulator fragment of tile (I, J): element e is row 16 I + g + 8 (e >> 1), column 8 J + 2 t + (e & 1)
         __syncwarp();
         bool zero_band = false;
-        hot = __any_sync(FULLMASK, hot);
+        // band powers = diagonal of Re C: lanes with g in {2t, 2t+1} hold them.  A NaN power means an SHP of this pixel
+        // carries the out-of-range marker of k_layout_f16 (its hi row is all NaN): FP32 recomputation below.
+        float p0 = 1.f, p1 = 1.f, p2 = 1.f, p3 = 1.f;
+        const bool diag = (g == 2 * t || g == 2 * t + 1);
+        if (diag) {
+            const bool odd = (g != 2 * t);              // selects, not a runtime index: keeps the tiles in registers
+            p0 = odd ? cre[0][1] : cre[0][0]; p1 = odd ? cre[1][3] : cre[1][2];
+            p2 = odd ? cre[4][1] : cre[4][0]; p3 = odd ? cre[5][3] : cre[5][2];
+        }
+        const bool hot = __any_sync(FULLMASK, (p0 != p0) || (p1 != p1) || (p2 != p2) || (p3 != p3));
         if (!hot) {
-            if (g == 2 * t || g == 2 * t + 1) {
-                const bool odd = (g != 2 * t);              // selects, not a runtime index: keeps the tiles in registers
-                const float p0 = odd ? cre[0][1] : cre[0][0], p1 = odd ? cre[1][3] : cre[1][2];
-                const float p2 = odd ? cre[4][1] : cre[4][0], p3 = odd ? cre[5][3] : cre[5][2];
+            if (diag) {
                 // padded bands get +inf so that their scaled entries come out as exact zeros
                 s_pw[g] = (g < N) ? sqrtf(p0) : CUDART_INF_F;
                 s_pw[g + 8] = (g + 8 < N) ? sqrtf(p1) : CUDART_INF_F;
