@@ -515,6 +515,9 @@ __global__ void __launch_bounds__(FRINGE_MMA_WARPS * 32, 1) k_evd_mma(const EvdA
         if (solve && zero_band) tc = CUDART_NAN_F;
         if (solve && !zero_band) {
             ++st_pix;
+            // the centre pixel's own samples for the compressed SLC: fetched now, needed after the iteration
+            float2 zc = make_float2(0.f, 0.f);
+            if (lane < N && lane >= k0) zc = __ldg(&a.slc[(long)lane * npix_block + pg]);
             const int r = (lane < NE) ? lane : NE;           // lanes beyond the matrix read the zero row
             // row r of the matrix as pairs of consecutive columns: cr2[k] = (Re C[r][2k], Re C[r][2k+1])
             constexpr int NP2 = NE / 2;
@@ -699,9 +702,8 @@ __global__ void __launch_bounds__(FRINGE_MMA_WARPS * 32, 1) k_evd_mma(const EvdA
                 // ---------------- compressed SLC (evd.cpp:755-762) ------------------
                 float cr = 0.f, ci = 0.f;
                 if (lane < N && lane >= k0) {
-                    const float2 z = __ldg(&a.slc[(long)lane * npix_block + pg]);
-                    cr = z.x * o.x + z.y * o.y;
-                    ci = z.y * o.x - z.x * o.y;
+                    cr = zc.x * o.x + zc.y * o.y;
+                    ci = zc.y * o.x - zc.x * o.y;
                 }
                 // ---------------- temporal coherence (evd.cpp:770-786) --------------
                 float* ov = s_vec + buf * 64;
