@@ -18,7 +18,7 @@
 //                KS2: the p-value threshold is turned into an integer bound k on
 //                     max_v |#{a<=v} - #{b<=v}| on the host (fringe_ks2_critical_count); that
 //                     bound holds iff b[i-k] <= a[i] and a[i-k] <= b[i] for all i >= k, so the
-//                     device test is 2(N-k) exact integer compares, no merge (ks_within).
+//                     device test is 2(N-k) exact integer compares, no merge (ks_bad4).
 //                AD2: the inner sum of AD2unique.hpp:287-303 only takes values from a
 //                     (2N-1)x(N+1) table of doubles T[j][|2m-(j+1)|]; the table is built on
 //                     the host with the reference's expression and the device adds the same
@@ -276,26 +276,45 @@ struct NmapKernelArgs {
 // compares instead of a 2n-step merge.  Keys are rank-major with a compile-time plane stride PS
 // ([rank][region pixel], as the TMA boxes land), so rank i of a pixel is an immediate offset from
 // the pixel's rank-0 address and the lanes of a warp (consecutive pixels) never collide on a bank.
-// pa / pb point at rank 0 of the two pixels.
+// pa points at rank 0 of the centre pixel.
+// Four neighbours of one pixel are tested at once: the centre pixel's two keys of a step are loaded once
+// and shared by the four pairs -- 10 shared-memory loads per step for four pairs instead of 16 (the kernel is bound by
+// shared-memory bandwidth).  d[j] = offset of neighbour j from the centre pixel in region pixels (the same for every
+// thread of the CTA).  Returns bit j set when pair j violates an inequality.
 template <int PS>
-__device__ __forceinline__ bool ks_within(const uint32_t* __restrict__ pa, const uint32_t* __restrict__ pb,
-                                          int n, int k) {
-    const uint32_t* __restrict__ ah = pa + k * PS;
-    const uint32_t* __restrict__ bh = pb + k * PS;
+__device__ __forceinline__ uint32_t ks_bad4(const uint32_t* __restrict__ pa, const int (&d)[4], int n, int k) {
+    const uint32_t* __restrict__ lo = pa;
+    const uint32_t* __restrict__ hi = pa + k * PS;
     const int m = n - k;
-    bool bad = false;                     // no short circuit: all loads of a step issue together
+    bool bad0 = false, bad1 = false, bad2 = false, bad3 = false;
     int i = 0;
 #pragma unroll 1
-    for (; i + 4 <= m; i += 4) {
-        uint32_t a_hi[4], a_lo[4], b_hi[4], b_lo[4];
+    for (; i + 2 <= m; i += 2) {
+        uint32_t a_hi[2], a_lo[2], b_hi[4][2], b_lo[4][2];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { a_hi[u] = ah[u * PS]; a_lo[u] = pa[u * PS]; b_hi[u] = bh[u * PS]; b_lo[u] = pb[u * PS]; }
+        for (int u = 0; u < 2; ++u) {
+            a_hi[u] = hi[u * PS]; a_lo[u] = lo[u * PS];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) bad |= (b_lo[u] > a_hi[u]) | (a_lo[u] > b_hi[u]);
-        ah += 4 * PS; bh += 4 * PS; pa += 4 * PS; pb += 4 * PS;
+            for (int j = 0; j < 4; ++j) { b_hi[j][u] = hi[d[j] + u * PS]; b_lo[j][u] = lo[d[j] + u * PS]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            bad0 |= (b_lo[0][u] > a_hi[u]) | (a_lo[u] > b_hi[0][u]);
+            bad1 |= (b_lo[1][u] > a_hi[u]) | (a_lo[u] > b_hi[1][u]);
+            bad2 |= (b_lo[2][u] > a_hi[u]) | (a_lo[u] > b_hi[2][u]);
+            bad3 |= (b_lo[3][u] > a_hi[u]) | (a_lo[u] > b_hi[3][u]);
+        }
+        lo += 2 * PS; hi += 2 * PS;
     }
-    for (; i < m; ++i) { bad |= (pb[0] > ah[0]) | (pa[0] > bh[0]); ah += PS; bh += PS; pa += PS; pb += PS; }
-    return !bad;
+    for (; i < m; ++i) {
+        const uint32_t ah = hi[0], al = lo[0];
+        bad0 |= (lo[d[0]] > ah) | (al > hi[d[0]]);
+        bad1 |= (lo[d[1]] > ah) | (al > hi[d[1]]);
+        bad2 |= (lo[d[2]] > ah) | (al > hi[d[2]]);
+        bad3 |= (lo[d[3]] > ah) | (al > hi[d[3]]);
+        lo += PS; hi += PS;
+    }
+    return (bad0 ? 1u : 0u) | (bad1 ? 2u : 0u) | (bad2 ? 4u : 0u) | (bad3 ? 8u : 0u);
 }
 
 // AD2unique.hpp:211-303: merge (on equality the element of B goes first) and table sum.
@@ -396,22 +415,49 @@ __global__ void k_nmap(const NmapKernelArgs a, const __grid_constant__ CUtensorM
     const int WX = 2 * Nx + 1, W = WX * (2 * Ny + 1), center = Ny * WX + Nx;
     uint32_t word = 1u << (center & 31);            // a valid pixel is always its own neighbour
     const int kc = min(max(a.kcrit, 0), N);         // k >= N accepts every pair, k < 0 none
-    int dy = 0, dx = 1;
-    for (int f = center + 1; f < W; ++f) {
-        if (dx > Nx) { dx = -Nx; ++dy; }
-        if ((f & 31) == 0) { atomicOr(&wp[(f - 1) >> 5], word); word = 0u; }
-        const int rq = rp + dy * RW + dx;
-        if (s_top[rq]) {
-            bool similar;
-            if (METHOD == 0) similar = (a.kcrit >= 0) && ks_within<PS>(s_key + rp, s_key + rq, N, kc);
-            else similar = ad_inner_sum(s_key, rp, rq, N, PS, T) <= a.scrit;
-            if (similar) {
+    if (METHOD == 0) {
+        // KS2: four window positions per pass (ks_bad4).  Positions beyond the window and invalid neighbours are tested
+        // against the pixel itself (offset 0) and their result is dropped.
+        int dy = 0, dx = 1;
+        for (int f0 = center + 1; f0 < W; f0 += 4) {
+            int d[4], ddy[4], ddx[4];
+            uint32_t live = 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (dx > Nx) { dx = -Nx; ++dy; }
+                ddy[j] = dy; ddx[j] = dx;
+                const bool in_window = (f0 + j < W);
+                d[j] = in_window ? dy * RW + dx : 0;
+                if (in_window && s_top[rp + d[j]]) live |= 1u << j;
+                ++dx;
+            }
+            uint32_t bad = 0xFu;
+            if (a.kcrit >= 0) bad = ks_bad4<PS>(s_key + rp, d, N, kc);
+            const uint32_t ok = live & ~bad;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int f = f0 + j;
+                if (f < W && (f & 31) == 0) { atomicOr(&wp[(f - 1) >> 5], word); word = 0u; }
+                if ((ok >> j) & 1u) {
+                    word |= (1u << (f & 31));
+                    const int fm = W - 1 - f;               // bit of (-dy,-dx) in q's mask
+                    atomicOr(&a.wts[(p + (long)ddy[j] * a.cols + ddx[j]) * a.nulong + (fm >> 5)], 1u << (fm & 31));
+                }
+            }
+        }
+    } else {
+        int dy = 0, dx = 1;
+        for (int f = center + 1; f < W; ++f) {
+            if (dx > Nx) { dx = -Nx; ++dy; }
+            if ((f & 31) == 0) { atomicOr(&wp[(f - 1) >> 5], word); word = 0u; }
+            const int rq = rp + dy * RW + dx;
+            if (s_top[rq] && ad_inner_sum(s_key, rp, rq, N, PS, T) <= a.scrit) {
                 word |= (1u << (f & 31));
                 const int fm = W - 1 - f;               // bit of (-dy,-dx) in q's mask
                 atomicOr(&a.wts[(p + (long)dy * a.cols + dx) * a.nulong + (fm >> 5)], 1u << (fm & 31));
             }
+            ++dx;
         }
-        ++dx;
     }
     atomicOr(&wp[(W - 1) >> 5], word);
 }

@@ -1,4 +1,4 @@
-"""The identity the KS2 device test rests on (fringe_b200/csrc/nmap_kernels.cu, ks_within):
+"""The identity the KS2 device test rests on (fringe_b200/csrc/nmap_kernels.cu, ks_bad4):
 
     max_v |#{a <= v} - #{b <= v}| <= k   <=>   b[i-k] <= a[i] and a[i-k] <= b[i] for all i in [k, n)
 
