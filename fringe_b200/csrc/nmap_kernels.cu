@@ -417,7 +417,6 @@ __global__ void k_nmap(const NmapKernelArgs a, const __grid_constant__ CUtensorM
     if (!s_top[rp]) return;                         // mask words stay zero
     const long p = (long)gy * a.cols + gx;
     uint32_t* wp = a.wts + p * a.nulong;
-    const double* T = (METHOD == 1) ? (a.table_in_smem ? s_tab : a.ad_table) : nullptr;
     const int WX = 2 * Nx + 1, W = WX * (2 * Ny + 1), center = Ny * WX + Nx;
     uint32_t word = 1u << (center & 31);            // a valid pixel is always its own neighbour
     const int kc = min(max(a.kcrit, 0), N);         // k >= N accepts every pair, k < 0 none
@@ -452,6 +451,9 @@ __global__ void k_nmap(const NmapKernelArgs a, const __grid_constant__ CUtensorM
             }
         }
     } else {
+        // (the walk is instantiated once per address space of the term table, so that its loads are plain LDS / LDG
+        // instead of generic loads)
+        auto walk_window = [&](const double* __restrict__ Tq) {
         // AD2: four window positions per pass (ad_inner_sums); positions beyond the window and invalid neighbours walk
         // against the pixel itself and their result is dropped
         int dy = 0, dx = 1;
@@ -471,7 +473,7 @@ __global__ void k_nmap(const NmapKernelArgs a, const __grid_constant__ CUtensorM
             double S[AD_BATCH];
             #pragma unroll
             for (int j = 0; j < AD_BATCH; ++j) S[j] = 0.0;
-            if (live != 0u) ad_inner_sums(s_key, rp, rq, N, PS, T, S);
+            if (live != 0u) ad_inner_sums(s_key, rp, rq, N, PS, Tq, S);
 #pragma unroll
             for (int j = 0; j < AD_BATCH; ++j) {
                 const int f = f0 + j;
@@ -483,6 +485,8 @@ __global__ void k_nmap(const NmapKernelArgs a, const __grid_constant__ CUtensorM
                 }
             }
         }
+        };
+        if (a.table_in_smem) walk_window(s_tab); else walk_window(a.ad_table);
     }
     atomicOr(&wp[(W - 1) >> 5], word);
 }
