@@ -602,7 +602,10 @@ __device__ bool smallest_eigen_mle(const WarpSmem& w, int n, int ldc, int ld, in
     return true;
 }
 
-template <int HR, bool DP>
+// GS: the per-warp workspace lives in the global scratch buffer (large N) instead of shared memory -- a template
+// parameter, not a run-time select, so that the shared-memory instantiations address it with plain LDS / STS (a pointer
+// chosen at run time makes every workspace access a generic load or store)
+template <int HR, bool DP, bool GS>
 __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
     const int WARPS = blockDim.x >> 5;
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -610,8 +613,8 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
     const int N = a.bands, NP = a.NP;
     const int ldc = N | 1, ld = N | 1;
     // per-warp workspace: shared memory, or (large N) a slice of the global scratch buffer
-    unsigned char* wbase = a.scratch ? a.scratch + ((size_t)blockIdx.x * WARPS + warp) * evd_warp_smem_bytes(N, DP)
-                                     : s_raw + (size_t)warp * evd_warp_smem_bytes(N, DP);
+    unsigned char* wbase = GS ? a.scratch + ((size_t)blockIdx.x * WARPS + warp) * evd_warp_smem_bytes(N, DP)
+                              : s_raw + (size_t)warp * evd_warp_smem_bytes(N, DP);
     const WarpSmem w = carve(wbase, N, DP);
     const long npix_block = (long)a.cols * a.lines;
 
@@ -979,12 +982,16 @@ int evd_max_bands(int, int) { return 128; }
 size_t evd_generic_workspace_bytes(int bands, bool dp) { return evd_warp_smem_bytes(bands, dp); }
 
 // grid x warps chosen so that the (optional) global scratch stays bounded
+template <int HR, bool DP, bool GS>
+static cudaError_t launch_evd_gs(const EvdArgs& a, cudaStream_t st, int WARPS, long grid, size_t smem) {
+    cudaError_t e = cudaFuncSetAttribute(k_evd<HR, DP, GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_evd<HR, DP, GS><<<(unsigned)grid, WARPS * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
 template <int HR, bool DP>
 static cudaError_t launch_evd_t(const EvdArgs& a, cudaStream_t st, int WARPS, long grid, size_t smem) {
-    cudaError_t e = cudaFuncSetAttribute(k_evd<HR, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    k_evd<HR, DP><<<(unsigned)grid, WARPS * 32, smem, st>>>(a);
-    return cudaGetLastError();
+    return a.scratch ? launch_evd_gs<HR, DP, true>(a, st, WARPS, grid, smem) : launch_evd_gs<HR, DP, false>(a, st, WARPS, grid, smem);
 }
 
 void evd_generic_plan(const EvdArgs& a, int* warps, long* grid, size_t* smem, bool* use_scratch) {
