@@ -557,7 +557,7 @@ static int check_evd(fringe_ctx* ctx, int cols, int lines, int bands, int Nx, in
 
 namespace {
 
-struct EvdPlan { int NP = 0; int zblock = 0; bool generic = false; bool scaled = false; int prof_bits = 0; };
+struct EvdPlan { int NP = 0; int zblock = 0; bool generic = false; int prof_bits = 0; };
 
 int evd_prepare(fringe_ctx* ctx, int cols, int lines, int bands, int method, int variant, cudaStream_t st,
                 EvdPlan* plan) {
@@ -570,6 +570,7 @@ int evd_prepare(fringe_ctx* ctx, int cols, int lines, int bands, int method, int
         plan->NP = 32;                        // 64 words per pixel: FP16 hi and lo parts of 32 bands
         plan->zblock = -1;
         CU(ctx->zscale.ensure(32 * sizeof(float)));
+        CU(cudaMemsetAsync(ctx->zscale.p, 0, 32 * sizeof(float), st));        // every band's scale still open
     }
     // one extra, all-zero sample vector behind the image: the register-blocked kernel points
     // exhausted / out-of-block SHP slots at it instead of branching
@@ -581,17 +582,16 @@ int evd_prepare(fringe_ctx* ctx, int cols, int lines, int bands, int method, int
 }
 
 // re-layout of input rows [t0, t0+tn), then the solve for output rows [first_line, first_line+n_lines)
-int evd_launch_rows(fringe_ctx* ctx, EvdPlan& plan, const float* slc, const uint32_t* wts, int cols,
+int evd_launch_rows(fringe_ctx* ctx, const EvdPlan& plan, const float* slc, const uint32_t* wts, int cols,
                     int lines, int bands, int Nx, int Ny, int t0, int tn, int first_line, int n_lines,
                     int method, int bandwidth, int mini_stack_count, int variant, int min_neighbors,
                     float* out, float* tcorr, float* comp, cudaStream_t st) {
     const size_t npix = (size_t)cols * lines;
     CU(cudaEventRecord(ctx->ev[FRINGE_KERNEL_TRANSPOSE][0], st));
     if (plan.zblock < 0) {
-        if (!plan.scaled && tn > 0) {          // per-band scales from the first rows of this block that reach the device
+        if (tn > 0) {          // per-band scales: fixed by the first rows of this block call that hold data, a no-op afterwards
             CU(fringe::launch_band_scale((const float2*)slc, (long)npix, (long)t0 * cols, (long)tn * cols, bands,
                                          (float*)ctx->zscale.p, st));
-            plan.scaled = true;
             ctx->launches += 1;
         }
         CU(fringe::launch_transpose_mma((const float2*)slc, (long)npix, (long)t0 * cols, (long)tn * cols, bands,

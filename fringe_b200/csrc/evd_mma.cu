@@ -170,40 +170,51 @@ __device__ __forceinline__ u64 pack2(float x, float y) {
 
 // ---------------------------------------------------------------------------------------
 // per-band power-of-two scale: 2^(5 - E), E = rounded mean binary exponent of the finite non-zero components of a
-// sample of the rows at hand (a geometric mean: one absurd value cannot move it).  For Gaussian components of standard
+// sample of the first rows of the block call that hold any data (scale[b] = 0 means "still open") (a geometric mean: one absurd value cannot move it).  For Gaussian components of standard
 // deviation s the mean exponent is log2(s) - 1.4, so s lands near 2^6.4.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_band_scale(const float2* __restrict__ slc, long npix, long first, long count,
                                                     float* __restrict__ scale) {
     const int b = blockIdx.x;
-    const long groups = (count + 3) / 4;                       // 4 consecutive pixels = one 32-byte sector
-    const long want = 16384;                                   // sectors sampled per band
-    const long step = groups > want ? groups / want : 1;
-    long esum = 0; int n = 0;
-    for (long gi = threadIdx.x; gi * step < groups; gi += blockDim.x) {
-        const long p0 = first + gi * step * 4;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (p0 + k >= first + count) break;
-            const float2 v = __ldg(&slc[(long)b * npix + p0 + k]);
-            const uint32_t ex = (__float_as_uint(v.x) >> 23) & 0xffu, ey = (__float_as_uint(v.y) >> 23) & 0xffu;
-            if (ex > 0 && ex < 255) { esum += (int)ex - 127; ++n; }
-            if (ey > 0 && ey < 255) { esum += (int)ey - 127; ++n; }
-        }
-    }
+    if (scale[b] != 0.f) return;                               // fixed by an earlier row chunk of this block call
     __shared__ long s_sum[256];
     __shared__ int s_n[256];
-    s_sum[threadIdx.x] = esum; s_n[threadIdx.x] = n;
-    __syncthreads();
-    for (int s2 = 128; s2 > 0; s2 >>= 1) {
-        if (threadIdx.x < s2) { s_sum[threadIdx.x] += s_sum[threadIdx.x + s2]; s_n[threadIdx.x] += s_n[threadIdx.x + s2]; }
+    const long groups = (count + 3) / 4;                       // 4 consecutive pixels = one 32-byte sector
+    const long want = 16384;                                   // sectors sampled per band
+    // pass 0 samples; if it finds nothing but zeros (or non-finite values), pass 1 looks at every pixel: the scale must
+    // be fixed by the first rows that hold any data at all, because rows laid out earlier keep the factor 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const long step = (pass == 0 && groups > want) ? groups / want : 1;
+        long esum = 0; int n = 0;
+        for (long gi = threadIdx.x; gi * step < groups; gi += blockDim.x) {
+            const long p0 = first + gi * step * 4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (p0 + k >= first + count) break;
+                const float2 v = __ldg(&slc[(long)b * npix + p0 + k]);
+                const uint32_t ex = (__float_as_uint(v.x) >> 23) & 0xffu, ey = (__float_as_uint(v.y) >> 23) & 0xffu;
+                if (ex > 0 && ex < 255) { esum += (int)ex - 127; ++n; }
+                if (ey > 0 && ey < 255) { esum += (int)ey - 127; ++n; }
+            }
+        }
+        s_sum[threadIdx.x] = esum; s_n[threadIdx.x] = n;
         __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        int e = 0;
-        if (s_n[0] > 0) e = 5 - (int)floor((double)s_sum[0] / (double)s_n[0] + 0.5);
-        e = max(-100, min(100, e));
-        scale[b] = exp2f((float)e);
+        for (int s2 = 128; s2 > 0; s2 >>= 1) {
+            if (threadIdx.x < s2) { s_sum[threadIdx.x] += s_sum[threadIdx.x + s2]; s_n[threadIdx.x] += s_n[threadIdx.x + s2]; }
+            __syncthreads();
+        }
+        const int total = s_n[0];
+        const long sum = s_sum[0];
+        __syncthreads();
+        if (total > 0) {
+            if (threadIdx.x == 0) {
+                int e = 5 - (int)floor((double)sum / (double)total + 0.5);
+                e = max(-100, min(100, e));
+                scale[b] = exp2f((float)e);
+            }
+            return;
+        }
+        if (step == 1) return;                                 // the sample was already exhaustive: the scale stays open
     }
 }
 
@@ -226,7 +237,8 @@ __global__ void __launch_bounds__(256) k_layout_f16(const float2* __restrict__ s
         float2 v = make_float2(0.f, 0.f);
         if (live && b < bands) {
             v = __ldg(&slc[(long)b * npix + p]);
-            const float sc = __ldg(&scale[b]);
+            float sc = __ldg(&scale[b]);
+            if (sc == 0.f) sc = 1.f;                           // still open: nothing but zeros so far
             v.x *= sc; v.y *= sc;
         }
         const float ax = fabsf(v.x), ay = fabsf(v.y);

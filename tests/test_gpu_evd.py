@@ -273,3 +273,31 @@ def test_samples_outside_the_fp16_range_take_the_fp32_recomputation(ctx, oracle_
     _compare(ref, gpu)
     stats = ctx.evd_stats()
     assert stats["fp32_recomputed"] >= (2 * Ny + 1) * (2 * Nx + 1) + 12 * 16, stats
+
+
+def test_band_scale_is_fixed_by_the_first_rows_that_hold_data(ctx):
+    """Host-pointer call in several row chunks (the upload pipeline) on a stack whose first stages are all zero -- the
+    zero-filled border of a burst -- and whose samples are small (calibrated backscatter): the per-band FP16 scale stays
+    open until a chunk holds data, nothing takes the FP32 recomputation, and the result equals the one-shot device call."""
+    import torch
+    from fringe_b200.engine import nulong
+    bands, lines, cols, Nx, Ny = 8, 1700, 4096, 5, 2          # 384 MB stages = 1464 rows; ramp stages of 366 / 732 rows
+    dev = torch.device("cuda", 0)
+    slc = synth.make_stack_torch(bands, lines, cols, seed=5, device=dev) * 2.0e-3
+    slc[:, :420] = 0                                          # the first (quarter) stage holds no data at all
+    W = (2 * Nx + 1) * (2 * Ny + 1)
+    nu = nulong(Nx, Ny)
+    bits = np.zeros(nu * 32, np.uint8); bits[:W] = 1
+    words = np.packbits(bits.reshape(nu, 32)[:, ::-1], axis=1).view(">u4").astype(np.uint32).reshape(nu)
+    wts = np.broadcast_to(words, (lines, cols, nu)).copy()
+    wts[:420] = 0
+    h_out, h_tc, h_comp = ctx.evd_block(slc.cpu().numpy(), wts, Nx, Ny, method="EVD")
+    assert ctx.evd_stats()["fp32_recomputed"] == 0
+    d_wts = torch.from_numpy(wts.view(np.int32)).to(dev)
+    d_out, d_tc, d_comp = ctx.evd_block_device(slc.contiguous(), d_wts, Nx, Ny, "EVD")
+    torch.cuda.synchronize()
+    d_tc = d_tc.cpu().numpy(); d_out = d_out.cpu().numpy()
+    solved = d_tc > 0
+    assert solved[430:].mean() > 0.99 and not solved[:415].any()
+    assert np.abs(h_tc - d_tc).max() <= 1e-6
+    assert wrapped_diff(h_out[:, solved], d_out[:, solved]).max() <= 1e-5
