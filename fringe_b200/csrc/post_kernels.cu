@@ -183,13 +183,23 @@ cudaError_t launch_despeck(const float2* z1, const float2* z2, const uint32_t* w
 __global__ void __launch_bounds__(256) k_ampdispersion(const float2* __restrict__ slc, const double* __restrict__ alpha,
                                                        long npix, int bands, float* __restrict__ da,
                                                        float* __restrict__ meanamp) {
+    // valid / alpha[b] only takes two values per band (valid is 0 or 1): both quotients once per block instead of a
+    // double-precision division per sample, the same correctly rounded numbers
+    extern __shared__ double s_q[];                         // [bands][2]: 0 / alpha, 1 / alpha
+    for (int b = threadIdx.x; b < bands; b += blockDim.x) {
+        const double al = alpha ? alpha[b] : 1.0;
+        s_q[2 * b] = __ddiv_rn(0.0, al);
+        s_q[2 * b + 1] = __ddiv_rn(1.0, al);
+    }
+    __syncthreads();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;
     double mean = 0.0, meansq = 0.0, norms = 0.0;
+#pragma unroll 4
     for (int b = 0; b < bands; ++b) {
         double absval = (double)hypotf_exact(__ldg(slc + (long)b * npix + i));
         const int valid = (absval != 0.0);
-        absval = __dmul_rn(absval, __ddiv_rn((double)valid, alpha ? alpha[b] : 1.0));
+        absval = __dmul_rn(absval, s_q[2 * b + valid]);
         mean = __dadd_rn(mean, absval);
         meansq = __dadd_rn(meansq, __dmul_rn(absval, absval));
         norms += (double)valid;
@@ -208,7 +218,7 @@ __global__ void __launch_bounds__(256) k_ampdispersion(const float2* __restrict_
 cudaError_t launch_ampdispersion(const float2* slc, const double* alpha, long npix, int bands, float* da, float* meanamp,
                                  cudaStream_t st) {
     if (npix <= 0) return cudaSuccess;
-    k_ampdispersion<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(slc, alpha, npix, bands, da, meanamp);
+    k_ampdispersion<<<(unsigned)((npix + 255) / 256), 256, (size_t)bands * 2 * sizeof(double), st>>>(slc, alpha, npix, bands, da, meanamp);
     return cudaGetLastError();
 }
 
