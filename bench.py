@@ -381,6 +381,7 @@ def main():
 
     # ---- end to end through the host C ABI --------------------------------------------------
     e2e = None
+    affinity0 = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
     if not args.no_e2e:
         numa_node = bind_to_gpu_numa_node(local)
         pin = lambda *shape, dtype: torch.empty(shape, dtype=dtype, pin_memory=True)
@@ -453,6 +454,8 @@ def main():
                "host_link": {"gbs_each_way": link_gbs, "note": "pinned copies of %d MB up and down at the same time on every rank, "
                              "max over ranks" % (nb >> 20), "floor_ms_per_step": max(h2d, d2h) / (link_gbs * 1e9) * 1e3}}
 
+    if affinity0 is not None:
+        os.sched_setaffinity(0, affinity0)          # the CPU baseline below gets every usable core again
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         _, cpu, _ = cpu_reference_rate(cfg, 1, 0)
