@@ -38,6 +38,7 @@ def build(ref: bool | None = None) -> None:
         ref = os.path.isdir("/root/reference")
     if ref:
         subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+        subprocess.check_call(["make", "-s", "-C", _HERE, "refdrivers"])
 
 
 def nulong(Nx: int, Ny: int) -> int:
@@ -260,3 +261,33 @@ def load(kind: str | None = None) -> Oracle:
                 raise FileNotFoundError(_PATHS[kind] + " (build with `make -C oracle ref` where /root/reference exists)")
         _CACHE[kind] = Oracle(_PATHS[kind])
     return _CACHE[kind]
+
+
+# ---- the reference's own block drivers (oracle/ref_drivers/, built by `make -C oracle refdrivers`) -----------------
+REF_DRIVERS = ("nmap", "evd", "phase_link", "despeck", "ampdispersion", "calamp")
+_REF_DRIVER_CACHE: dict[str, C.CDLL] = {}
+
+
+def ref_driver_available(name: str) -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", f"libref_{name}.so"))
+
+
+def ref_driver(name: str) -> C.CDLL:
+    """ctypes handle of the reference driver `name` (src/<name>/<name>.cpp compiled unmodified against the GDAL /
+    Armadillo stand-ins of oracle/shims/; file in, file out, like the reference's command line)."""
+    if name not in _REF_DRIVER_CACHE:
+        os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+        lib = C.CDLL(os.path.join(_HERE, "_ref", f"libref_{name}.so"))
+        s, i, d = C.c_char_p, C.c_int, C.c_double
+        if name == "nmap":
+            lib.ref_nmap.argtypes = [s, s, s, s, i, i, s, d, i, i]
+        elif name in ("evd", "phase_link"):
+            getattr(lib, "ref_" + name).argtypes = [s, s, s, s, s, i, i, s, i, i, i, i, i]
+        elif name == "despeck":
+            lib.ref_despeck.argtypes = [s, s, s, i, i, i, i, i, i, i]
+        elif name == "ampdispersion":
+            lib.ref_ampdispersion.argtypes = [s, s, s, i, i, i]
+        elif name == "calamp":
+            lib.ref_calamp.argtypes = [s, s, s, d, i, i, i, i, C.POINTER(C.c_double)]
+        _REF_DRIVER_CACHE[name] = lib
+    return _REF_DRIVER_CACHE[name]

@@ -1,0 +1,3 @@
+// TEST INFRASTRUCTURE ONLY -- see gdal_shim.hpp
+#pragma once
+#include "gdal_shim.hpp"
