@@ -12,6 +12,10 @@ Two builds of the same loop text (``oracle/loops.hpp``) exist:
   place from ``/root/reference`` (built in the authoring container only; the ``.so`` travels).
 
 ``load()`` prefers the reference build when it is present.
+
+``ref_driver(name)`` gives the reference's own block drivers (``src/<name>/<name>.cpp`` compiled unmodified against the
+GDAL / Armadillo stand-ins of ``oracle/shims/``, ``oracle/ref_drivers/``): the restated loops are pinned to them in
+``tests/test_reference_drivers_cpu.py``.
 """
 from __future__ import annotations
 

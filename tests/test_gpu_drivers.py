@@ -158,3 +158,39 @@ def test_despeck_cli_multi_block(stack, oracle_lib):
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
     with pytest.raises(Exception, match="coherence"):
         despeck_cli.main(["-i", vrt, "-w", wts_path, "-o", out + "x", "-b", "1", "-c"])
+
+
+def test_rasters_equal_the_reference_drivers_rasters(stack, tmp_path):
+    """File in, file out on both sides: the reference's own nmap.cpp / evd.cpp (compiled unmodified against the GDAL /
+    Armadillo stand-ins, oracle/ref_drivers/) and this repository's drivers read the same stack VRT; the neighbour mask
+    and count rasters must be byte-identical, the phase-linked rasters within the parity gates."""
+    import oracle as oracle_pkg
+    if not all(oracle_pkg.ref_driver_available(n) for n in ("nmap", "evd")):
+        pytest.skip("reference drivers not built")
+    root, slc, vrt = stack
+    enc = lambda s: str(s).encode()
+    r_w, r_c = str(tmp_path / "ref_nmap"), str(tmp_path / "ref_count")
+    assert oracle_pkg.ref_driver("nmap").ref_nmap(enc(vrt), enc(r_w), enc(r_c), None, 5, 2, b"KS2", 0.05, 1, 64) == 0
+    g_w, g_c = str(tmp_path / "gpu_nmap"), str(tmp_path / "gpu_count")
+    nmap_cli.main(["-i", vrt, "-o", g_w, "-c", g_c, "-x", "5", "-y", "2", "-r", "1"])
+    for a, b in ((r_w, g_w), (r_c, g_c)):
+        assert open(a, "rb").read() == open(b, "rb").read()
+        ha, hb = stackio.read_envi_header(a), stackio.read_envi_header(b)
+        assert all(ha[k] == hb[k] for k in ("samples", "lines", "bands", "data type", "interleave", "halfwindowx", "halfwindowy"))
+    dates = stackio.default_dates(12)
+    for method in ("EVD", "MLE"):
+        r_out, g_out = str(tmp_path / ("ref_" + method)), str(tmp_path / ("gpu_" + method))
+        assert oracle_pkg.ref_driver("evd").ref_evd(enc(vrt), enc(r_w), enc(r_out), enc(r_out), b"compslc.bin", 5, 2, enc(method),
+                                                    -1, 1, 2, 1, 64) == 0
+        evd_cli.main(["-i", vrt, "-w", g_w, "-o", g_out, "-x", "5", "-y", "2", "-m", method, "-r", "1"])
+        t_ref, t_gpu = stackio.read_envi(os.path.join(r_out, "tcorr.bin")), stackio.read_envi(os.path.join(g_out, "tcorr.bin"))
+        codes_differ = np.where(t_ref <= 0, t_ref, 0) != np.where(t_gpu <= 0, t_gpu, 0)
+        assert codes_differ.sum() <= (3 if method == "MLE" else 0)          # MLE: pixels on the 1e-6 eigenvalue gates
+        ok = (t_ref > 0) & (t_gpu > 0)
+        assert np.abs(t_ref - t_gpu)[ok].max() <= 1e-4
+        good = ok & (t_ref > 0.3)
+        p_ref = np.stack([stackio.read_envi(os.path.join(r_out, d + ".slc")) for d in dates])
+        p_gpu = np.stack([stackio.read_envi(os.path.join(g_out, d + ".slc")) for d in dates])
+        assert wrapped_diff(p_ref[:, good], p_gpu[:, good]).max() <= 1e-3
+        c_ref, c_gpu = stackio.read_envi(os.path.join(r_out, "compslc.bin")), stackio.read_envi(os.path.join(g_out, "compslc.bin"))
+        assert np.abs(c_ref - c_gpu)[good].max() <= 2e-3 * np.abs(c_ref).max()
