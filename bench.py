@@ -150,9 +150,68 @@ def usable_cores() -> int:
         return os.cpu_count() or 1
 
 
+def cpu_reference_rate_drivers(cfg, steps: int, warmup: int):
+    """Time the reference's OWN block drivers -- src/nmap/nmap.cpp followed by src/evd/evd.cpp (or phase_link.cpp),
+    compiled unmodified with OpenMP against the GDAL / Armadillo stand-ins of oracle/shims/ -- file in, file out on a strip
+    of the workload in a RAM-backed directory.  None when those builds are absent or the config is the sequential chain."""
+    import shutil
+    import tempfile
+    import oracle
+    from fringe_b200 import stackio, synth
+    second = "phase_link" if cfg["variant"] == 1 else "evd"
+    cores = usable_cores()
+    if cfg["s"] or cores < 2 or not (oracle.ref_driver_available("nmap", True) and oracle.ref_driver_available(second, True)):
+        return None
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    nmap_lib, evd_lib = oracle.ref_driver("nmap", True), oracle.ref_driver(second, True)
+    sl, sc = cfg["sample"]
+    slc = synth.make_stack(cfg["bands"], sl, sc, seed=2)
+    root = tempfile.mkdtemp(prefix="fringe_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    enc = lambda x: str(x).encode()
+    times = []
+    try:
+        vrt = stackio.make_stack_on_disk(root, slc)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(devnull, 1)                                   # the drivers report on stdout; this process owes it one JSON line
+        try:
+            for it in range(warmup + steps):
+                w, c, out = (os.path.join(root, f"{n}{it}") for n in ("nmap", "count", "evd"))
+                t0 = time.perf_counter()
+                rc = nmap_lib.ref_nmap(enc(vrt), enc(w), enc(c), None, cfg["Nx"], cfg["Ny"], enc(cfg["nmap"]), 0.05, 8192, 64)
+                rc2 = getattr(evd_lib, "ref_" + second)(enc(vrt), enc(w), enc(out), enc(out), b"compslc.bin", cfg["Nx"], cfg["Ny"],
+                                                        enc(cfg["method"]), -1, 1, cfg["minn"], 8192, 64)
+                dt = time.perf_counter() - t0
+                if rc or rc2:
+                    return None
+                if it >= warmup:
+                    times.append(dt)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved); os.close(devnull)
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+    rate = sl * sc * len(times) / sum(times)
+    desc = {"value": rate, "unit": "pixels/s", "cores": cores, "kind": "reference",
+            "sample": f"{sl}x{sc} strip of the same {cfg['bands']}-date workload, {len(times)} pass(es) of the reference's own "
+                      f"src/nmap/nmap.cpp + src/{second}/{second}.cpp (compiled unmodified, OpenMP on the {cores} usable cores, "
+                      f"OpenBLAS single-threaded per call; GDAL / Armadillo replaced by I/O and storage stand-ins), files in a "
+                      f"RAM-backed directory, wall clock incl. that file I/O"}
+    return rate, desc, sum(times) / len(times)
+
+
 def cpu_reference_rate(cfg, steps: int, warmup: int):
-    """Time the CPU oracle (the reference's own headers + restated loops, OpenMP over pixels) on a strip of the
-    workload.  Returns (pixels/s, description dict, seconds per pass)."""
+    """Time the reference's CPU path on a strip of the workload: its own drivers where they are built
+    (cpu_reference_rate_drivers), else the reference's headers inside the restated loops (OpenMP over pixels).
+    Returns (pixels/s, description dict, seconds per pass)."""
+    try:
+        got = cpu_reference_rate_drivers(cfg, steps, warmup)
+    except Exception:
+        got = None
+    if got is not None:
+        return got
     import oracle
     from fringe_b200 import synth
     o = oracle.load()

@@ -272,16 +272,18 @@ REF_DRIVERS = ("nmap", "evd", "phase_link", "despeck", "ampdispersion", "calamp"
 _REF_DRIVER_CACHE: dict[str, C.CDLL] = {}
 
 
-def ref_driver_available(name: str) -> bool:
-    return os.path.exists(os.path.join(_HERE, "_ref", f"libref_{name}.so"))
+def ref_driver_available(name: str, openmp: bool = False) -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", f"libref_{name}{'_omp' if openmp else ''}.so"))
 
 
-def ref_driver(name: str) -> C.CDLL:
+def ref_driver(name: str, openmp: bool = False) -> C.CDLL:
     """ctypes handle of the reference driver `name` (src/<name>/<name>.cpp compiled unmodified against the GDAL /
-    Armadillo stand-ins of oracle/shims/; file in, file out, like the reference's command line)."""
-    if name not in _REF_DRIVER_CACHE:
+    Armadillo stand-ins of oracle/shims/; file in, file out, like the reference's command line).  openmp=True: the
+    multi-threaded build (nmap / evd / phase_link only), for timing -- nmap.cpp's pair loop races there."""
+    key = name + ("_omp" if openmp else "")
+    if key not in _REF_DRIVER_CACHE:
         os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
-        lib = C.CDLL(os.path.join(_HERE, "_ref", f"libref_{name}.so"))
+        lib = C.CDLL(os.path.join(_HERE, "_ref", f"libref_{key}.so"))
         s, i, d = C.c_char_p, C.c_int, C.c_double
         if name == "nmap":
             lib.ref_nmap.argtypes = [s, s, s, s, i, i, s, d, i, i]
@@ -293,5 +295,5 @@ def ref_driver(name: str) -> C.CDLL:
             lib.ref_ampdispersion.argtypes = [s, s, s, i, i, i]
         elif name == "calamp":
             lib.ref_calamp.argtypes = [s, s, s, d, i, i, i, i, C.POINTER(C.c_double)]
-        _REF_DRIVER_CACHE[name] = lib
-    return _REF_DRIVER_CACHE[name]
+        _REF_DRIVER_CACHE[key] = lib
+    return _REF_DRIVER_CACHE[key]

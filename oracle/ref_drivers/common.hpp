@@ -9,7 +9,11 @@
 // synchronisation (nmap.cpp:464-468) -- the result would not be reproducible.  These builds therefore compile WITHOUT
 // OpenMP (the pragmas are ignored: one thread, the race-free reading of the loop) and provide the three helpers the
 // drivers take from that header.
+//
+// -DFRINGE_REF_OPENMP (the *_omp.so builds, used only to TIME the reference's drivers on all host cores in bench.py's
+// reference arm): nothing is replaced, the drivers are compiled with -fopenmp exactly as the reference builds them.
 #pragma once
+#ifndef FRINGE_REF_OPENMP
 #define FRINGE_COMMON_H
 #include <sys/time.h>
 
@@ -23,3 +27,4 @@ inline double getWallTime() {
 }
 inline int numberOfThreads() { return 1; }
 inline int omp_get_thread_num() { return 0; }
+#endif  // FRINGE_REF_OPENMP
