@@ -36,3 +36,20 @@ def test_integrate_ps_oracle_equals_numpy():
     want[ps == 1] = ifg[ps == 1]
     assert np.abs(got - want).max() <= 1e-6
     assert got[3, 3] == 1.0 + 0j                                  # angle(0) = 0
+
+
+def test_integrate_ps_oracle_equals_the_reference_scripts_output():
+    """tests/golden/integrate_ps_24x40.npz holds what the reference's own python/integratePS.py (integratePS2DS,
+    getCoherence) produced for these inputs (tests/golden/make_golden_integrate_ps.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "integrate_ps_24x40.npz"))
+    o = oracle.load()
+    for j in (1, 2, 3):
+        got = o.integrate_ps(g["ds"][0], g["ds"][j], g["slc"][0], g["slc"][j], g["ps"])
+        want = g[f"ifg_0_{j}"]
+        assert np.abs(got - want).max() <= 1e-6
+        # (numpy's complex64 multiply is SIMD code that may contract into FMAs: its last bit is the machine's, so the
+        # DS pixels are compared to an ulp, not bit for bit)
+        assert np.abs(got - want)[g["ps"] != 1].max() <= 1.5e-7
+    assert got[7, 9].real == -1.0                                # product on the negative real axis: angle = pi
+    assert np.array_equal(np.where(g["ps"] == 1, np.float32(0.95), g["tcorr"]), g["coherence"])

@@ -73,3 +73,14 @@ def test_integrate_ps_against_oracle_and_cli(tmp_path, ctx, oracle_lib):
         assert np.abs(ifg - oracle_lib.integrate_ps(ds[0], ds[j], slc[0], slc[j], ps)).max() <= 1e-6
     cor = stackio.read_envi(os.path.join(out, "tcorr_ds_ps.bin"))
     assert np.array_equal(cor, np.where(ps == 1, np.float32(0.95), tcorr))
+
+
+def test_integrate_ps_against_the_reference_scripts_output(ctx):
+    """The kernel against the vectors the reference's own integratePS.py produced (tests/golden/make_golden_integrate_ps.py)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "integrate_ps_24x40.npz"))
+    for j in (1, 2, 3):
+        got = ctx.integrate_ps(g["ds"][0], g["ds"][j], g["slc"][0], g["slc"][j], g["ps"])
+        want = g[f"ifg_0_{j}"]
+        assert np.abs(got - want).max() <= 1e-6
+        assert np.abs(got - want)[g["ps"] != 1].max() <= 1.5e-7          # an ulp: see tests/test_calamp_ps_cpu.py
+    assert np.array_equal(ctx.ps_coherence(g["tcorr"], g["ps"]), g["coherence"])
