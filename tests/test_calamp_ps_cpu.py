@@ -51,5 +51,6 @@ def test_integrate_ps_oracle_equals_the_reference_scripts_output():
         # (numpy's complex64 multiply is SIMD code that may contract into FMAs: its last bit is the machine's, so the
         # DS pixels are compared to an ulp, not bit for bit)
         assert np.abs(got - want)[g["ps"] != 1].max() <= 1.5e-7
-    assert got[7, 9].real == -1.0                                # product on the negative real axis: angle = pi
+    got = o.integrate_ps(g["ds"][0], g["ds"][2], g["slc"][0], g["slc"][2], g["ps"])
+    assert got[7, 9].real == -1.0 and g["ifg_0_2"][7, 9].real == -1.0        # product on the negative real axis: angle = pi
     assert np.array_equal(np.where(g["ps"] == 1, np.float32(0.95), g["tcorr"]), g["coherence"])
