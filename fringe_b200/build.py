@@ -23,7 +23,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--use_fast_math=false", "-Xcompiler", "-fPIC",
               "-ccbin", HOST_CXX] + ARCH
 
-CUDA_SOURCES = ["capi.cu", "nmap_kernels.cu", "evd_kernels.cu", "evd_mma.cu", "mle_kernels.cu", "post_kernels.cu"]
+CUDA_SOURCES = ["capi.cu", "nmap_kernels.cu", "evd_kernels.cu", "evd_mma.cu", "evd_cta.cu", "mle_kernels.cu", "post_kernels.cu"]
 CUDA_LIB = os.path.join(LIBDIR, "libfringe_b200.so")
 # profiling microbenchmarks: their own library (include/fringe_b200_prof.h), not part of the drop-in one
 PROF_SOURCES = ["microbench.cu"]

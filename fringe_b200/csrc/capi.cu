@@ -39,7 +39,7 @@ struct fringe_ctx {
     int64_t launches = 0;
     int prof_generic = 0;                 // fringe_prof_force_generic: A/B comparisons only (bit 0; bits 8.. launch-shape overrides)
     // workspaces reused across blocks
-    DevBuf amp, valid, zpix, zscale, adtab, alpha, stats, scratch;
+    DevBuf amp, valid, zpix, zscale, adtab, alpha, stats, scratch, worklist;
     DevBuf in_slc, in_mask, in_wts, o_count, o_wts, o_out, o_tcorr, o_comp;
     DevBuf seq_stack[2], seq_comp, seq_mini, seq_datum;     // fringe_sequential_block
     // cached AD2 table key
@@ -225,7 +225,7 @@ int fringe_destroy(fringe_ctx* c) {
     if (!c) return FRINGE_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf* all[] = {&c->amp, &c->valid, &c->zpix, &c->zscale, &c->adtab, &c->alpha, &c->stats, &c->scratch, &c->in_slc, &c->in_mask,
+    DevBuf* all[] = {&c->amp, &c->valid, &c->zpix, &c->zscale, &c->adtab, &c->alpha, &c->stats, &c->scratch, &c->worklist, &c->in_slc, &c->in_mask,
                      &c->in_wts, &c->o_count, &c->o_wts, &c->o_out, &c->o_tcorr, &c->o_comp, &c->seq_stack[0], &c->seq_stack[1],
                      &c->seq_comp, &c->seq_mini, &c->seq_datum};
     for (DevBuf* b : all) b->release();
@@ -618,6 +618,10 @@ int evd_launch_rows(fringe_ctx* ctx, const EvdPlan& plan, const float* slc, cons
             const bool dp = (method == FRINGE_EVD_MLE) || (variant == FRINGE_VARIANT_PHASE_LINK);
             CU(ctx->scratch.ensure((size_t)gg * gw * fringe::evd_generic_workspace_bytes(bands, dp)));
             a.scratch = (unsigned char*)ctx->scratch.p;
+        }
+        if (fringe::evd_cta_order(bands, Nx, Ny, method, variant) > 0) {     // CTA-per-pixel kernel: counters + deferred pixels
+            CU(ctx->worklist.ensure((2 + (size_t)std::max(n_lines, 1) * cols) * sizeof(int)));
+            a.worklist = (int*)ctx->worklist.p;
         }
     }
     int nl = 0;

@@ -62,6 +62,8 @@ struct EvdArgs {
     unsigned char* scratch;      // generic kernel, large bands: per-warp workspaces in global memory (else NULL)
     int tile_pairs;              // set by the launchers of the specialised kernels: columns per CTA segment
     int zblock;                  // 0: zpix is interleaved complex [pix][NP]; -1: the FP16 hi/lo layout of evd_mma.cu
+    int* worklist = nullptr;     // [2 + pixels]: [0] pixel counter of k_evd_cta, [1] number of deferred pixels, [2..] their indices
+    int list_mode = 0;           // k_evd<...>: solve the pixels of the work list instead of the line range
 };
 int evd_max_bands(int method, int variant);
 // launch geometry of the generic kernel; *use_scratch = the per-warp workspace does not fit shared
@@ -83,6 +85,11 @@ cudaError_t launch_evd_mma(const EvdArgs& a, cudaStream_t st);
 // same pixel-major layout as the generic kernel (zblock = 0).  evd_mle_order = 0: not covered.
 int evd_mle_order(int bands);
 cudaError_t launch_evd_mle(const EvdArgs& a, cudaStream_t st);
+// phase_link with 32 < bands <= 104 (evd_cta.cu): one CTA per pixel, coherence matrix on chip; pixels whose |C| is
+// positive definite (or whose iteration stalls) are appended to EvdArgs::worklist for k_evd<...> in list mode.
+// evd_cta_order = 0: not covered (other variants / sizes, or the window's SHP list does not fit shared memory)
+int evd_cta_order(int bands, int Nx, int Ny, int method, int variant);
+cudaError_t launch_evd_cta(const EvdArgs& a, cudaStream_t st);
 
 // out[i] = a[i] * b[i] (complex64, double arithmetic inside), n pixels; 16-byte aligned pointers
 cudaError_t launch_cmul(const float2* a, const float2* b, float2* out, long n, cudaStream_t st);

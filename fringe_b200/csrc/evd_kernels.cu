@@ -639,7 +639,9 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
     const bool isstbas = (a.method == 2), ismle = (a.method == 1);
     const int BW = a.bandwidth;
 
-    const long total = (long)a.n_lines * a.cols;
+    // list mode: the pixels k_evd_cta left over (evd_cta.cu), their number known on the device only
+    const int* plist = a.list_mode ? a.worklist + 2 : nullptr;
+    const long total = a.list_mode ? (long)a.worklist[1] : (long)a.n_lines * a.cols;
     const long chunk = (total + gridDim.x - 1) / gridDim.x;
     const long beg = (long)blockIdx.x * chunk;
     const long end = min(total, beg + chunk);
@@ -647,7 +649,7 @@ __global__ void __launch_bounds__(256) k_evd(const EvdArgs a) {
     GPH_DECL
 
     for (long i = beg + warp; i < end; i += WARPS) {
-        const long p = (long)a.first_line * a.cols + i;
+        const long p = plist ? (long)plist[i] : (long)a.first_line * a.cols + i;
         const int ci = (int)(p / a.cols), cj = (int)(p - (long)ci * a.cols);
         // lane w keeps mask word (32 * round + w); windows of more than 1024 pixels take several rounds
         uint32_t myword = (lane < a.nulong) ? __ldg(&a.wts[p * a.nulong + lane]) : 0u;
@@ -1040,6 +1042,15 @@ cudaError_t launch_evd(const EvdArgs& a, cudaStream_t st, int* n_launches) {
     if (n_launches) *n_launches = 1;
     if (!(a.force_generic & 1) && a.zblock < 0) return launch_evd_mma(a, st);
     if (!(a.force_generic & 1) && dp && a.zblock == 0 && evd_mle_order(a.bands) > 0) return launch_evd_mle(a, st);
+    if (!(a.force_generic & 1) && dp && a.zblock == 0 && a.worklist &&
+        evd_cta_order(a.bands, a.Nx, a.Ny, a.method, a.variant) > 0) {
+        cudaError_t e = launch_evd_cta(a, st);                  // CTA per pixel; what it defers ...
+        if (e != cudaSuccess) return e;
+        EvdArgs b = a;
+        b.list_mode = 1;                                        // ... the warp-per-pixel kernel solves from the list
+        if (n_launches) *n_launches = 2;
+        return launch_evd_dp<true>(b, st);
+    }
     return dp ? launch_evd_dp<true>(a, st) : launch_evd_dp<false>(a, st);
 }
 
