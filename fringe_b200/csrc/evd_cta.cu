@@ -25,6 +25,8 @@
 // samples come from L2).
 #include <math_constants.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace fringe {
@@ -33,7 +35,7 @@ namespace {
 #define FULLM 0xffffffffu
 
 // profiling build only (-DFRINGE_PHASE_CLOCKS): cycles of thread 0 per phase into stats[8..15] -- [0] pixel draw + SHP list,
-// [1] staging loads, [2] covariance, [3] coherence + |C|, [4] LDL^T test, [5] strip load + power iteration, [6] epilogue
+// [1] staging loads, [2] covariance, [3] coherence + |C|, [4] LDL^T test, [5] strip load + power iteration, [6] epilogue, [7] Gram path: B, G and v = B u
 #ifdef FRINGE_PHASE_CLOCKS
 #define CPH_DECL long long cph_t = clock64(); unsigned long long cph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define CPH_MARK(k) { const long long cph_n = clock64(); cph[k] += (unsigned long long)(cph_n - cph_t); cph_t = cph_n; }
@@ -50,7 +52,7 @@ struct CtaLayout {
     int npad;      // staged sample vector, float2 units (multiple of 4)
     int cap;       // SHPs staged at a time
     int nx;        // length of the broadcast vectors (>= 4 * CP)
-    size_t off_a, off_pow, off_dinv, off_xd, off_xo, off_red, off_list, off_misc, bytes;
+    size_t r0_bytes, a_bytes, off_a, off_pow, off_dd, off_dinv, off_xd, off_xo, off_red, off_list, off_misc, bytes;
 };
 
 __host__ __device__ inline CtaLayout cta_layout(int N, int W, int CP) {
@@ -59,64 +61,136 @@ __host__ __device__ inline CtaLayout cta_layout(int N, int W, int CP) {
     if (L.ld < N) L.ld += 8;
     L.npad = (N + 3) & ~3;
     L.nx = 4 * CP;
-    size_t o = (size_t)N * L.ld * sizeof(double2);
-    L.off_a = o;
-    const size_t a_bytes = (size_t)N * (N + 1) / 2 * sizeof(double);
-    int cap = (int)(a_bytes / ((size_t)L.npad * sizeof(float2)));
-    if (cap < 8) cap = 8;
+    // region 0: C (N x ld double2) -- before that the staged samples, which sit at its END (the Gram path builds its
+    // scaled copy of them from the start of the region while they are still needed)
+    L.r0_bytes = (size_t)N * L.ld * sizeof(double2);
+    int cap = (int)(L.r0_bytes / ((size_t)L.npad * sizeof(float2)));
     if (cap > W) cap = W;
     L.cap = cap;
-    const size_t z_bytes = (size_t)cap * L.npad * sizeof(float2);
-    o += ((a_bytes > z_bytes ? a_bytes : z_bytes) + 15) & ~(size_t)15;
+    size_t o = L.r0_bytes;
+    L.off_a = o;
+    L.a_bytes = (((size_t)N * (N + 1) / 2 * sizeof(double)) + 15) & ~(size_t)15;
+    o += L.a_bytes;
     L.off_pow = o;  o += (size_t)L.nx * sizeof(double);
+    L.off_dd = o;   o += (size_t)L.nx * sizeof(double);
     L.off_dinv = o; o += (size_t)L.nx * sizeof(double);
     L.off_xd = o;   o += 2 * (size_t)L.nx * sizeof(double2);
-    L.off_xo = o;   o += 2 * (size_t)L.nx * sizeof(float2);
-    L.off_red = o;  o += 4 * 16 * sizeof(double2);
+    L.off_xo = o;   o += (size_t)L.nx * sizeof(float2);
+    L.off_red = o;  o += 4 * 64 * sizeof(double);
     L.off_list = o; o += ((size_t)W * sizeof(int) + 15) & ~(size_t)15;
     L.off_misc = o; o += 16 * sizeof(int);
     L.bytes = o;
     return L;
 }
 
-// sum over the CTA of two doubles, the same bits in every thread (one barrier; four rotating buffers, so a buffer is
-// written again only three barriers after its last reader)
-__device__ __forceinline__ double2 cta_sum2(double a, double b, double2* red, int& slot, int lane, int warp, int nw) {
+// Sum over the CTA of K doubles that only the first lanes of the four-lane groups carry (lanes 0, 4, 8, ...: zero
+// elsewhere), the same bits in every thread: three shuffle rounds, one barrier, the per-warp partials added as a tree.
+// Four rotating buffers [K][16 warps] (slots of absent warps stay zero), so a buffer is rewritten only three barriers
+// after its last reader.
+template <int K>
+__device__ __forceinline__ void cta_sum_rows(double (&v)[K], double* red, int& slot, int lane, int warp) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        a += __shfl_xor_sync(FULLM, a, o);
-        b += __shfl_xor_sync(FULLM, b, o);
-    }
-    double2* buf = red + (slot & 3) * 16;
+    for (int o = 16; o >= 4; o >>= 1)
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] += __shfl_xor_sync(FULLM, v[k], o);
+    double* buf = red + (slot & 3) * 64;
     ++slot;
-    if (lane == 0) buf[warp] = make_double2(a, b);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) buf[k * 16 + warp] = v[k];
+    }
     __syncthreads();
-    double2 s = make_double2(0.0, 0.0);
-    for (int w = 0; w < nw; ++w) { const double2 v = buf[w]; s.x += v.x; s.y += v.y; }
-    return s;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const double2* q = reinterpret_cast<const double2*>(buf + k * 16);
+        const double2 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4], q5 = q[5], q6 = q[6], q7 = q[7];
+        v[k] = (((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y))) +
+               (((q4.x + q4.y) + (q5.x + q5.y)) + ((q6.x + q6.y) + (q7.x + q7.y)));
+    }
+}
+
+// the same among the first nwg warps only (named barrier 1): the Gram-matrix iteration occupies S rows x 4 lanes
+template <int K>
+__device__ __forceinline__ void grp_sum_rows(double (&v)[K], double* red, int& slot, int lane, int warp, int nwg) {
+#pragma unroll
+    for (int o = 16; o >= 4; o >>= 1)
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] += __shfl_xor_sync(FULLM, v[k], o);
+    double* buf = red + (slot & 3) * 64;
+    ++slot;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) buf[k * 16 + warp] = v[k];
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(nwg * 32) : "memory");
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double t = 0.0;
+        for (int w = 0; w < nwg; ++w) t += buf[k * 16 + w];
+        v[k] = t;
+    }
+}
+
+// 1 / x and 1 / sqrt(x) for positive normal x: the hardware seed (~2^-22) and two Newton steps -- ~50 cycles of latency
+// where the IEEE division / square root sequences take several hundred; the solver's scalars need no last-bit rounding
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x * r, r, 1.0);
+    r = fma(0.5 * r, e, r);
+    e = fma(-x * r, r, 1.0);
+    return fma(0.5 * r, e, r);
+}
+
+// sum_k g[k] * x[4k] for the first NK strip entries, four independent accumulator chains
+template <int NK>
+__device__ __forceinline__ double2 strip_dot(const double2 (&g)[12], const double2* xv) {
+    double yr[2] = {0.0, 0.0}, yi[2] = {0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+        const double2 xj = xv[4 * k];
+        yr[k & 1] = fma(g[k].x, xj.x, yr[k & 1]); yr[k & 1] = fma(-g[k].y, xj.y, yr[k & 1]);
+        yi[k & 1] = fma(g[k].x, xj.y, yi[k & 1]); yi[k & 1] = fma(g[k].y, xj.x, yi[k & 1]);
+    }
+    return make_double2(yr[0] + yr[1], yi[0] + yi[1]);
 }
 
 template <int CP>
-struct CtaCfg { static constexpr int THREADS = 32 * ((16 * CP + 31) / 32); };
+struct CtaCfg {
+    static constexpr int THREADS = 32 * ((16 * CP + 31) / 32);
+    // strip entries held in registers; the rest is read from the shared-memory copy every iteration.  Thirteen warps leave
+    // 128 registers per thread (four warps on one scheduler): 100+ strip registers would spill to local memory, i.e. to L2
+    static constexpr int KR = (THREADS > 384) ? CP - 8 : CP;
+};
+constexpr int KG = 12;          // Gram path: strip entries per thread, i.e. at most 48 SHPs
+
+__device__ __forceinline__ int tri(int r) { return (r * (r + 1)) >> 1; }
 
 template <int CP>
-__global__ void __launch_bounds__(CtaCfg<CP>::THREADS) k_evd_cta(const EvdArgs a) {
-    constexpr int NT = CtaCfg<CP>::THREADS;
+__global__ void __launch_bounds__(CtaCfg<CP>::THREADS, 1) k_evd_cta(const EvdArgs a) {
+    constexpr int NT = CtaCfg<CP>::THREADS, KR = CtaCfg<CP>::KR;
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = NT / 32;
     const int N = a.bands, NP = a.NP;
     const int WX = 2 * a.Nx + 1, W = WX * (2 * a.Ny + 1), center = a.Ny * WX + a.Nx;
     const CtaLayout L = cta_layout(N, W, CP);
     const int ld = L.ld, npad = L.npad;
-    double2* Cd = reinterpret_cast<double2*>(smem);
-    double* A = reinterpret_cast<double*>(smem + L.off_a);          // |C|, packed lower triangle (row r at r(r+1)/2) ...
-    float2* zs = reinterpret_cast<float2*>(smem + L.off_a);         // ... after the staged samples are done with
-    double* rp = reinterpret_cast<double*>(smem + L.off_pow);       // band powers, then their inverse square roots
+    double2* Cd = reinterpret_cast<double2*>(smem);                 // C: upper triangle (and the lower one in the tail columns >= 4 KR)
+    double* A = reinterpret_cast<double*>(smem + L.off_a);          // |C|, packed lower triangle (row r at r(r+1)/2); later the Gram matrix
+    double* rpw = reinterpret_cast<double*>(smem + L.off_pow);      // inverse square roots of the band powers
+    double* rp = reinterpret_cast<double*>(smem + L.off_dd);        // the pivots D of the LDL^T sweep
     double* dinv = reinterpret_cast<double*>(smem + L.off_dinv);
     double2* xd = reinterpret_cast<double2*>(smem + L.off_xd);      // [2][nx]
-    float2* xo = reinterpret_cast<float2*>(smem + L.off_xo);        // [2][nx]
-    double2* red = reinterpret_cast<double2*>(smem + L.off_red);
+    float2* xo = reinterpret_cast<float2*>(smem + L.off_xo);        // [nx]
+    double* red = reinterpret_cast<double*>(smem + L.off_red);
     int* list = reinterpret_cast<int*>(smem + L.off_list);
     volatile int* misc = reinterpret_cast<volatile int*>(smem + L.off_misc);
 
@@ -136,6 +210,7 @@ __global__ void __launch_bounds__(CtaCfg<CP>::THREADS) k_evd_cta(const EvdArgs a
         TI = I; TJ = I + t;
     }
     for (int i = tid; i < 2 * L.nx; i += NT) xd[i] = make_double2(0.0, 0.0);    // the tails beyond N stay zero
+    for (int i = tid; i < 4 * 64; i += NT) red[i] = 0.0;
     int slot = 0;
     unsigned long long st_pix = 0, st_it = 0;
     CPH_DECL
@@ -179,8 +254,31 @@ __global__ void __launch_bounds__(CtaCfg<CP>::THREADS) k_evd_cta(const EvdArgs a
         bool solved = false;
         float2 o = make_float2(0.f, 0.f), cmp = make_float2(0.f, 0.f);
 
+        // Gram path: with fewer SHPs than dates, C = B B^H (B = D^-1/2 Z, N x S) has rank S, and its dominant eigenvector is
+        // B u with u the dominant eigenvector of the S x S Gram matrix G = B^H B -- (N/S)^2 fewer operations per iteration.
+        // Taken when the padded S is at most N / 2 (G fits the |C| buffer; B, the unit phasors of C and the staged samples
+        // fit region 0) and the SHPs were staged in one piece.
+        // staged samples [min(S, cap)][npad], ending with region 0
+        const size_t zs_bytes = (size_t)min(S, L.cap) * npad * sizeof(float2);
+        float2* zs = reinterpret_cast<float2*>(smem + L.r0_bytes - zs_bytes);
+        const int SB = (S + 3) & ~3, SBP = SB + 1;
+        const int ntp = (ntiles + 7) & ~7;
+        const size_t bd_bytes = (size_t)N * SBP * sizeof(double2), e_bytes = (size_t)16 * ntp * sizeof(float2);
+        const size_t h_bytes = (size_t)SB * SBP * sizeof(double2);             // second S x S buffer of the squarings, over the samples
+        const size_t tail_bytes = zs_bytes > h_bytes ? zs_bytes : h_bytes;
+        const bool gpath = (SB <= 4 * KG) && (S <= L.cap) && (h_bytes <= L.a_bytes) &&
+                           (bd_bytes + e_bytes + tail_bytes <= L.r0_bytes);
+        double2* Bd = reinterpret_cast<double2*>(smem);                      // [N][SBP]
+        float2* E = reinterpret_cast<float2*>(smem + bd_bytes);              // [16][ntp]: unit phasors of this thread's tile
+
         if (misc[2] && S >= need) {
+            // the centre pixel's own sample of this row, for the compressed SLC (in flight during everything below)
+            const float2 zc = (rowp && r >= k0) ? __ldg(&a.zpix[pix * NP + r]) : make_float2(0.f, 0.f);
             // ---- covariance (evd.cpp:537-564 / phase_link.cpp:500-527) ------------------------
+            bool pd = true;
+            int zero_band = 0;
+            ++st_pix;
+          do {
             double2 acc[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) acc[e] = make_double2(0.0, 0.0);
@@ -229,205 +327,492 @@ __global__ void __launch_bounds__(CtaCfg<CP>::THREADS) k_evd_cta(const EvdArgs a
             }
             pw += __shfl_xor_sync(FULLM, pw, 1);
             pw += __shfl_xor_sync(FULLM, pw, 2);
-            ++st_pix;
             // a band that is zero in every SHP: NaNs in C, zheevr reports failure, the reference writes -1
-            const int zero_band = __syncthreads_or((r < N) && !(pw > 0.0));      // also: the staged samples are consumed
+            zero_band = __syncthreads_or((r < N) && !(pw > 0.0));      // also: the staged samples are consumed
             CPH_MARK(2)
-            if (zero_band) {
-                tc = -1.f;
-            } else {
-                if (rowp) rp[r] = 1.0 / sqrt(pw);
+            if (zero_band) break;
+            {
+                if (rowp) rpw[r] = 1.0 / sqrt(pw);
                 __syncthreads();
                 // ---- coherence (evd.cpp:569-582) and |C| -------------------------------------
+                // C: the upper triangle only (the solver's strips read the mirror image), except for the tail columns
+                // the strips fetch from here in every iteration
                 if (TI >= 0) {
+                    const bool mirror = (TI >= KR);
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
 #pragma unroll
                         for (int v = 0; v < 4; ++v) {
                             const int ti = 4 * TI + u, tj = 4 * TJ + v;
                             if (ti < tj && tj < N) {
-                                const double sc = rp[ti] * rp[tj];
+                                const double sc = rpw[ti] * rpw[tj];
                                 const double2 c = make_double2(acc[4 * u + v].x * sc, acc[4 * u + v].y * sc);
-                                Cd[ti * ld + tj] = c;
-                                Cd[tj * ld + ti] = make_double2(c.x, -c.y);
-                                A[((tj * (tj + 1)) >> 1) + ti] = sqrt(c.x * c.x + c.y * c.y);
+                                const double m2 = c.x * c.x + c.y * c.y;
+                                A[tri(tj) + ti] = sqrt(m2);
+                                if (gpath) {                       // C itself is only needed as exp(i arg C) (temporal coherence)
+                                    const float cx = (float)c.x, cy = (float)c.y;
+                                    const float f2 = cx * cx + cy * cy;
+                                    float2 e = make_float2(1.f, 0.f);
+                                    if (f2 > 0.f) { const float im = rsqrtf(f2); e = make_float2(cx * im, cy * im); }
+                                    E[(4 * u + v) * ntp + tid] = e;
+                                } else {
+                                    Cd[ti * ld + tj] = c;
+                                    if (mirror) Cd[tj * ld + ti] = make_double2(c.x, -c.y);
+                                }
                             }
                         }
                 }
                 if (tid < N) {
-                    Cd[tid * ld + tid] = make_double2(1.0, 0.0);
-                    A[((tid * (tid + 1)) >> 1) + tid] = 1.0;
+                    if (!gpath) Cd[tid * ld + tid] = make_double2(1.0, 0.0);
+                    A[tri(tid) + tid] = 1.0;
                 }
                 __syncthreads();
                 CPH_MARK(3)
 
-                // ---- is |C| positive definite?  LDL^T, column by column (zpotrf's verdict, phase_link.cpp:556-566)
-                // A[r][k] holds U = L D (undivided) for the finished columns k, dinv[k] = 1 / D_k
-                bool pd = true;
+                // ---- is |C| positive definite?  (zpotrf's verdict, phase_link.cpp:556-566) --------------------
+                // LDL^T in panels of eight columns = the rows of one warp, three barriers per panel: (A) every row
+                // takes the finished columns' contribution off its panel entries, (B) the panel's warp factors the 8x8
+                // diagonal block, (C) the rows below finish their panel columns in registers.  A[r][k] = L[r][k] for
+                // finished columns k, rp[k] = D_k, dinv[k] = 1 / D_k.
+                pd = true;
                 {
-                    const double* Ur = A + ((r * (r + 1)) >> 1);
-                    for (int j = 0; j < N; ++j) {
-                        const double* Uj = A + ((j * (j + 1)) >> 1);
-                        double s = 0.0;
-                        const bool act = (r >= j) && (r < N);
-                        if (act)
-                            for (int k = p; k < j; k += 4) s = fma(Ur[k], Uj[k] * dinv[k], s);
-                        s += __shfl_xor_sync(FULLM, s, 1);
-                        s += __shfl_xor_sync(FULLM, s, 2);
+                    double* Ar = A + tri(r);
+                    for (int j0 = 0; j0 < N; j0 += 8) {
+                        const int jw = min(8, N - j0);
+                        if (j0 > 0 && r >= j0 && r < N) {
+                            const int ca = j0 + p, cb = j0 + p + 4;              // this lane's two panel columns
+                            const bool ha = (ca <= r) && (p < jw), hb = (cb <= r) && (p + 4 < jw);
+                            const double* La = A + tri(min(ca, N - 1));
+                            const double* Lb = A + tri(min(cb, N - 1));
+                            double sa = 0.0, sb = 0.0;
+#pragma unroll 4
+                            for (int k = 0; k < j0; ++k) {
+                                const double t = Ar[k] * rp[k];
+                                sa = fma(t, La[k], sa);
+                                sb = fma(t, Lb[k], sb);
+                            }
+                            if (ha) Ar[ca] -= sa;
+                            if (hb) Ar[cb] -= sb;
+                        }
+                        __syncthreads();
                         bool bad = false;
-                        if (act && p == 0) {
-                            const double v = Ur[j] - s;
-                            A[((r * (r + 1)) >> 1) + j] = v;
-                            if (r == j) { bad = !(v > 0.0); dinv[j] = 1.0 / v; }
+                        if (warp == (j0 >> 3)) {
+                            // the 8x8 diagonal block, factored redundantly by every lane in registers (no exchange, no
+                            // barrier inside); rows / columns beyond N behave like an identity block
+                            double v[8][8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                                for (int j = 0; j <= i; ++j)
+                                    v[i][j] = (i < jw) ? A[tri(j0 + i) + j0 + j] : (i == j ? 1.0 : 0.0);
+                            double dv[8], di[8];
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                dv[c] = v[c][c];
+                                bad = bad || !(dv[c] > 0.0);
+                                di[c] = fast_rcp(dv[c]);
+#pragma unroll
+                                for (int j = c + 1; j < 8; ++j) {
+                                    const double l = v[j][c] * di[c];
+#pragma unroll
+                                    for (int i = j; i < 8; ++i) v[i][j] = fma(-v[i][c], l, v[i][j]);     // V[i][j] -= V[i][c] L[j][c]
+                                }
+#pragma unroll
+                                for (int i = c + 1; i < 8; ++i) v[i][c] *= di[c];                          // column c: V -> L
+                            }
+                            // every lane holds the same values and stores them all (same address, same bits: one wavefront per
+                            // store); a lane-dependent choice of the entry would turn v[][] into a local-memory array
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                                for (int j = 0; j < i; ++j)
+                                    if (i < jw) A[tri(j0 + i) + j0 + j] = v[i][j];
+#pragma unroll
+                            for (int c = 0; c < 8; ++c)
+                                if (c < jw) { rp[j0 + c] = dv[c]; dinv[j0 + c] = di[c]; }
                         }
                         if (__syncthreads_or(bad)) { pd = false; break; }
+                        if (r >= j0 + 8 && r < N && p == 0) {                            // then jw == 8
+                            double u[8];
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) u[c] = Ar[j0 + c];
+#pragma unroll
+                            for (int c = 0; c < 8; ++c)
+#pragma unroll
+                                for (int b = c + 1; b < 8; ++b) u[b] = fma(-u[c], A[tri(j0 + b) + j0 + c], u[b]);
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) Ar[j0 + c] = u[c] * dinv[j0 + c];
+                        }
+                        __syncthreads();
                     }
                 }
-
                 CPH_MARK(4)
+            }
+          } while (false);
+            if (zero_band) {
+                tc = -1.f;
+            } else {
                 bool defer = pd;          // the MLE branch proper: left to the warp-per-pixel kernel
                 if (!pd) {
-                    // ---- dominant eigenpair of C (phase_link.cpp:586-600): FP64 power iteration with momentum ----
-                    double2 c[CP];
-#pragma unroll
-                    for (int k = 0; k < CP; ++k) {
-                        const int j = 4 * k + p;
-                        c[k] = (r < N && j < N) ? Cd[r * ld + j] : make_double2(0.0, 0.0);
-                    }
-                    double2 x = (r < N) ? Cd[r * ld + k0] : make_double2(0.0, 0.0), xp = make_double2(0.0, 0.0);
-                    double2 vfin = make_double2(0.0, 0.0);
-                    bool got = false;
-                    const double nrm = cta_sum2(rowp ? x.x * x.x + x.y * x.y : 0.0, 0.0, red, slot, lane, warp, NW).x;
-                    if (nrm > 0.0) {
-                        double sc = 1.0 / sqrt(nrm);
-                        x.x *= sc; x.y *= sc;
-                        int cur = 0;
-                        if (rowp) xd[r] = x;
+                    // ---- dominant eigenpair of C (phase_link.cpp:586-600) ---------------------------------------
+                    // phase reference, compression, temporal coherence (evd.cpp:738-786) behind either solver; tsum adds
+                    // this thread's share of sum_{i<j} exp(i arg C_ij) conj(o_i) o_j, with the phasors o in xo
+                    auto finish = [&](const double2 vfin, auto&& tsum) {
+                        if (rowp) xd[r] = vfin;
                         __syncthreads();
-                        double lam = 1.0, beta = 0.0, rho_prev = -1.0;
-                        int next_chk = 2;
-                        constexpr int gap = 2;
-                        int it = 0;
-                        for (; it < 400; ++it) {
-                            const double2* xv = xd + cur * L.nx + p;
-                            double yr0 = 0.0, yi0 = 0.0, yr1 = 0.0, yi1 = 0.0;
-#pragma unroll
-                            for (int k = 0; k < CP; ++k) {
-                                const double2 xj = xv[4 * k];
-                                if (k & 1) {
-                                    yr1 = fma(c[k].x, xj.x, yr1); yr1 = fma(-c[k].y, xj.y, yr1);
-                                    yi1 = fma(c[k].x, xj.y, yi1); yi1 = fma(c[k].y, xj.x, yi1);
-                                } else {
-                                    yr0 = fma(c[k].x, xj.x, yr0); yr0 = fma(-c[k].y, xj.y, yr0);
-                                    yi0 = fma(c[k].x, xj.y, yi0); yi0 = fma(c[k].y, xj.x, yi0);
-                                }
-                            }
-                            double2 y = make_double2(yr0 + yr1, yi0 + yi1);
-                            y.x += __shfl_xor_sync(FULLM, y.x, 1); y.y += __shfl_xor_sync(FULLM, y.y, 1);
-                            y.x += __shfl_xor_sync(FULLM, y.x, 2); y.y += __shfl_xor_sync(FULLM, y.y, 2);
-                            if (it == next_chk) {
-                                const double2 s1 = cta_sum2(rowp ? x.x * y.x + x.y * y.y : 0.0,
-                                                            rowp ? x.x * x.x + x.y * x.y : 0.0, red, slot, lane, warp, NW);
-                                const double xx = s1.y;
-                                lam = s1.x / xx;
-                                const double rx = y.x - lam * x.x, ry = y.y - lam * x.y;
-                                const double2 s2 = cta_sum2(rowp ? rx * rx + ry * ry : 0.0,
-                                                            rowp ? y.x * y.x + y.y * y.y : 0.0, red, slot, lane, warp, NW);
-                                const double rho2 = s2.x / (lam * lam * xx);
-                                if (rho2 <= 1.0e-18) {                         // one more plain step, then done
-                                    sc = 1.0 / sqrt(s2.y);
-                                    vfin = make_double2(y.x * sc, y.y * sc);
-                                    got = true;
-                                    ++it;
-                                    break;
-                                }
-                                if (rho_prev > 0.0 && rho2 < rho_prev) {
-                                    if (beta == 0.0) {
-                                        const double rr = sqrt(sqrt(rho2 / rho_prev));       // (rho2 / rho_prev)^(0.5 / gap)
-                                        beta = fmin(0.575 * rr * 0.575 * rr, 0.2);
-                                    }
-                                } else if (rho_prev > 0.0) beta *= 0.5;
-                                rho_prev = rho2;
-                                next_chk = it + gap;
-                                sc = 1.0 / sqrt(xx);
-                                const double il = 1.0 / lam;
-                                const double2 xn = make_double2((y.x * il - beta * xp.x) * sc, (y.y * il - beta * xp.y) * sc);
-                                xp = make_double2(x.x * sc, x.y * sc);
-                                x = xn;
-                            } else if (it < 2) {                               // lambda still unknown: plain normalised steps
-                                const double y2 = cta_sum2(rowp ? y.x * y.x + y.y * y.y : 0.0, 0.0, red, slot, lane, warp, NW).x;
-                                sc = 1.0 / sqrt(y2);
-                                xp = make_double2(0.0, 0.0);
-                                x = make_double2(y.x * sc, y.y * sc);
-                            } else {
-                                const double il = 1.0 / lam;
-                                const double2 xn = make_double2(y.x * il - beta * xp.x, y.y * il - beta * xp.y);
-                                xp = x;
-                                x = xn;
-                            }
-                            cur ^= 1;
-                            if (rowp) xd[cur * L.nx + r] = x;
-                            __syncthreads();
+                        const double2 ref = xd[k0];
+                        const double rn = 1.0 / fmax(sqrt(ref.x * ref.x + ref.y * ref.y), 1e-300);
+                        const double qx = ref.x * rn, qy = ref.y * rn;                 // v * conj(ref / |ref|), then FP32
+                        const float2 vf = make_float2((float)(vfin.x * qx + vfin.y * qy), (float)(vfin.y * qx - vfin.x * qy));
+                        const float2 rf = make_float2((float)(ref.x * qx + ref.y * qy), (float)(ref.y * qx - ref.x * qy));
+                        if (r < N) {
+                            float ux = vf.x * rf.x + vf.y * rf.y;
+                            float uy = vf.y * rf.x - vf.x * rf.y;
+                            const float m = sqrtf(ux * ux + uy * uy);
+                            if (m == 0.f) {                                           // arg(0) = 0 in the reference
+                                const float mr = sqrtf(rf.x * rf.x + rf.y * rf.y);
+                                ux = rf.x / mr; uy = -rf.y / mr;
+                            } else { ux /= m; uy /= m; }
+                            if (r == k0) { ux = 1.f; uy = 0.f; }
+                            o = make_float2(ux, uy);
+                            if (p == 0) xo[r] = o;
                         }
+                        __syncthreads();
+                        float sr = 0.f, si = 0.f;
+                        tsum(sr, si);
+                        sr += __shfl_xor_sync(FULLM, sr, 1); si += __shfl_xor_sync(FULLM, si, 1);
+                        sr += __shfl_xor_sync(FULLM, sr, 2); si += __shfl_xor_sync(FULLM, si, 2);
+                        double s4[4];
+                        s4[0] = rowp ? (double)(zc.x * o.x + zc.y * o.y) : 0.0;        // z * conj(o), rows >= k0 (zc = 0 elsewhere)
+                        s4[1] = rowp ? (double)(zc.y * o.x - zc.x * o.y) : 0.0;
+                        s4[2] = rowp ? (double)sr : 0.0;
+                        s4[3] = rowp ? (double)si : 0.0;
+                        cta_sum_rows<4>(s4, red, slot, lane, warp);
+                        const float invn = 1.0f / (float)(N - a.mini_stack_count + 1);
+                        cmp = make_float2((float)s4[0] * invn, (float)s4[1] * invn);
+                        const float fr = (float)s4[2], fi = (float)s4[3];
+                        tc = sqrtf(fr * fr + fi * fi) / (float)((N * (N - 1)) >> 1);
+                        solved = true;
+                    };
+                    bool got = false;
+                    int it = 0;
+                    if (gpath) {
+                        // ---- (a) B = D^-1/2 Z in double, [date][SHP], rows SBP (odd) apart; SHP columns beyond S are zero ----
+                        for (int idx = tid; idx < SB * npad; idx += NT) {
+                            const int sh = idx / npad, t = idx - sh * npad;
+                            if (t < N) {
+                                double2 bv = make_double2(0.0, 0.0);
+                                if (sh < S) { const float2 z = zs[idx]; const double w = rpw[t]; bv = make_double2((double)z.x * w, (double)z.y * w); }
+                                Bd[t * SBP + sh] = bv;
+                            }
+                        }
+                        __syncthreads();
+                        // ---- (b) G = B^H B, then G^16 by four squarings (G is Hermitian: G^2 = G^H G, the same product).
+                        // dst = src^H src for src [nrows][stride]: 4x4 tiles of the upper triangle, eight lanes per tile each
+                        // taking every eighth row; the eight partial tiles are folded by recursive halving (lane q ends with
+                        // entries 2q, 2q+1).  Every thread of the CTA works here -- throughput work -- where a power iteration
+                        // on G itself is a chain of ~22 latency-bound steps on five warps: on G^16 it takes two or three.
+                        // trace G = N, so G^16 stays below 1e32.
+                        // LP lanes per tile: 8 for the N rows of B, 4 for the squarings (S rows: the folding shuffles, not
+                        // the products, are what a pass costs there)
+                        auto gram = [&](auto lp_tag, const double2* src, const int nrows, const int stride, double2* G) {
+                            constexpr int LP = decltype(lp_tag)::value;
+                            const int nbg = SB >> 2, ntg = nbg * (nbg + 1) / 2, q = lane & (LP - 1);
+                            for (int t0 = 0; t0 < ntg; t0 += NT / LP) {
+                                const int tile = t0 + tid / LP;
+                                const bool act = tile < ntg;
+                                int GI = 0, GJ = 0;
+                                if (act) { int t = tile; while (t >= nbg - GI) { t -= nbg - GI; ++GI; } GJ = GI + t; }
+                                double2 g[16];
+#pragma unroll
+                                for (int e = 0; e < 16; ++e) g[e] = make_double2(0.0, 0.0);
+                                if (act) {
+                                    for (int t = q; t < nrows; t += LP) {
+                                        const double2* bi = src + t * stride + 4 * GI;
+                                        const double2* bj = src + t * stride + 4 * GJ;
+                                        double2 vi[4], vj[4];
+#pragma unroll
+                                        for (int u = 0; u < 4; ++u) { vi[u] = bi[u]; vj[u] = bj[u]; }
+#pragma unroll
+                                        for (int u = 0; u < 4; ++u)
+#pragma unroll
+                                            for (int v = 0; v < 4; ++v) {                        // conj(b_i) b_j
+                                                g[4 * u + v].x = fma(vi[u].x, vj[v].x, g[4 * u + v].x);
+                                                g[4 * u + v].x = fma(vi[u].y, vj[v].y, g[4 * u + v].x);
+                                                g[4 * u + v].y = fma(vi[u].x, vj[v].y, g[4 * u + v].y);
+                                                g[4 * u + v].y = fma(-vi[u].y, vj[v].x, g[4 * u + v].y);
+                                            }
+                                    }
+                                }
+                                // lane q of the tile's LP lanes ends with entries (16 / LP) q ... of the 4x4 tile
+                                constexpr int X1 = LP / 2, X2 = LP / 4;                  // partner distances of the first two rounds
+                                const bool h1 = (q & X1) != 0, h2 = (q & X2) != 0, h3 = (q & 1) != 0;
+                                double2 g8[8], g4[4], g2[2];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    const double2 lo = g[e], hi = g[e + 8];
+                                    const double2 snd = h1 ? lo : hi, kp = h1 ? hi : lo;
+                                    g8[e] = make_double2(kp.x + __shfl_xor_sync(FULLM, snd.x, X1), kp.y + __shfl_xor_sync(FULLM, snd.y, X1));
+                                }
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const double2 lo = g8[e], hi = g8[e + 4];
+                                    const double2 snd = h2 ? lo : hi, kp = h2 ? hi : lo;
+                                    g4[e] = make_double2(kp.x + __shfl_xor_sync(FULLM, snd.x, X2), kp.y + __shfl_xor_sync(FULLM, snd.y, X2));
+                                }
+                                if constexpr (LP == 8) {
+#pragma unroll
+                                    for (int e = 0; e < 2; ++e) {
+                                        const double2 lo = g4[e], hi = g4[e + 2];
+                                        const double2 snd = h3 ? lo : hi, kp = h3 ? hi : lo;
+                                        g2[e] = make_double2(kp.x + __shfl_xor_sync(FULLM, snd.x, 1), kp.y + __shfl_xor_sync(FULLM, snd.y, 1));
+                                    }
+                                }
+                                if (act) {
+                                    constexpr int PER = 16 / LP;
+#pragma unroll
+                                    for (int e = 0; e < PER; ++e) {
+                                        const int id = PER * q + e, row = 4 * GI + (id >> 2), col = 4 * GJ + (id & 3);
+                                        const double2 val = (LP == 8) ? g2[e & 1] : g4[e];
+                                        G[row * SBP + col] = val;
+                                        if (GI != GJ) G[col * SBP + row] = make_double2(val.x, -val.y);
+                                    }
+                                }
+                            }
+                        };
+                        double2* G = reinterpret_cast<double2*>(A);                                  // [SB][SBP] (odd row stride, as B: conflict-free column blocks), the |C| buffer
+                        double2* H = reinterpret_cast<double2*>(smem + L.r0_bytes - tail_bytes);       // the same, over the staged samples
+                        gram(std::integral_constant<int, 8>{}, Bd, N, SBP, G);
+                        __syncthreads();
+                        gram(std::integral_constant<int, 4>{}, G, SB, SBP, H);
+                        __syncthreads();
+                        gram(std::integral_constant<int, 4>{}, H, SB, SBP, G);
+                        __syncthreads();
+                        gram(std::integral_constant<int, 4>{}, G, SB, SBP, H);
+                        __syncthreads();
+                        gram(std::integral_constant<int, 4>{}, H, SB, SBP, G);
+                        __syncthreads();
+                        CPH_MARK(7)
+                        // ---- (c) dominant eigenvector u of G^16: plain power iteration on S rows x 4 lanes, the row strips
+                        // (<= 12 entries) in registers, the first nwg warps only (named barrier), Rayleigh quotient and
+                        // residual in every step.  A residual <= 1e-9 on G^16 bounds the one on G (same eigenvectors,
+                        // 1 - (l_i / l_1)^16 >= 1 - l_i / l_1).
+                        const int nwg = (4 * SB + 31) >> 5;
+                        if (warp < nwg) {
+                            const bool rowg = (r < SB) && (p == 0);
+                            double2 gk[KG];
+#pragma unroll
+                            for (int k = 0; k < KG; ++k)
+                                gk[k] = (r < SB && 4 * k + p < SB) ? G[r * SBP + 4 * k + p] : make_double2(0.0, 0.0);
+                            double2 x = make_double2(0.0, 0.0);
+                            if (r < SB) { const double2 b0 = Bd[k0 * SBP + r]; x = make_double2(b0.x, -b0.y); }    // u0 = B^H e_k0
+                            double s4[4];
+                            s4[0] = rowg ? x.x * x.x + x.y * x.y : 0.0;
+                            grp_sum_rows<1>(reinterpret_cast<double(&)[1]>(s4[0]), red, slot, lane, warp, nwg);
+                            if (s4[0] > 0.0) {
+                                const double sc0 = fast_rsqrt(s4[0]);
+                                x.x *= sc0; x.y *= sc0;
+                                int cur = 0;
+                                if (p == 0 && r >= SB && r < 4 * KG) { xd[r] = make_double2(0.0, 0.0); xd[L.nx + r] = make_double2(0.0, 0.0); }
+                                if (rowg) xd[r] = x;
+                                asm volatile("bar.sync 1, %0;" ::"r"(nwg * 32) : "memory");
+                                double lam = 1.0;
+                                for (; it < 60; ++it) {
+                                    const double2* xv = xd + cur * L.nx + p;
+                                    // straight-line code (a branch per strip entry would serialise the loads): 8 entries, or
+                                    // all 12 -- the strip and the vector are zero beyond SB
+                                    double2 y = (SB <= 32) ? strip_dot<8>(gk, xv) : strip_dot<KG>(gk, xv);
+                                    y.x += __shfl_xor_sync(FULLM, y.x, 1); y.y += __shfl_xor_sync(FULLM, y.y, 1);
+                                    y.x += __shfl_xor_sync(FULLM, y.x, 2); y.y += __shfl_xor_sync(FULLM, y.y, 2);
+                                    // x.y, x.x, y.y and the residual against the previous Rayleigh quotient:
+                                    // |y - lam x|^2 = |y - lam' x|^2 - (lam - lam')^2 x.x
+                                    const double lam_prev = lam;
+                                    const double rx = y.x - lam_prev * x.x, ry = y.y - lam_prev * x.y;
+                                    s4[0] = rowg ? x.x * y.x + x.y * y.y : 0.0;
+                                    s4[1] = rowg ? x.x * x.x + x.y * x.y : 0.0;
+                                    s4[2] = rowg ? y.x * y.x + y.y * y.y : 0.0;
+                                    s4[3] = rowg ? rx * rx + ry * ry : 0.0;
+                                    grp_sum_rows<4>(s4, red, slot, lane, warp, nwg);
+                                    const double xx = s4[1];
+                                    lam = s4[0] * fast_rcp(xx);
+                                    const double dl = lam - lam_prev;
+                                    const double r2 = fmax(s4[3] - dl * dl * xx, 0.0);
+                                    const double sc = fast_rsqrt(s4[2]);
+                                    x = make_double2(y.x * sc, y.y * sc);
+                                    cur ^= 1;
+                                    if (rowg) xd[cur * L.nx + r] = x;
+                                    if (r2 <= 1.0e-18 * lam * lam * xx && fabs(dl) <= 1.0e-3 * lam) { got = true; ++it; break; }
+                                    asm volatile("bar.sync 1, %0;" ::"r"(nwg * 32) : "memory");
+                                }
+                                if (lane == 0 && warp == 0) { misc[3] = got ? 1 : 0; misc[4] = cur; misc[5] = it; misc[6] = slot; }
+                            } else if (lane == 0 && warp == 0) { misc[3] = 0; misc[4] = 0; misc[5] = 0; misc[6] = slot; }
+                        }
+                        __syncthreads();
+                        got = misc[3] != 0;
+                        it = misc[5];
+                        slot = misc[6];                   // the reduction buffers rotate in step in every warp
                         st_it += it;
                         CPH_MARK(5)
                         if (got) {
-                            // ---- phase reference, compression, temporal coherence (evd.cpp:738-786) ----
-                            cur ^= 1;
-                            if (rowp) xd[cur * L.nx + r] = vfin;
-                            __syncthreads();
-                            const double2 ref = xd[cur * L.nx + k0];
-                            const double rn = 1.0 / fmax(hypot(ref.x, ref.y), 1e-300);
-                            const double qx = ref.x * rn, qy = ref.y * rn;                 // v * conj(ref / |ref|), then FP32
-                            const float2 vf = make_float2((float)(vfin.x * qx + vfin.y * qy), (float)(vfin.y * qx - vfin.x * qy));
-                            if (rowp) xo[r] = vf;
-                            __syncthreads();
-                            const float2 rf = xo[k0];
-                            float cr = 0.f, cim = 0.f;
+                            // ---- (d) v = B u, normalised ----
+                            const double2* uv = xd + misc[4] * L.nx + p;
+                            double2 v = make_double2(0.0, 0.0);
                             if (r < N) {
-                                float ux = vf.x * rf.x + vf.y * rf.y;
-                                float uy = vf.y * rf.x - vf.x * rf.y;
-                                const float m = sqrtf(ux * ux + uy * uy);
-                                if (m == 0.f) {                                           // arg(0) = 0 in the reference
-                                    const float mr = sqrtf(rf.x * rf.x + rf.y * rf.y);
-                                    ux = rf.x / mr; uy = -rf.y / mr;
-                                } else { ux /= m; uy /= m; }
-                                if (r == k0) { ux = 1.f; uy = 0.f; }
-                                o = make_float2(ux, uy);
-                                if (p == 0) {
-                                    xo[L.nx + r] = o;
-                                    if (r >= k0) {
-                                        const float2 z = __ldg(&a.zpix[pix * NP + r]);
-                                        cr = z.x * ux + z.y * uy;                         // z * conj(o)
-                                        cim = z.y * ux - z.x * uy;
-                                    }
+                                const double2* br = Bd + r * SBP + p;
+                                for (int k = 0; 4 * k < SB; ++k) {
+                                    const double2 b = br[4 * k], u = uv[4 * k];
+                                    v.x = fma(b.x, u.x, v.x); v.x = fma(-b.y, u.y, v.x);
+                                    v.y = fma(b.x, u.y, v.y); v.y = fma(b.y, u.x, v.y);
                                 }
                             }
-                            const double2 sc2 = cta_sum2((double)cr, (double)cim, red, slot, lane, warp, NW);   // barrier: xo[1] complete
-                            const float invn = 1.0f / (float)(N - a.mini_stack_count + 1);
-                            cmp = make_float2((float)sc2.x * invn, (float)sc2.y * invn);
-                            float sr = 0.f, si = 0.f;
-                            if (r < N) {
-                                const float2* ov = xo + L.nx + p;
+                            v.x += __shfl_xor_sync(FULLM, v.x, 1); v.y += __shfl_xor_sync(FULLM, v.y, 1);
+                            v.x += __shfl_xor_sync(FULLM, v.x, 2); v.y += __shfl_xor_sync(FULLM, v.y, 2);
+                            double n1[1] = {rowp ? v.x * v.x + v.y * v.y : 0.0};
+                            cta_sum_rows<1>(n1, red, slot, lane, warp);        // barrier: every thread is done reading u
+                            const double sc = 1.0 / sqrt(n1[0]);
+                            CPH_MARK(7)
+                            finish(make_double2(v.x * sc, v.y * sc), [&](float& sr, float& si) {
+                                if (TI >= 0) {
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                                        for (int w = 0; w < 4; ++w) {
+                                            const int ti = 4 * TI + u, tj = 4 * TJ + w;
+                                            if (ti < tj && tj < N) {
+                                                const float2 e = E[(4 * u + w) * ntp + tid];
+                                                const float2 oi = xo[ti], oj = xo[tj];
+                                                const float tx = e.x * oi.x + e.y * oi.y, ty = e.y * oi.x - e.x * oi.y;
+                                                sr += tx * oj.x - ty * oj.y;
+                                                si += tx * oj.y + ty * oj.x;
+                                            }
+                                        }
+                                }
+                            });
+                        }
+                    } else {
+                        // ---- power iteration on C itself (more SHPs than half the dates) ----
+                        auto centry = [&](int j) -> double2 {                    // C[r][j] from the stored triangle
+                            if (j >= r) return Cd[r * ld + j];
+                            const double2 m = Cd[j * ld + r];
+                            return make_double2(m.x, -m.y);
+                        };
+                        double2 c[KR];
+#pragma unroll
+                        for (int k = 0; k < KR; ++k) {
+                            const int j = 4 * k + p;
+                            c[k] = (r < N && j < N) ? centry(j) : make_double2(0.0, 0.0);
+                        }
+                        // tail columns: straight from shared memory (both triangles are stored there); rows beyond N read row 0
+                        // and are never used
+                        const double2* ctail = Cd + (r < N ? r : 0) * ld + p;
+                        double2 x = (r < N) ? centry(k0) : make_double2(0.0, 0.0), xp = make_double2(0.0, 0.0);
+                        double2 vfin = make_double2(0.0, 0.0);
+                        double s4[4];
+                        s4[0] = rowp ? x.x * x.x + x.y * x.y : 0.0;
+                        cta_sum_rows<1>(reinterpret_cast<double(&)[1]>(s4[0]), red, slot, lane, warp);
+                        const double nrm = s4[0];
+                        if (nrm > 0.0) {
+                            double sc = 1.0 / sqrt(nrm);
+                            x.x *= sc; x.y *= sc;
+                            int cur = 0;
+                            if (rowp) xd[r] = x;
+                            __syncthreads();
+                            double lam = 1.0, beta = 0.0, rho_prev = -1.0;
+                            int next_chk = 2;
+                            constexpr int gap = 2;
+                            for (; it < 400; ++it) {
+                                const double2* xv = xd + cur * L.nx + p;
+                                double yr[4] = {0.0, 0.0, 0.0, 0.0}, yi[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
                                 for (int k = 0; k < CP; ++k) {
-                                    const int j = 4 * k + p;
-                                    if (j > r && j < N) {
-                                        const float cx = (float)c[k].x, cy = (float)c[k].y;
-                                        const float m = sqrtf(cx * cx + cy * cy);
-                                        float ex = 1.f, ey = 0.f;
-                                        if (m > 0.f) { ex = cx / m; ey = cy / m; }
-                                        const float2 oj = ov[4 * k];
-                                        const float tx = ex * o.x + ey * o.y, ty = ey * o.x - ex * o.y;   // e * conj(o_r) * o_j
-                                        sr += tx * oj.x - ty * oj.y;
-                                        si += tx * oj.y + ty * oj.x;
-                                    }
+                                    const double2 xj = xv[4 * k];
+                                    double2 ck;
+                                    if (k < KR) ck = c[k < KR ? k : 0];
+                                    else ck = (4 * k + p < N) ? ctail[4 * k] : make_double2(0.0, 0.0);
+                                    yr[k & 3] = fma(ck.x, xj.x, yr[k & 3]); yr[k & 3] = fma(-ck.y, xj.y, yr[k & 3]);
+                                    yi[k & 3] = fma(ck.x, xj.y, yi[k & 3]); yi[k & 3] = fma(ck.y, xj.x, yi[k & 3]);
                                 }
+                                double2 y = make_double2((yr[0] + yr[1]) + (yr[2] + yr[3]), (yi[0] + yi[1]) + (yi[2] + yi[3]));
+                                y.x += __shfl_xor_sync(FULLM, y.x, 1); y.y += __shfl_xor_sync(FULLM, y.y, 1);
+                                y.x += __shfl_xor_sync(FULLM, y.x, 2); y.y += __shfl_xor_sync(FULLM, y.y, 2);
+                                if (it == next_chk) {
+                                    // one reduction per test: x.y, x.x, y.y and the residual against the previous Rayleigh
+                                    // quotient; |y - lam x|^2 = |y - lam' x|^2 - (lam - lam')^2 x.x  (the residual of the
+                                    // Rayleigh quotient is orthogonal to x), free of cancellation once lam has settled
+                                    const double lam_prev = lam;
+                                    const double rx = y.x - lam_prev * x.x, ry = y.y - lam_prev * x.y;
+                                    s4[0] = rowp ? x.x * y.x + x.y * y.y : 0.0;
+                                    s4[1] = rowp ? x.x * x.x + x.y * x.y : 0.0;
+                                    s4[2] = rowp ? y.x * y.x + y.y * y.y : 0.0;
+                                    s4[3] = rowp ? rx * rx + ry * ry : 0.0;
+                                    cta_sum_rows<4>(s4, red, slot, lane, warp);
+                                    const double xx = s4[1];
+                                    lam = s4[0] / xx;
+                                    const double dl = lam - lam_prev;
+                                    const double r2 = fmax(s4[3] - dl * dl * xx, 0.0);
+                                    const double rho2 = r2 / (lam * lam * xx);
+                                    if (rho2 <= 1.0e-18 && fabs(dl) <= 1.0e-3 * lam) {     // one more plain step, then done
+                                        sc = 1.0 / sqrt(s4[2]);
+                                        vfin = make_double2(y.x * sc, y.y * sc);
+                                        got = true;
+                                        ++it;
+                                        break;
+                                    }
+                                    if (rho_prev > 0.0 && rho2 < rho_prev) {
+                                        if (beta == 0.0) {
+                                            const double rr = sqrt(sqrt(rho2 / rho_prev));       // (rho2 / rho_prev)^(0.5 / gap)
+                                            beta = fmin(0.575 * rr * 0.575 * rr, 0.2);
+                                        }
+                                    } else if (rho_prev > 0.0) beta *= 0.5;
+                                    rho_prev = rho2;
+                                    next_chk = it + gap;
+                                    sc = 1.0 / sqrt(xx);
+                                    const double il = 1.0 / lam;
+                                    const double2 xn = make_double2((y.x * il - beta * xp.x) * sc, (y.y * il - beta * xp.y) * sc);
+                                    xp = make_double2(x.x * sc, x.y * sc);
+                                    x = xn;
+                                } else if (it < 2) {                               // lambda still unknown: plain normalised steps
+                                    s4[0] = rowp ? y.x * y.x + y.y * y.y : 0.0;
+                                    cta_sum_rows<1>(reinterpret_cast<double(&)[1]>(s4[0]), red, slot, lane, warp);
+                                    sc = 1.0 / sqrt(s4[0]);
+                                    xp = make_double2(0.0, 0.0);
+                                    x = make_double2(y.x * sc, y.y * sc);
+                                } else {
+                                    const double il = 1.0 / lam;
+                                    const double2 xn = make_double2(y.x * il - beta * xp.x, y.y * il - beta * xp.y);
+                                    xp = x;
+                                    x = xn;
+                                }
+                                cur ^= 1;
+                                if (rowp) xd[cur * L.nx + r] = x;
+                                __syncthreads();
                             }
-                            const double2 st = cta_sum2((double)sr, (double)si, red, slot, lane, warp, NW);
-                            const float fr = (float)st.x, fi = (float)st.y;
-                            tc = sqrtf(fr * fr + fi * fi) / (float)((N * (N - 1)) >> 1);
-                            solved = true;
+                            st_it += it;
+                            CPH_MARK(5)
+                            if (got) {
+                                finish(vfin, [&](float& sr, float& si) {
+                                    if (r < N) {
+                                        const float2* ov = xo + p;
+#pragma unroll
+                                        for (int k = 0; k < CP; ++k) {
+                                            const int j = 4 * k + p;
+                                            if (j > r && j < N) {
+                                                double2 ck;
+                                                if (k < KR) ck = c[k < KR ? k : 0];
+                                                else ck = ctail[4 * k];
+                                                const float cx = (float)ck.x, cy = (float)ck.y;
+                                                const float m2 = cx * cx + cy * cy;
+                                                float ex = 1.f, ey = 0.f;
+                                                if (m2 > 0.f) { const float im = rsqrtf(m2); ex = cx * im; ey = cy * im; }
+                                                const float2 oj = ov[4 * k];
+                                                const float tx = ex * o.x + ey * o.y, ty = ey * o.x - ex * o.y;   // e * conj(o_r) * o_j
+                                                sr += tx * oj.x - ty * oj.y;
+                                                si += tx * oj.y + ty * oj.x;
+                                            }
+                                        }
+                                    }
+                                });
+                            }
                         }
                     }
                     if (!got) defer = true;       // not converged: certified inverse iteration of the warp-per-pixel kernel

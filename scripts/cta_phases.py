@@ -11,7 +11,7 @@ from fringe_b200._lib import lib  # noqa: E402
 from fringe_b200.engine import Context  # noqa: E402
 
 bands = int(sys.argv[1]) if len(sys.argv) > 1 else 100
-lines, cols = 200, 2000
+lines, cols = (int(sys.argv[2]) if len(sys.argv) > 2 else 200), 2000
 dev = torch.device("cuda", 0)
 ctx = Context(0)
 slc = synth.make_stack_torch(bands, lines, cols, seed=2, device=dev)
@@ -33,5 +33,5 @@ print(f"bands {bands}: evd ms {min(ts):.2f} for {px} solved pixels = {px / min(t
 cyc = (C.c_int64 * 8)()
 lib.fringe_evd_phase_cycles(ctx._h, cyc)
 if sum(cyc):
-    names = ["draw+list", "staging", "covariance", "coherence+|C|", "LDLt", "iteration", "epilogue", "-"]
+    names = ["draw+list", "staging", "covariance", "coherence+|C|", "LDLt", "iteration", "epilogue", "B+G+v"]
     print("   cycles per solved pixel (thread 0):", {n: round(c / px) for n, c in zip(names, cyc)})
