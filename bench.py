@@ -400,8 +400,11 @@ def main():
         fl = flops_per_launch(BANDS, shp_sum, solved, mle=(cfg["method"] == "MLE"))
         k_ms = float(np.mean(evd_ms))
         kernel = ("k_mle<NT> (exact covariance, PSD gates, inv(|C|), certified inverse iteration, FP64)" if is_dp and BANDS <= 32 else
+                  "k_evd_cta<CP> (phase_link, 32 < bands <= 104: CTA per pixel, exact covariance tiles in registers, LDL^T test of |C|, "
+                  "EVD fall-back on the S x S Gram matrix raised to G^16, FP64) + k_evd<HR,DP> for the pixels it defers"
+                  if is_dp and cfg.get("variant") == 1 and 32 < BANDS <= 104 else
                   "k_evd<HR,DP> (generic any-N kernel, FP64 path)" if is_dp else
-                  "k_evd_mma (masked Gram product on 3xTF32 mma.sync + FP32 dominant eigenvector + phase ref + tcorr + compressed SLC)")
+                  "k_evd_mma (masked Gram product on a two-term FP16 split, mma.sync.m16n8k16 + FP32 dominant eigenvector + phase ref + tcorr + compressed SLC)")
     achieved = fl / (k_ms * 1e-3) * 1e-12
     peak = ctx.fp64_peak_tflops() if is_dp else ctx.fp32_peak_tflops()
     peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
