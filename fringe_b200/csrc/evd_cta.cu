@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(CtaCfg<CP>::THREADS, 1) k_evd_cta(const EvdArg
                                 const double sc = rpw[ti] * rpw[tj];
                                 const double2 c = make_double2(acc[4 * u + v].x * sc, acc[4 * u + v].y * sc);
                                 const double m2 = c.x * c.x + c.y * c.y;
-                                A[tri(tj) + ti] = sqrt(m2);
+                                A[tri(tj) + ti] = (m2 > 0.0) ? m2 * fast_rsqrt(m2) : 0.0;          // |C_ij| to a few ulp
                                 if (gpath) {                       // C itself is only needed as exp(i arg C) (temporal coherence)
                                     const float cx = (float)c.x, cy = (float)c.y;
                                     const float f2 = cx * cx + cy * cy;
@@ -507,12 +507,12 @@ __global__ void __launch_bounds__(CtaCfg<CP>::THREADS, 1) k_evd_cta(const EvdArg
                             }
                         }
                         __syncthreads();
-                        // ---- (b) G = B^H B, then G^16 by four squarings (G is Hermitian: G^2 = G^H G, the same product).
+                        // ---- (b) G = B^H B, then G^4 by two squarings (G is Hermitian: G^2 = G^H G, the same product).
                         // dst = src^H src for src [nrows][stride]: 4x4 tiles of the upper triangle, eight lanes per tile each
                         // taking every eighth row; the eight partial tiles are folded by recursive halving (lane q ends with
                         // entries 2q, 2q+1).  Every thread of the CTA works here -- throughput work -- where a power iteration
-                        // on G itself is a chain of ~22 latency-bound steps on five warps: on G^16 it takes two or three.
-                        // trace G = N, so G^16 stays below 1e32.
+                        // on G itself is a chain of ~22 latency-bound steps on five warps: with G^4 applied four times per step it takes ~5.
+                        // trace G = N, so a unit vector times G^16 stays below 1e32.
                         // LP lanes per tile: 8 for the N rows of B, 4 for the squarings (S rows: the folding shuffles, not
                         // the products, are what a pass costs there)
                         auto gram = [&](auto lp_tag, const double2* src, const int nrows, const int stride, double2* G) {
@@ -584,16 +584,12 @@ __global__ void __launch_bounds__(CtaCfg<CP>::THREADS, 1) k_evd_cta(const EvdArg
                         double2* H = reinterpret_cast<double2*>(smem + L.r0_bytes - tail_bytes);       // the same, over the staged samples
                         gram(std::integral_constant<int, 8>{}, Bd, N, SBP, G);
                         __syncthreads();
-                        gram(std::integral_constant<int, 4>{}, G, SB, SBP, H);
+                        gram(std::integral_constant<int, 4>{}, G, SB, SBP, H);          // G^2
                         __syncthreads();
-                        gram(std::integral_constant<int, 4>{}, H, SB, SBP, G);
-                        __syncthreads();
-                        gram(std::integral_constant<int, 4>{}, G, SB, SBP, H);
-                        __syncthreads();
-                        gram(std::integral_constant<int, 4>{}, H, SB, SBP, G);
+                        gram(std::integral_constant<int, 4>{}, H, SB, SBP, G);          // G^4
                         __syncthreads();
                         CPH_MARK(7)
-                        // ---- (c) dominant eigenvector u of G^16: plain power iteration on S rows x 4 lanes, the row strips
+                        // ---- (c) dominant eigenvector u of G^16 = (G^4)^4: plain power iteration on S rows x 4 lanes, the row strips
                         // (<= 12 entries) in registers, the first nwg warps only (named barrier), Rayleigh quotient and
                         // residual in every step.  A residual <= 1e-9 on G^16 bounds the one on G (same eigenvectors,
                         // 1 - (l_i / l_1)^16 >= 1 - l_i / l_1).
@@ -618,6 +614,20 @@ __global__ void __launch_bounds__(CtaCfg<CP>::THREADS, 1) k_evd_cta(const EvdArg
                                 asm volatile("bar.sync 1, %0;" ::"r"(nwg * 32) : "memory");
                                 double lam = 1.0;
                                 for (; it < 60; ++it) {
+                                    // G^4 applied four times per step (a product is ~10x cheaper than another squaring):
+                                    // three plain applications (unit vector times at most N^12) ...
+#pragma unroll 1
+                                    for (int rep = 0; rep < 3; ++rep) {
+                                        const double2* xw = xd + cur * L.nx + p;
+                                        double2 yw = (SB <= 32) ? strip_dot<8>(gk, xw) : strip_dot<KG>(gk, xw);
+                                        yw.x += __shfl_xor_sync(FULLM, yw.x, 1); yw.y += __shfl_xor_sync(FULLM, yw.y, 1);
+                                        yw.x += __shfl_xor_sync(FULLM, yw.x, 2); yw.y += __shfl_xor_sync(FULLM, yw.y, 2);
+                                        x = yw;
+                                        cur ^= 1;
+                                        if (rowg) xd[cur * L.nx + r] = x;
+                                        asm volatile("bar.sync 1, %0;" ::"r"(nwg * 32) : "memory");
+                                    }
+                                    // ... and the fourth with the Rayleigh quotient and the residual
                                     const double2* xv = xd + cur * L.nx + p;
                                     // straight-line code (a branch per strip entry would serialise the loads): 8 entries, or
                                     // all 12 -- the strip and the vector are zero beyond SB
