@@ -289,9 +289,10 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL_DEBUG=VERSION prints a banner there
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        # keep stdout to the one JSON line: NCCL_DEBUG=VERSION (environment or nccl.conf) prints a banner there
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     BANDS, NX, NY = cfg["bands"], cfg["Nx"], cfg["Ny"]
