@@ -170,6 +170,9 @@ struct CtaCfg {
     // 128 registers per thread (four warps on one scheduler): 100+ strip registers would spill to local memory, i.e. to L2
     static constexpr int KR = (THREADS > 384) ? CP - 8 : CP;
 };
+#ifndef CTA_NSQ
+#define CTA_NSQ 2            // squarings of the Gram matrix before the power iteration
+#endif
 constexpr int KG = 12;          // Gram path: strip entries per thread, i.e. at most 48 SHPs
 
 __device__ __forceinline__ int tri(int r) { return (r * (r + 1)) >> 1; }
@@ -584,10 +587,14 @@ __global__ void __launch_bounds__(CtaCfg<CP>::THREADS, 1) k_evd_cta(const EvdArg
                         double2* H = reinterpret_cast<double2*>(smem + L.r0_bytes - tail_bytes);       // the same, over the staged samples
                         gram(std::integral_constant<int, 8>{}, Bd, N, SBP, G);
                         __syncthreads();
+#if CTA_NSQ >= 1
                         gram(std::integral_constant<int, 4>{}, G, SB, SBP, H);          // G^2
                         __syncthreads();
+#endif
+#if CTA_NSQ >= 2
                         gram(std::integral_constant<int, 4>{}, H, SB, SBP, G);          // G^4
                         __syncthreads();
+#endif
                         CPH_MARK(7)
                         // ---- (c) dominant eigenvector u of G^16 = (G^4)^4: plain power iteration on S rows x 4 lanes, the row strips
                         // (<= 12 entries) in registers, the first nwg warps only (named barrier), Rayleigh quotient and
@@ -599,7 +606,7 @@ __global__ void __launch_bounds__(CtaCfg<CP>::THREADS, 1) k_evd_cta(const EvdArg
                             double2 gk[KG];
 #pragma unroll
                             for (int k = 0; k < KG; ++k)
-                                gk[k] = (r < SB && 4 * k + p < SB) ? G[r * SBP + 4 * k + p] : make_double2(0.0, 0.0);
+                                gk[k] = (r < SB && 4 * k + p < SB) ? ((CTA_NSQ == 1) ? H : G)[r * SBP + 4 * k + p] : make_double2(0.0, 0.0);
                             double2 x = make_double2(0.0, 0.0);
                             if (r < SB) { const double2 b0 = Bd[k0 * SBP + r]; x = make_double2(b0.x, -b0.y); }    // u0 = B^H e_k0
                             double s4[4];
@@ -613,7 +620,7 @@ __global__ void __launch_bounds__(CtaCfg<CP>::THREADS, 1) k_evd_cta(const EvdArg
                                 if (rowg) xd[r] = x;
                                 asm volatile("bar.sync 1, %0;" ::"r"(nwg * 32) : "memory");
                                 double lam = 1.0;
-                                for (; it < 60; ++it) {
+                                for (; it < 150; ++it) {
                                     // G^4 applied four times per step (a product is ~10x cheaper than another squaring):
                                     // three plain applications (unit vector times at most N^12) ...
 #pragma unroll 1
