@@ -169,6 +169,9 @@ struct CtaCfg {
     // strip entries held in registers; the rest is read from the shared-memory copy every iteration.  Thirteen warps leave
     // 128 registers per thread (four warps on one scheduler): 100+ strip registers would spill to local memory, i.e. to L2
     static constexpr int KR = (THREADS > 384) ? CP - 8 : CP;
+    // up to 64 dates two CTAs fit one SM (shared memory and, at 128 registers, the register file): twice the warps to
+    // cover the latency chains of every phase
+    static constexpr int MIN_CTAS = (THREADS <= 256) ? 2 : 1;
 };
 #ifndef CTA_NSQ
 #define CTA_NSQ 2            // squarings of the Gram matrix before the power iteration
@@ -178,7 +181,7 @@ constexpr int KG = 12;          // Gram path: strip entries per thread, i.e. at 
 __device__ __forceinline__ int tri(int r) { return (r * (r + 1)) >> 1; }
 
 template <int CP>
-__global__ void __launch_bounds__(CtaCfg<CP>::THREADS, 1) k_evd_cta(const EvdArgs a) {
+__global__ void __launch_bounds__(CtaCfg<CP>::THREADS, CtaCfg<CP>::MIN_CTAS) k_evd_cta(const EvdArgs a) {
     constexpr int NT = CtaCfg<CP>::THREADS, KR = CtaCfg<CP>::KR;
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
