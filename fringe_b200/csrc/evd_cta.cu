@@ -78,7 +78,7 @@ __host__ __device__ inline CtaLayout cta_layout(int N, int W, int CP) {
     L.off_xo = o;   o += (size_t)L.nx * sizeof(float2);
     L.off_red = o;  o += 4 * 64 * sizeof(double);
     L.off_list = o; o += ((size_t)W * sizeof(int) + 15) & ~(size_t)15;
-    L.off_misc = o; o += 16 * sizeof(int);
+    L.off_misc = o; o += 64 * sizeof(int);          // [0..15] scalars, [16..47] the next pixel's mask words
     L.bytes = o;
     return L;
 }
@@ -221,11 +221,15 @@ __global__ void __launch_bounds__(CtaCfg<CP>::THREADS, CtaCfg<CP>::MIN_CTAS) k_e
     unsigned long long st_pix = 0, st_it = 0;
     CPH_DECL
 
+    // The next pixel is drawn, and its mask words fetched, by the last warp while the others work on the current one
+    // (misc[8] = its index, misc[9] = words present in wpre): three dependent global round trips off the critical path
+    volatile uint32_t* wpre = reinterpret_cast<volatile uint32_t*>(misc + 16);
+    constexpr int NW = NT / 32;
+    if (tid == 0) { misc[8] = atomicAdd(&a.worklist[0], 1); misc[9] = 0; }
     for (;;) {
         __syncthreads();                               // every thread is done with the previous pixel
-        if (tid == 0) misc[0] = atomicAdd(&a.worklist[0], 1);
-        __syncthreads();
-        const long i = misc[0];
+        const long i = misc[8];
+        const bool pre = misc[9] != 0;
         if (i >= total) break;
         const long pix = (long)a.first_line * a.cols + i;
         const int ci = (int)(pix / a.cols), cj = (int)(pix - (long)ci * a.cols);
@@ -238,7 +242,7 @@ __global__ void __launch_bounds__(CtaCfg<CP>::THREADS, CtaCfg<CP>::MIN_CTAS) k_e
                 bool on = false;
                 int q = 0;
                 if (f < W) {
-                    const uint32_t wd = __ldg(&a.wts[pix * a.nulong + (f >> 5)]);
+                    const uint32_t wd = pre ? wpre[f >> 5] : __ldg(&a.wts[pix * a.nulong + (f >> 5)]);
                     const int fy = f / WX;
                     const int yy = ci + fy - a.Ny, xx = cj + (f - fy * WX) - a.Nx;
                     on = ((wd >> (f & 31)) & 1u) && yy >= 0 && yy < a.lines && xx >= 0 && xx < a.cols;
@@ -250,11 +254,22 @@ __global__ void __launch_bounds__(CtaCfg<CP>::THREADS, CtaCfg<CP>::MIN_CTAS) k_e
             }
             if (lane == 0) {
                 misc[1] = base;
-                misc[2] = (int)((__ldg(&a.wts[pix * a.nulong + (center >> 5)]) >> (center & 31)) & 1u);
+                const uint32_t cw = pre ? wpre[center >> 5] : __ldg(&a.wts[pix * a.nulong + (center >> 5)]);
+                misc[2] = (int)((cw >> (center & 31)) & 1u);
             }
         }
         __syncthreads();
         CPH_MARK(0)
+        int nxt_pending = 0;
+        if (warp == NW - 1 && lane == 0) nxt_pending = atomicAdd(&a.worklist[0], 1);      // consumed in publish_next
+        auto publish_next = [&]() {
+            if (warp == NW - 1) {
+                const int nxt = __shfl_sync(FULLM, nxt_pending, 0);
+                const bool have = (nxt < total) && (a.nulong <= 32);
+                if (have && lane < a.nulong) wpre[lane] = __ldg(&a.wts[((long)a.first_line * a.cols + nxt) * a.nulong + lane]);
+                if (lane == 0) { misc[8] = nxt; misc[9] = have ? 1 : 0; }
+            }
+        };
         const int S = misc[1];
         float tc = 0.f;
         bool solved = false;
@@ -292,9 +307,23 @@ __global__ void __launch_bounds__(CtaCfg<CP>::THREADS, CtaCfg<CP>::MIN_CTAS) k_e
             for (int c0 = 0; c0 < S; c0 += L.cap) {
                 const int ns = min(L.cap, S - c0);
                 if (c0 > 0) __syncthreads();
-                for (int idx = tid; idx < ns * npad; idx += NT) {
-                    const int s = idx / npad, t = idx - s * npad;
-                    zs[idx] = (t < N) ? __ldg(&a.zpix[(long)list[c0 + s] * NP + t]) : make_float2(0.f, 0.f);
+                // eight loads in flight per thread before the first store (one round trip per batch, not per element)
+                for (int b0 = 0; b0 < ns * npad; b0 += 8 * NT) {
+                    float2 zv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int idx = b0 + u * NT + tid;
+                        zv[u] = make_float2(0.f, 0.f);
+                        if (idx < ns * npad) {
+                            const int s = idx / npad, t = idx - s * npad;
+                            if (t < N) zv[u] = __ldg(&a.zpix[(long)list[c0 + s] * NP + t]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int idx = b0 + u * NT + tid;
+                        if (idx < ns * npad) zs[idx] = zv[u];
+                    }
                 }
                 __syncthreads();
                 CPH_MARK(1)
@@ -335,10 +364,11 @@ __global__ void __launch_bounds__(CtaCfg<CP>::THREADS, CtaCfg<CP>::MIN_CTAS) k_e
             pw += __shfl_xor_sync(FULLM, pw, 2);
             // a band that is zero in every SHP: NaNs in C, zheevr reports failure, the reference writes -1
             zero_band = __syncthreads_or((r < N) && !(pw > 0.0));      // also: the staged samples are consumed
+            publish_next();
             CPH_MARK(2)
             if (zero_band) break;
             {
-                if (rowp) rpw[r] = 1.0 / sqrt(pw);
+                if (rowp) rpw[r] = fast_rsqrt(pw);
                 __syncthreads();
                 // ---- coherence (evd.cpp:569-582) and |C| -------------------------------------
                 // C: the upper triangle only (the solver's strips read the mirror image), except for the tail columns
@@ -846,6 +876,8 @@ __global__ void __launch_bounds__(CtaCfg<CP>::THREADS, CtaCfg<CP>::MIN_CTAS) k_e
                     continue;
                 }
             }
+        } else {
+            publish_next();
         }
         if (rowp) a.out[(long)r * npix_block + pix] = solved ? o : make_float2(0.f, 0.f);
         if (tid == 0) { a.tcorr[pix] = tc; a.comp[pix] = cmp; }
