@@ -12,17 +12,22 @@
 //     covariance in registers (16 complex double accumulators) and reads 8 samples per SHP for 16 entries; products are
 //     rounded the way libgcc's complex multiply rounds them, summed in double in raster order (evd.cpp:557), as the
 //     reference does -- bit for bit the sums of k_evd<.,true,.>;
-//   * C (FP64, full Hermitian) and |C| (packed lower triangle) go to shared memory; an LDL^T sweep of |C| with one
-//     barrier per column decides positive definiteness.  PD pixels (the MLE branch proper) are appended to a work list
-//     and solved by the warp-per-pixel kernel afterwards -- rare where this kernel is chosen;
-//   * the fallback's dominant eigenpair: FP64 power iteration with the heavy-ball momentum rule of power_iteration_dp
-//     (evd_kernels.cu), four threads per matrix row, **the row strip of each thread in registers** (N = 100: 25 complex
-//     doubles), so an iteration reads only the vector from shared memory: it runs at the FP64 pipe's rate
-//     (4 N^2 DFMA per iteration) instead of the 16 N^2 bytes of shared-memory traffic per iteration a resident matrix costs;
-//     pixels that do not reach a 1e-9 residual within 400 iterations join the work list too;
-//   * phase reference, compressed SLC and temporal coherence from the same registers.
+//   * |C| (packed lower triangle) goes to shared memory; an LDL^T sweep in panels of eight columns (the rows of one warp,
+//     the 8x8 diagonal block factored in registers, three barriers per panel) decides positive definiteness.  PD pixels
+//     (the MLE branch proper) are appended to a work list and solved by the warp-per-pixel kernel afterwards -- rare
+//     where this kernel is chosen;
+//   * the fallback's dominant eigenpair, Gram path (padded S <= N / 2 and <= 48): C = B B^H with B = D^-1/2 Z (N x S), so
+//     the eigenvector is B u with u the dominant eigenvector of G = B^H B (S x S).  G by tiles on all warps, squared
+//     twice (G^4), then a plain power iteration applying G^4 four times per step on S rows x 4 lanes; C itself is never
+//     stored, only the unit phasors exp(i arg C_ij) the temporal coherence needs;
+//   * otherwise (more SHPs): FP64 power iteration on C with the heavy-ball momentum rule of power_iteration_dp
+//     (evd_kernels.cu), four threads per matrix row, most of a thread's row strip in registers; that product is bound by
+//     the bytes the shared-memory crossbar delivers for the vector broadcast, which is why the Gram path exists;
+//   * pixels that do not reach a 1e-9 residual join the work list too;
+//   * phase reference, compressed SLC and temporal coherence behind either solver.
 // Pixels are drawn from a global counter (persistent CTAs; neighbouring CTAs work on neighbouring pixels, so the SHPs'
-// samples come from L2).
+// samples come from L2); the last warp draws the next pixel and fetches its mask words ahead of time.  One CTA per SM at
+// 100 dates (209 kB of shared memory), two up to 64 dates.  DESIGN.md 3.6b has the measurements.
 #include <math_constants.h>
 
 #include <type_traits>
@@ -35,7 +40,8 @@ namespace {
 #define FULLM 0xffffffffu
 
 // profiling build only (-DFRINGE_PHASE_CLOCKS): cycles of thread 0 per phase into stats[8..15] -- [0] pixel draw + SHP list,
-// [1] staging loads, [2] covariance, [3] coherence + |C|, [4] LDL^T test, [5] strip load + power iteration, [6] epilogue, [7] Gram path: B, G and v = B u
+// [1] staging loads, [2] covariance, [3] coherence + |C|, [4] LDL^T test, [5] power iteration (either path), [6] epilogue,
+// [7] Gram path: B, G, its squarings and v = B u
 #ifdef FRINGE_PHASE_CLOCKS
 #define CPH_DECL long long cph_t = clock64(); unsigned long long cph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define CPH_MARK(k) { const long long cph_n = clock64(); cph[k] += (unsigned long long)(cph_n - cph_t); cph_t = cph_n; }
@@ -48,7 +54,7 @@ namespace {
 
 struct CtaLayout {
     int ld;        // row stride of C in double2 units; ld % 8 == 4: the 64-byte pieces four lanes read from two rows of a wavefront
-                   // fall into different halves of the 128 bytes
+                   // fall into different halves of the 128 bytes (path that iterates on C itself)
     int npad;      // staged sample vector, float2 units (multiple of 4)
     int cap;       // SHPs staged at a time
     int nx;        // length of the broadcast vectors (>= 4 * CP)
